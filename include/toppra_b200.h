@@ -1,0 +1,158 @@
+/*
+ * toppra_b200.h — C-ABI of libtoppra_b200.so: batched TOPP-RA (time-optimal path
+ * parameterisation by reachability analysis) on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of hungpham2511/toppra v0.6.2
+ * (paths below are relative to the reference tree):
+ *
+ *   tb_spline_fit        <-> SplineInterpolator.__init__            toppra/interpolator.py:385-421 (scipy CubicSpline)
+ *   tb_ppoly_eval        <-> SplineInterpolator.__call__(s, order)  toppra/interpolator.py:423-430 (scipy PPoly)
+ *   tb_coeff_velacc      <-> JointVelocityConstraint.compute_constraint_params      toppra/constraint/linear_joint_velocity.py:43-53
+ *                            + _create_velocity_constraint                          toppra/_CythonUtils.pyx:16-59
+ *                            + JointAccelerationConstraint.compute_constraint_params toppra/constraint/linear_joint_acceleration.py:63-104
+ *                            + canlinear_colloc_to_interpolate                      toppra/constraint/linear_constraint.py:84-192
+ *                            + seidelWrapper.__init__ row assembly                  toppra/solverwrapper/cy_seidel_solverwrapper.pyx:425-531
+ *   tb_rows_canlinear    <-> the same row assembly for a generic CanonicalLinear constraint
+ *                            (a, b, c, F, g), e.g. SecondOrderConstraint            toppra/constraint/linear_second_order.py:142-173
+ *   tb_scan              <-> ReachabilityAlgorithm.compute_parameterization         toppra/algorithm/reachabilitybased/reachability_algorithm.py:240-376
+ *                            = compute_controllable_sets (:166-238) + forward pass (TOPPRA._forward_step,
+ *                            time_optimal_algorithm.py:55-92), every stage LP solved like
+ *                            seidelWrapper.solve_stagewise_optim (cy_seidel_solverwrapper.pyx:549-697,
+ *                            cy_solve_lp2d :149-390, cy_solve_lp1d :93-144)
+ *   tb_feasible_sets     <-> ReachabilityAlgorithm.compute_feasible_sets            reachability_algorithm.py:131-164
+ *   tb_solve_velacc_host <-> the whole `TOPPRA([vel, acc], SplineInterpolator(ss, wp), gridpoints,
+ *                            solver_wrapper="seidel").compute_parameterization(sd_start, sd_end)` for a batch of
+ *                            paths with HOST buffers (copies included).
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes, no C++/torch types, no exceptions cross the boundary.
+ *   - Every function returns 0 on success, a negative TB_ERR_* for argument errors, or a positive
+ *     cudaError_t value; tb_last_error() returns a thread-local message.
+ *   - Unless a name ends in _host, every pointer is a DEVICE pointer owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()); nothing is allocated or freed inside; `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream); calls are asynchronous.
+ *   - All reals are IEEE fp64; arithmetic order follows the reference so that results are
+ *     bit-identical to its Cython seidelWrapper (kernels are compiled with -fmad=false).
+ *   - "shared" flags: 1 = one array shared by all B paths, 0 = one array per path ([B][...]).
+ *
+ * Stage record layout (one per path and gridpoint, `W` doubles, W even so that W*8 % 16 == 0):
+ *      rec[0      .. R)   a-coefficients of the R static LP rows  (u multiplier)
+ *      rec[R      .. 2R)  b-coefficients                          (x multiplier)
+ *      rec[2R     .. 3R)  c-coefficients
+ *      rec[3R], rec[3R+1] x lower / upper bound (xbound; +-1e8 when absent)
+ *      rec[3R+2 .. W)     padding (R odd only)
+ *   i.e. row r is  a*u + b*x + c <= 0, exactly a_arr/b_arr/c_arr[i, 2+r] of the reference's
+ *   seidelWrapper; rows 0,1 of the reference (the x_next rows it rewrites per call) are synthesised
+ *   inside tb_scan.
+ */
+#ifndef TOPPRA_B200_H_
+#define TOPPRA_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_VERSION 100
+
+/* argument errors */
+#define TB_ERR_ARG (-1)          /* null pointer / non-positive size */
+#define TB_ERR_UNSUPPORTED (-2)  /* size outside the compiled limits (see tb_limits) */
+#define TB_ERR_ALIGN (-3)        /* pointer or record stride not 16-byte aligned */
+
+/* per-path status written by tb_scan; values follow the order of the reference enum
+ * ParameterizationReturnCode (toppra/algorithm/algorithm.py:49-56) */
+#define TB_STATUS_OK 0
+#define TB_STATUS_ERR_UNKNOWN 1          /* NaN in the forward pass (retry budget exhausted) */
+#define TB_STATUS_ERR_SHORT_PATH 2       /* (unused by this path, kept for code parity) */
+#define TB_STATUS_FAIL_UNCONTROLLABLE 3  /* NaN in K, or sd_start^2 outside K[0] +- 1e-5 */
+#define TB_STATUS_ERR_FORWARD_PASS_FAIL 4
+
+/* boundary-condition kinds of tb_spline_fit (scipy CubicSpline bc_type) */
+#define TB_BC_NOT_A_KNOT 0
+#define TB_BC_FIRST_DERIV 1   /* 'clamped' = first derivative 0 */
+#define TB_BC_SECOND_DERIV 2  /* 'natural' = second derivative 0 */
+
+int tb_version(void);
+const char *tb_last_error(void);
+
+/* Compiled limits: max_rows = largest R (static LP rows per stage), max_knots = largest n. */
+int tb_limits(int *max_rows, int *max_knots);
+
+/* Record stride in doubles for R static rows: 3R+2 rounded up to even. */
+int tb_record_doubles(int R);
+
+/* K0 — not-a-knot / clamped / natural cubic spline through wp[B][n][dof] at ss.
+ *   ss: [n] (ss_shared=1) or [B][n]; bc0/bc1: boundary values [B][dof] or NULL (= zeros);
+ *   ppoly out: [B][4][n-1][dof] (scipy PPoly.c layout per path, highest power first). */
+int tb_spline_fit(const double *ss, int ss_shared, const double *wp, int B, int n, int dof, int bc0_kind,
+                  const double *bc0, int bc1_kind, const double *bc1, double *ppoly, void *stream);
+
+/* path(s, order), order in {0,1,2}.  breaks: [nseg+1] or [B][nseg+1]; s: [G] or [B][G];
+ *   out: [B][G][dof]. */
+int tb_ppoly_eval(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                  const double *s, int s_shared, int G, int order, double *out, void *stream);
+
+/* K1 — stage records for JointVelocityConstraint (vlim, may be NULL) + JointAccelerationConstraint (alim).
+ *   vlim/alim: [dof][2] (lim_shared=1) or [B][dof][2], (lower, upper);
+ *   interp: 1 = DiscretizationType.Interpolation (R = 4*dof), 0 = Collocation (R = 2*dof);
+ *   records out: [B][G][W] with the accel rows at row offset `row0` of R_total rows
+ *   (row0=0, R_total=R for vel+acc only; other constraints append with tb_rows_canlinear);
+ *   write_xbound: 0 = leave the xbound slots alone; 1 = overwrite them with the velocity bound intersected
+ *   with [-1e8, 1e8] (the seidelWrapper low/high init, pyx:477-478,517-520), or +-1e8 when vlim==NULL;
+ *   2 = overwrite with the raw xbound of compute_constraint_params (no clipping);
+ *   3 = intersect with what the slots already hold (several velocity constraints). */
+int tb_coeff_velacc(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                    const double *grid, int grid_shared, int G, const double *vlim, const double *alim,
+                    int lim_shared, int interp, double *records, int W, int R_total, int row0, int write_xbound,
+                    void *stream);
+
+/* Row assembly for a generic CanonicalLinear constraint given its collocation parameters:
+ *   a, b, c: [B][G][m];  F: [k][m] (F_mode=0, identical) or [B][G][k][m] (F_mode=1);
+ *   g: [k] / [B][G][k];  F_mode=2: F = [I; -I] (k = 2m) with g: [k] shared (torque-limit form);
+ *   F_mode=3: same with g per path [B][k];
+ *   interp: 1 = lift with canlinear_colloc_to_interpolate (2k rows), 0 = k rows.
+ *   Writes rows [row0, row0 + (interp?2k:k)) of every record. */
+int tb_rows_canlinear(const double *a, const double *b, const double *c, const double *F, const double *g, int F_mode,
+                      int B, int G, int m, int k, const double *grid, int grid_shared, int interp, double *records,
+                      int W, int R_total, int row0, void *stream);
+
+/* Fill the xbound slots of every record with the defaults (-1e8, +1e8) (no velocity constraint). */
+int tb_init_bounds(double *records, int B, int G, int W, int R_total, void *stream);
+
+/* K2 — backward controllable sets + forward parameterisation, one warp per path.
+ *   records: [B][G][W]; grid: [G] or [B][G]; sd_start, sd_end: [B] (NULL = zeros);
+ *   K out: [B][G][2]; sd out: [B][G]; u out: [B][G-1]; status out: [B] (TB_STATUS_*);
+ *   fail_stage out (nullable): [B], stage index where the pass failed, -1 if Ok. */
+int tb_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+            const double *sd_start, const double *sd_end, double *K, double *sd, double *u, int *status,
+            int *fail_stage, void *stream);
+
+/* Feasible sets X[B][G][2] (compute_feasible_sets). */
+int tb_feasible_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                     double *X, void *stream);
+
+/* Extended K2 entry:
+ *   sd_end_hi (nullable): [B] upper terminal velocity, K[N] = [sd_end^2, sd_end_hi^2]
+ *                         (compute_controllable_sets(sdmin, sdmax), reachability_algorithm.py:166-202);
+ *   flags: TB_SCAN_BACKWARD_ONLY = stop after the backward pass (K and status only; sd/u may be NULL);
+ *   counters (nullable): device [B][4] int32 = (2-D LP solves, 1-D LP solves, projected re-solves,
+ *                        forward retries) — instrumentation for profiling. */
+#define TB_SCAN_BACKWARD_ONLY 1
+int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+               const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,
+               double *u, int *status, int *fail_stage, int *counters, void *stream);
+
+/* Whole pipeline with HOST buffers (K0 -> K1 -> K2, H2D/D2H inside, synchronous):
+ *   ss [n] shared; wp [B][n][dof]; grid [G] shared; vlim (nullable) / alim: [dof][2] shared or [B][dof][2];
+ *   outputs (host): K [B][G][2], sd [B][G], u [B][G-1], status [B].  device: CUDA device ordinal. */
+int tb_solve_velacc_host(int device, const double *ss, const double *wp, int B, int n, int dof, const double *grid,
+                         int G, const double *vlim, const double *alim, int lim_shared, int interp,
+                         const double *sd_start, const double *sd_end, double *K, double *sd, double *u,
+                         int *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPPRA_B200_H_ */

@@ -1,0 +1,36 @@
+"""Seeded synthetic TOPP-RA problems shared by tests, bench.py and smoke().
+
+Generation order per path follows the reference example examples/plot_kinematics.py:22-33:
+way_pts = randn(n, dof); vlims = 10 + rand(dof)*20; alims = 10 + rand(dof)*2; ss = linspace(0,1,n)."""
+import numpy as np
+
+
+def make_path(seed, dof=7, nway=5, vel_active=False):
+    rng = np.random.RandomState(seed)
+    way = rng.randn(nway, dof)
+    vl = (0.5 + rng.rand(dof)) if vel_active else (10 + rng.rand(dof) * 20)
+    al = 10 + rng.rand(dof) * 2
+    vlim = np.vstack((-vl, vl)).T
+    alim = np.vstack((-al, al)).T
+    return way, vlim, alim
+
+
+def make_batch(B, seed0=1000, dof=7, nway=5, vel_active=False):
+    """B paths with seeds seed0+b.  Returns ss [n], way [B,n,dof], vlim [B,dof,2], alim [B,dof,2]."""
+    way = np.empty((B, nway, dof))
+    vlim = np.empty((B, dof, 2))
+    alim = np.empty((B, dof, 2))
+    for b in range(B):
+        way[b], vlim[b], alim[b] = make_path(seed0 + b, dof, nway, vel_active)
+    return np.linspace(0, 1, nway), way, vlim, alim
+
+
+def make_batch_fast(B, seed=1234, dof=7, nway=5):
+    """Large batches for the bench: one RandomState for the whole batch (same distributions)."""
+    rng = np.random.RandomState(seed)
+    way = rng.randn(B, nway, dof)
+    vl = 10 + rng.rand(B, dof) * 20
+    al = 10 + rng.rand(B, dof) * 2
+    vlim = np.stack((-vl, vl), axis=-1)
+    alim = np.stack((-al, al), axis=-1)
+    return np.linspace(0, 1, nway), way, vlim, alim

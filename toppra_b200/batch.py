@@ -1,0 +1,160 @@
+"""Batched TOPP-RA: B independent paths per launch.  There is no reference equivalent (the reference solves one
+path per Python object); the per-path semantics are exactly those of
+`TOPPRA(constraints, path, gridpoints, solver_wrapper="seidel").compute_parameterization(sd_start, sd_end)`
+(reference reachability_algorithm.py:240-376), see csrc/tb_scan.cu."""
+import numpy as np
+
+from . import engine
+from .constraint import (ConstraintType, JointAccelerationConstraint, JointVelocityConstraint, RecordContext)
+from .exceptions import BadInputVelocities
+from .interpolator import BatchSplineInterpolator
+
+
+def build_records(ctx, constraints):
+    """Stage records [B, G, W] for a list of CanonicalLinear constraints (= seidelWrapper.__init__,
+    cy_seidel_solverwrapper.pyx:425-531).  Returns (records, R)."""
+    for c in constraints:
+        if c.get_constraint_type() != ConstraintType.CanonicalLinear:
+            raise NotImplementedError("only CanonicalLinear constraints can be turned into LP rows")
+    rows = [c.num_rows(ctx) for c in constraints]
+    R = int(sum(rows))
+    records, _ = engine.alloc_records(ctx.B, ctx.G, R, ctx.device)
+    kinds = [type(c) for c in constraints]
+    if (len(constraints) == 2 and JointVelocityConstraint in kinds and JointAccelerationConstraint in kinds):
+        # headline case: one fused K1 launch writes the velocity bound and the acceleration rows
+        vel = constraints[kinds.index(JointVelocityConstraint)]
+        acc = constraints[kinds.index(JointAccelerationConstraint)]
+        for c in (vel, acc):
+            if ctx.bpath.dof != c.get_dof():
+                raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
+                    c.get_dof(), ctx.bpath.dof))
+        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, vel.device_limits(ctx.device),
+                            acc.device_limits(ctx.device), acc.interpolation, records, R, 0, 1)
+        return records, R
+    engine.init_bounds(records, R)
+    row0 = 0
+    for c, n in zip(constraints, rows):
+        c.append_records(ctx, records, R, row0)
+        row0 += n
+    return records, R
+
+
+class BatchResult(object):
+    """Device-resident result of BatchTOPPRA.compute_parameterization.
+
+    K [B,G,2] controllable sets, sd [B,G] path velocities, sdd [B,G-1] path accelerations (u),
+    status [B] int32 (toppra_b200.algorithm.STATUS_CODES order), fail_stage [B] int32."""
+
+    def __init__(self, out):
+        self.K = out["K"]
+        self.sd = out["sd"]
+        self.sdd = out["u"]
+        self.status = out["status"]
+        self.fail_stage = out["fail_stage"]
+        self.counters = out.get("counters")
+
+    def to_host(self, pinned=None):
+        """Copy to host.  `pinned`: optional dict of preallocated pinned tensors with the same keys."""
+        torch = engine.torch_mod()
+        host = {}
+        for key in ("K", "sd", "sdd", "status", "fail_stage"):
+            t = getattr(self, key)
+            if pinned is not None and key in pinned:
+                pinned[key].copy_(t, non_blocking=True)
+                host[key] = pinned[key]
+            else:
+                host[key] = t.to("cpu", non_blocking=False)
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in host.items()}
+
+
+class BatchTOPPRA(object):
+    """Time-optimal parameterisation of B independent paths on one GPU.
+
+    Parameters
+    ----------
+    constraint_list: list of toppra_b200.constraint objects (limits shared by all paths, or batched
+        (B, dof, 2) limits).
+    path: BatchSplineInterpolator
+    gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
+    """
+
+    def __init__(self, constraint_list, path, gridpoints):
+        if not isinstance(path, BatchSplineInterpolator):
+            raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
+        torch = engine.torch_mod()
+        self.constraints = constraint_list
+        self.path = path
+        self.device = path.device
+        grid_host = None
+        if not isinstance(gridpoints, torch.Tensor):
+            gp = np.ascontiguousarray(gridpoints, dtype=np.float64)
+            if gp.ndim == 1:
+                grid_host = gp
+            if np.any(np.diff(gp, axis=-1) <= 0):
+                raise ValueError("Bad input gridpoints.")
+        self.d_grid = engine.as_device(gridpoints, self.device)
+        if self.d_grid.dim() not in (1, 2) or (self.d_grid.dim() == 2 and self.d_grid.shape[0] != path.B):
+            raise ValueError("gridpoints must have shape (G,) or (B, G)")
+        self.ctx = RecordContext(path, self.d_grid, grid_host, None)
+        self.records = None
+        self.R = None
+
+    @property
+    def B(self):
+        return self.path.B
+
+    @property
+    def G(self):
+        return self.d_grid.shape[-1]
+
+    def setup(self):
+        """K1: constraint coefficients -> stage records (done once; reused by every solve)."""
+        self.records, self.R = build_records(self.ctx, self.constraints)
+        return self.records
+
+    def _vel_tensor(self, v):
+        if v is None:
+            return None
+        torch = engine.torch_mod()
+        if isinstance(v, torch.Tensor):
+            return engine.as_device(v, self.device)
+        arr = np.broadcast_to(np.asarray(v, dtype=np.float64), (self.B,))
+        if np.any(arr < 0):
+            raise BadInputVelocities("Negative path velocities: path velocities must be positive")
+        if not np.any(arr != 0):
+            return None  # kernels treat NULL as zeros
+        return engine.as_device(np.ascontiguousarray(arr), self.device)
+
+    def compute_parameterization(self, sd_start=0.0, sd_end=0.0, counters=False):
+        """Backward + forward pass for all paths (K2).  Returns a BatchResult (device tensors)."""
+        if self.records is None:
+            self.setup()
+        out = engine.scan(self.records, self.R, self.d_grid, self._vel_tensor(sd_start), self._vel_tensor(sd_end),
+                          counters=counters)
+        return BatchResult(out)
+
+    def compute_controllable_sets(self, sdmin, sdmax):
+        """K[B,G,2] with K[N] = [sdmin^2, sdmax^2] (reference reachability_algorithm.py:166-202) and status."""
+        if self.records is None:
+            self.setup()
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmin, dtype=np.float64), (self.B,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmax, dtype=np.float64), (self.B,)))
+        assert np.all(lo <= hi) and np.all(0 <= lo)
+        out = engine.scan(self.records, self.R, self.d_grid, None, engine.as_device(lo, self.device),
+                          engine.as_device(hi, self.device), backward_only=True)
+        return out["K"], out["status"]
+
+    def compute_feasible_sets(self):
+        if self.records is None:
+            self.setup()
+        return engine.feasible_sets(self.records, self.R, self.d_grid)
+
+
+def solve_batch(ss_waypoints, waypoints, gridpoints, vlim, alim, sd_start=0.0, sd_end=0.0,
+                discretization_scheme=1, device=None):
+    """One-call convenience: fit B splines, build vel+acc records, scan.  Inputs numpy or tensors."""
+    path = BatchSplineInterpolator(ss_waypoints, waypoints, device=device)
+    cons = [JointVelocityConstraint(vlim), JointAccelerationConstraint(alim, discretization_scheme)]
+    inst = BatchTOPPRA(cons, path, gridpoints)
+    return inst.compute_parameterization(sd_start, sd_end)

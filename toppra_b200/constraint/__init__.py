@@ -1,0 +1,10 @@
+"""Constraints — same names as the reference `toppra/constraint/__init__.py`."""
+from .constraint import ConstraintType, DiscretizationType, Constraint
+from .linear_constraint import LinearConstraint, canlinear_colloc_to_interpolate, RecordContext
+from .linear_joint_acceleration import JointAccelerationConstraint
+from .linear_joint_velocity import JointVelocityConstraint
+from .linear_second_order import SecondOrderConstraint
+
+__all__ = ["ConstraintType", "DiscretizationType", "Constraint", "LinearConstraint",
+           "canlinear_colloc_to_interpolate", "JointAccelerationConstraint", "JointVelocityConstraint",
+           "SecondOrderConstraint", "RecordContext"]

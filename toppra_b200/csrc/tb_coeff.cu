@@ -1,0 +1,269 @@
+// tb_coeff.cu — K1: constraint coefficients -> stage records, one coalesced pass over batch x gridpoint.
+//
+// Replaces (reference):
+//   path(gridpoints, 1), path(gridpoints, 2)                       toppra/interpolator.py:423-430 (scipy PPoly)
+//   JointVelocityConstraint.compute_constraint_params             toppra/constraint/linear_joint_velocity.py:43-53
+//   _create_velocity_constraint (fp32 accumulators!)              toppra/_CythonUtils.pyx:16-59
+//   JointAccelerationConstraint.compute_constraint_params         toppra/constraint/linear_joint_acceleration.py:63-104
+//   canlinear_colloc_to_interpolate                               toppra/constraint/linear_constraint.py:84-192
+//   seidelWrapper.__init__ row assembly (F.a, F.b, F.c - g)        toppra/solverwrapper/cy_seidel_solverwrapper.pyx:474-520
+//
+// Bound: HBM write bandwidth (3R+2 doubles per path and gridpoint; the PPoly input is 4*nseg*dof doubles
+// per path).  One CTA per (path, chunk of CH gridpoints): q', q'' of the chunk (+1 gridpoint for the
+// interpolation lift) are evaluated once into shared memory, then every thread writes consecutive doubles of
+// the record stream, so the stores are fully coalesced.
+#include "tb_common.cuh"
+
+namespace tb {
+namespace {
+
+constexpr int COEFF_THREADS = 256;
+constexpr int COEFF_CH = 32;  // gridpoints per CTA
+
+__global__ void __launch_bounds__(COEFF_THREADS)
+coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks, const int breaks_shared,
+                    const int nseg, const int dof, const double *__restrict__ grid, const int grid_shared, const int G,
+                    const double *__restrict__ vlim, const double *__restrict__ alim, const int lim_shared,
+                    const int interp, double *__restrict__ records, const int W, const int R_total, const int row0,
+                    const int write_xbound, const int nchunks) {
+  extern __shared__ double sm[];
+  double *qs = sm;                                 // [(CH+1)][dof]
+  double *qss = sm + (COEFF_CH + 1) * dof;         // [(CH+1)][dof]
+  double *sgrid = qss + (COEFF_CH + 1) * dof;      // [CH+1]
+  const long path = blockIdx.x / nchunks;
+  const int chunk = blockIdx.x % nchunks;
+  const int i0 = chunk * COEFF_CH;
+  const int N = G - 1;
+  const int npts = min(COEFF_CH, G - i0);          // gridpoints written by this CTA
+  const int nev = min(COEFF_CH + 1, G - i0);       // gridpoints evaluated (one extra for the lift)
+  const double *c = ppoly + path * 4 * nseg * dof;
+  const double *x = breaks + (breaks_shared ? 0 : path * (nseg + 1));
+  const double *gp = grid + (grid_shared ? 0 : path * G);
+  const int tid = threadIdx.x;
+
+  for (int idx = tid; idx < nev * dof; idx += COEFF_THREADS) {
+    const int ci = idx / dof, k = idx - ci * dof;
+    const double s = gp[i0 + ci];
+    const int seg = find_interval(x, nseg, s);
+    double v1, v2;
+    if (seg < 0) {
+      v1 = v2 = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+      const double ds = s - x[seg];
+      v1 = ppoly_eval1(c, nseg, dof, seg, k, ds, 1);
+      v2 = ppoly_eval1(c, nseg, dof, seg, k, ds, 2);
+    }
+    qs[idx] = v1;
+    qss[idx] = v2;
+  }
+  for (int ci = tid; ci < nev; ci += COEFF_THREADS) sgrid[ci] = gp[i0 + ci];
+  __syncthreads();
+
+  double *rec0 = records + (path * G + i0) * (long)W;
+  const double *al = alim ? alim + (lim_shared ? 0 : path * dof * 2) : nullptr;
+
+  // velocity bound -> xbound slots.  fp32 running min/max exactly like _CythonUtils.pyx:41-58.
+  if (write_xbound && tid < npts) {
+    const int ci = tid;
+    double xlo = VAR_MIN, xhi = VAR_MAX;  // seidelWrapper low_arr/high_arr init, pyx:477-478
+    if (vlim) {
+      const double *vl = vlim + (lim_shared ? 0 : path * dof * 2);
+      float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
+      for (int k = 0; k < dof; ++k) {
+        const double q = qs[ci * dof + k];
+        if (q > 0) {
+          const double hi = vl[k * 2 + 1] / q, lo = vl[k * 2 + 0] / q;
+          sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
+          sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);
+        } else if (q < 0) {
+          const double hi = vl[k * 2 + 0] / q, lo = vl[k * 2 + 1] / q;
+          sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
+          sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);
+        }
+      }
+      const float up = __fmul_rn(sdmax, sdmax);                          // powf(sdmax, 2) in fp32
+      const double lo_d = ((double)sdmin >= 0.0) ? (double)sdmin : 0.0;  // float64_max(sdmin, 0.)
+      xlo = lo_d * lo_d;
+      xhi = (double)up;
+      if (write_xbound != 2) {
+        // pyx:517-520: low = max(VAR_MIN, xbound_lo), high = min(VAR_MAX, xbound_hi)
+        xlo = fmax(VAR_MIN, xlo);
+        xhi = fmin(VAR_MAX, xhi);
+      }
+    }
+    double *rec = rec0 + (long)ci * W;
+    if (write_xbound == 3) {
+      xlo = fmax(rec[3 * R_total], xlo);
+      xhi = fmin(rec[3 * R_total + 1], xhi);
+    }
+    rec[3 * R_total] = xlo;
+    rec[3 * R_total + 1] = xhi;
+    for (int j = 3 * R_total + 2; j < W; ++j) rec[j] = 0.0;
+  }
+
+  // acceleration rows: F = blkdiag([I;-I],[I;-I]), g = [amax;-amin;amax;-amin]  (SURVEY.md §8 a')
+  if (!al) return;  // velocity-only call
+  const int Racc = (interp ? 4 : 2) * dof;
+  const int per_pt = 3 * Racc;
+  for (int o = tid; o < npts * per_pt; o += COEFF_THREADS) {
+    const int ci = o / per_pt;
+    const int rem = o - ci * per_pt;
+    const int kind = rem / Racc;  // 0: a, 1: b, 2: c
+    const int r = rem - kind * Racc;
+    const int blk = r / dof, k = r - blk * dof;
+    const int gi = i0 + ci;
+    double val;
+    if (kind == 2) {
+      val = (blk & 1) ? (0.0 - (-al[k * 2 + 0])) : (0.0 - al[k * 2 + 1]);
+    } else {
+      double base;
+      if (blk < 2) {
+        base = (kind == 0) ? qs[ci * dof + k] : qss[ci * dof + k];
+      } else if (gi < N) {
+        if (kind == 0) {
+          const double delta = sgrid[ci + 1] - sgrid[ci];
+          base = qs[(ci + 1) * dof + k] + (2 * delta) * qss[(ci + 1) * dof + k];  // linear_constraint.py:170
+        } else {
+          base = qss[(ci + 1) * dof + k];
+        }
+      } else {  // last gridpoint duplicates itself, linear_constraint.py:171,175
+        base = (kind == 0) ? qs[ci * dof + k] : qss[ci * dof + k];
+      }
+      val = (blk & 1) ? -base : base;
+    }
+    rec0[(long)ci * W + kind * R_total + row0 + r] = val;
+  }
+}
+
+// Generic CanonicalLinear row assembly (seidelWrapper.__init__ pyx:483-510 +
+// canlinear_colloc_to_interpolate linear_constraint.py:134-192).  One thread per (path, gridpoint, out row).
+__global__ void rows_canlinear_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                      const double *__restrict__ c, const double *__restrict__ F,
+                                      const double *__restrict__ g, const int F_mode, const long B, const int G,
+                                      const int m, const int k, const double *__restrict__ grid,
+                                      const int grid_shared, const int interp, double *__restrict__ records,
+                                      const int W, const int R_total, const int row0) {
+  const int nrows = interp ? 2 * k : k;
+  const long total = B * G * nrows;
+  const int N = G - 1;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % nrows);
+    const long pg = idx / nrows;
+    const int gi = (int)(pg % G);
+    const long p = pg / G;
+    const int second = r >= k;           // second block: constraint at s_{i+1} in stage-i variables
+    const int j = second ? r - k : r;    // row of F
+    const int src = (second && gi < N) ? gi + 1 : gi;  // last stage duplicates itself
+    const double *ap = a + (p * G + src) * m, *bp = b + (p * G + src) * m, *cp = c + (p * G + src) * m;
+    double two_delta = 0.0;
+    const bool lift = second && gi < N;
+    if (lift) {
+      const double *gp = grid + (grid_shared ? 0 : p * G);
+      two_delta = 2 * (gp[gi + 1] - gp[gi]);
+    }
+    double ta = 0.0, tb_ = 0.0, tc = 0.0, gv;
+    if (F_mode >= 2) {  // F = [I; -I]
+      const int col = (j < m) ? j : j - m;
+      const double sgn = (j < m) ? 1.0 : -1.0;
+      const double av = lift ? ap[col] + two_delta * bp[col] : ap[col];
+      ta = sgn * av;
+      tb_ = sgn * bp[col];
+      tc = sgn * cp[col];
+      gv = (F_mode == 3) ? g[p * k + j] : g[j];
+    } else {
+      const double *Fr = (F_mode == 0) ? F + (long)j * m : F + ((p * G + src) * k + j) * (long)m;
+      for (int q = 0; q < m; ++q) {
+        const double av = lift ? ap[q] + two_delta * bp[q] : ap[q];
+        ta = ta + Fr[q] * av;
+        tb_ = tb_ + Fr[q] * bp[q];
+        tc = tc + Fr[q] * cp[q];
+      }
+      gv = (F_mode == 0) ? g[j] : g[(p * G + src) * k + j];
+    }
+    double *rec = records + (p * G + gi) * (long)W;
+    rec[row0 + r] = ta;
+    rec[R_total + row0 + r] = tb_;
+    rec[2 * R_total + row0 + r] = tc - gv;
+  }
+}
+
+// Fill the xbound slots (and padding) with the defaults +-1e8 when no constraint supplies them.
+__global__ void init_bounds_kernel(double *__restrict__ records, const long BG, const int W, const int R_total) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < BG; idx += (long)gridDim.x * blockDim.x) {
+    double *rec = records + idx * W;
+    rec[3 * R_total] = VAR_MIN;
+    rec[3 * R_total + 1] = VAR_MAX;
+    for (int j = 3 * R_total + 2; j < W; ++j) rec[j] = 0.0;
+  }
+}
+
+}  // namespace
+}  // namespace tb
+
+extern "C" int tb_record_doubles(int R) {
+  if (R < 0) return TB_ERR_ARG;
+  const int w = 3 * R + 2;
+  return (w + 1) & ~1;
+}
+
+extern "C" int tb_coeff_velacc(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                               const double *grid, int grid_shared, int G, const double *vlim, const double *alim,
+                               int lim_shared, int interp, double *records, int W, int R_total, int row0,
+                               int write_xbound, void *stream) {
+  using namespace tb;
+  if (!ppoly || !breaks || !grid || (!alim && !vlim) || !records || B <= 0 || nseg <= 0 || dof <= 0 || G <= 0) {
+    set_error("tb_coeff_velacc: bad argument");
+    return TB_ERR_ARG;
+  }
+  const int Racc = alim ? (interp ? 4 : 2) * dof : 0;
+  if (row0 < 0 || row0 + Racc > R_total || W < 3 * R_total + 2) {
+    set_error("tb_coeff_velacc: rows [%d,%d) do not fit R_total=%d / W=%d", row0, row0 + Racc, R_total, W);
+    return TB_ERR_ARG;
+  }
+  if (R_total > MAX_ROWS) { set_error("tb_coeff_velacc: R=%d > %d", R_total, MAX_ROWS); return TB_ERR_UNSUPPORTED; }
+  const int nchunks = (G + COEFF_CH - 1) / COEFF_CH;
+  const long blocks = (long)B * nchunks;
+  if (blocks > 0x7fffffffL) { set_error("tb_coeff_velacc: batch too large for one launch"); return TB_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)((COEFF_CH + 1) * dof * 2 + COEFF_CH + 1) * sizeof(double);
+  if (smem > 48 * 1024) { set_error("tb_coeff_velacc: dof=%d too large", dof); return TB_ERR_UNSUPPORTED; }
+  coeff_velacc_kernel<<<(unsigned)blocks, COEFF_THREADS, smem, (cudaStream_t)stream>>>(
+      ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, vlim, alim, lim_shared, interp, records, W,
+      R_total, row0, write_xbound, nchunks);
+  return check_launch("tb_coeff_velacc");
+}
+
+extern "C" int tb_rows_canlinear(const double *a, const double *b, const double *c, const double *F, const double *g,
+                                 int F_mode, int B, int G, int m, int k, const double *grid, int grid_shared,
+                                 int interp, double *records, int W, int R_total, int row0, void *stream) {
+  using namespace tb;
+  if (!a || !b || !c || !g || !records || !grid || B <= 0 || G <= 0 || m <= 0 || k <= 0 || F_mode < 0 || F_mode > 3) {
+    set_error("tb_rows_canlinear: bad argument");
+    return TB_ERR_ARG;
+  }
+  if (F_mode < 2 && !F) { set_error("tb_rows_canlinear: F is null"); return TB_ERR_ARG; }
+  if (F_mode >= 2 && k != 2 * m) { set_error("tb_rows_canlinear: F=[I;-I] needs k == 2m"); return TB_ERR_ARG; }
+  const int nrows = interp ? 2 * k : k;
+  if (row0 < 0 || row0 + nrows > R_total || W < 3 * R_total + 2) {
+    set_error("tb_rows_canlinear: rows [%d,%d) do not fit R_total=%d / W=%d", row0, row0 + nrows, R_total, W);
+    return TB_ERR_ARG;
+  }
+  const long total = (long)B * G * nrows;
+  const int threads = 256;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  rows_canlinear_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(a, b, c, F, g, F_mode, B, G, m, k, grid,
+                                                                               grid_shared, interp, records, W,
+                                                                               R_total, row0);
+  return check_launch("tb_rows_canlinear");
+}
+
+extern "C" int tb_init_bounds(double *records, int B, int G, int W, int R_total, void *stream) {
+  using namespace tb;
+  if (!records || B <= 0 || G <= 0 || W < 3 * R_total + 2) { set_error("tb_init_bounds: bad argument"); return TB_ERR_ARG; }
+  const long BG = (long)B * G;
+  const int threads = 256;
+  long blocks = (BG + threads - 1) / threads;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  init_bounds_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(records, BG, W, R_total);
+  return check_launch("tb_init_bounds");
+}

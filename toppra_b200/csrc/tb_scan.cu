@@ -1,0 +1,539 @@
+// tb_scan.cu — K2: backward controllable sets + forward parameterisation (TOPP-RA), one warp per path.
+//
+// Replaces (reference, hungpham2511/toppra v0.6.2):
+//   ReachabilityAlgorithm.compute_controllable_sets / _one_step   reachability_algorithm.py:166-238
+//   ReachabilityAlgorithm.compute_parameterization                reachability_algorithm.py:240-376
+//   TOPPRA._forward_step                                          time_optimal_algorithm.py:55-92
+//   seidelWrapper.solve_stagewise_optim                           cy_seidel_solverwrapper.pyx:549-697
+//   cy_solve_lp2d / cy_solve_lp1d                                 cy_seidel_solverwrapper.pyx:149-390 / 93-144
+//
+// Design (B200): the stages of one path are strictly sequential (K[i] <- K[i+1], x[i+1] <- x[i]), so the
+// parallelism is (i) across paths: one warp per path, and (ii) across the LP rows of a stage: one row per lane
+// (RPL rows per lane when nC > 32).  Seidel's incremental 2-variable LP keeps its exact row order (including
+// the reference's warm-start permutation) so results are bit-identical to the Cython solver:
+//   * "first violated row in order"      -> per-lane position + redux.sync min
+//   * projection of earlier rows + box   -> one fp64 division per lane
+//   * 1-D LP (min of upper / max of lower limits) -> 5-step shuffle reductions
+// The per-stage record (3R+2 doubles) is streamed HBM -> shared memory with cp.async.bulk (TMA bulk copy,
+// mbarrier complete_tx), double-buffered one stage ahead of the solve.
+// Compiled with -fmad=false: no FMA contraction, same roundings as the x86-64 reference.
+#include <limits.h>
+
+#include "tb_common.cuh"
+
+namespace tb {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  uint32_t ok;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// Position of LP row r in Seidel's processing order, cy_seidel_solverwrapper.pyx:252-264:
+// a valid warm-start pair puts active_c[1] first, active_c[0] second, then the remaining rows ascending.
+__device__ __forceinline__ int row_pos(int r, bool valid, int ac0, int ac1) {
+  if (!valid) return r;
+  if (r == ac1) return 0;
+  if (r == ac0) return 1;
+  return 2 + r - (r > ac0 ? 1 : 0) - (r > ac1 ? 1 : 0);
+}
+__device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
+  if (!valid) return p;
+  if (p == 0) return ac1;
+  if (p == 1) return ac0;
+  const int lo = min(ac0, ac1), hi = max(ac0, ac1);
+  int r = p - 2;
+  if (r >= lo) ++r;
+  if (r >= hi) ++r;
+  return r;
+}
+
+constexpr int BOXBASE = 1 << 20;
+
+// cy_solve_lp2d (pyx:149-390) on one warp.  Lane `lane` holds LP rows r = lane + 32*s, s < RPL
+// (padding rows must be (0, 0, -1)).  maximise v0*u + v1*x  s.t.  a u + b x + c <= 0, low <= (u,x) <= high.
+// ac0/ac1: in = warm-start pair (active_c of the previous solve of this slot), out = new active pair
+// (updated only when feasible, like pyx:673-676,690-691).  Returns false when infeasible.
+template <int RPL>
+__device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, const double (&a)[RPL],
+                                          const double (&b)[RPL], const double (&c)[RPL], const int nC,
+                                          const double low0, const double high0, const double low1,
+                                          const double high1, int &ac0, int &ac1, double &out_u, double &out_x,
+                                          const int lane, int &n_resolve) {
+  if (low0 > high0 || low1 > high1) return false;  // pyx:233-235
+  double p0 = (v0 > LP_TINY) ? high0 : low0;       // pyx:236-247
+  double p1 = (v1 > LP_TINY) ? high1 : low1;
+  int nac0 = (v0 > LP_TINY) ? -2 : -1;
+  int nac1 = (v1 > LP_TINY) ? -4 : -3;
+  const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;
+  int pos[RPL];
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const int r = lane + 32 * s;
+    pos[s] = (r < nC) ? row_pos(r, valid, ac0, ac1) : INT_MAX;
+  }
+  int kpos = -1;
+  constexpr int IPL = RPL + 1;  // item slots per lane: nC rows + 4 box rows <= 32 * IPL
+  const int nitems = nC + 4;
+  while (true) {
+    // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
+    int mypos = INT_MAX;
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) {
+      const double val = a[s] * p0 + b[s] * p1 + c[s];
+      if (!(val < LP_TINY) && pos[s] > kpos && pos[s] != INT_MAX) mypos = min(mypos, pos[s]);
+    }
+    const int knew = __reduce_min_sync(FULL, mypos);
+    if (knew == INT_MAX) break;
+    kpos = knew;
+    const int krow = pos_row(kpos, valid, ac0, ac1);
+    ++n_resolve;
+    nac0 = krow;
+    // broadcast row k
+    double ak = a[0], bk = b[0], ck = c[0];
+#pragma unroll
+    for (int s = 1; s < RPL; ++s)
+      if ((krow >> 5) == s) { ak = a[s]; bk = b[s]; ck = c[s]; }
+    ak = __shfl_sync(FULL, ak, krow & 31);
+    bk = __shfl_sync(FULL, bk, krow & 31);
+    ck = __shfl_sync(FULL, ck, krow & 31);
+    // project the origin onto line k, pyx:290-295
+    const double nrm = ak * ak + bk * bk;
+    const double z0 = (-ak * ck) / nrm;
+    const double z1 = (-bk * ck) / nrm;
+    const double dt0 = -bk, dt1 = ak;
+    const double v1d = dt0 * v0 + dt1 * v1;
+    // project the earlier rows and the four box rows onto the line, pyx:298-347
+    double tt[IPL];
+    int cls[IPL], key[IPL];
+    bool bad = false;
+#pragma unroll
+    for (int s = 0; s < IPL; ++s) {
+      cls[s] = 0; tt[s] = 0.0; key[s] = INT_MAX;
+      if (32 * s >= nitems) continue;  // warp-uniform
+      const int it = lane + 32 * s;
+      const int sa = (s < RPL) ? s : RPL - 1;
+      double aj, bj, cj;
+      bool part;
+      if (s < RPL && it < nC) {
+        aj = a[sa]; bj = b[sa]; cj = c[sa];
+        part = pos[sa] < kpos;
+        key[s] = pos[sa];
+      } else {
+        const int m = it - nC;  // 0: low0 <= u, 1: u <= high0, 2: low1 <= x, 3: x <= high1
+        part = (m >= 0) && (m < 4);
+        aj = (m == 0) ? -1.0 : ((m == 1) ? 1.0 : 0.0);
+        bj = (m == 2) ? -1.0 : ((m == 3) ? 1.0 : 0.0);
+        cj = (m == 0) ? low0 : ((m == 1) ? -high0 : ((m == 2) ? low1 : -high1));
+        key[s] = BOXBASE + m;
+      }
+      if (part) {
+        const double denom = dt0 * aj + dt1 * bj;
+        const double num = cj + z1 * bj + z0 * aj;
+        if (denom > LP_TINY) {
+          cls[s] = 1; tt[s] = -num / denom;   // t <= tt
+        } else if (denom < -LP_TINY) {
+          cls[s] = 2; tt[s] = -num / denom;   // t >= tt
+        } else if (num > LP_SMALL) {
+          bad = true;                          // parallel and infeasible, pyx:342-344
+        }
+      }
+    }
+    // 1-D LP on the line with bounds +-INF, pyx:350 -> cy_solve_lp1d pyx:93-144
+    double my_hi = LP_INF, my_lo = -LP_INF;
+#pragma unroll
+    for (int s = 0; s < IPL; ++s) {
+      if (cls[s] == 1) my_hi = fmin(my_hi, tt[s]);
+      if (cls[s] == 2) my_lo = fmax(my_lo, tt[s]);
+    }
+    const double cur_max = warp_min(my_hi);
+    const double cur_min = warp_max(my_lo);
+    if (__any_sync(FULL, bad)) return false;
+    if (cur_min > cur_max) return false;
+    const bool pick_min = (fabs(v1d) < LP_TINY) || (v1d < 0);
+    const double tstar = pick_min ? cur_min : cur_max;
+    // optimum on the +-INF sentinel (1-D active index -1/-2) counts as infeasible, pyx:376-383
+    if (pick_min ? !(tstar > -LP_INF) : !(tstar < LP_INF)) return false;
+    const int want = pick_min ? 2 : 1;
+    int mykey = INT_MAX;
+#pragma unroll
+    for (int s = 0; s < IPL; ++s)
+      if (cls[s] == want && tt[s] == tstar) mykey = min(mykey, key[s]);
+    const int akey = __reduce_min_sync(FULL, mykey);
+    nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
+    p0 = z0 + tstar * dt0;  // pyx:362-363
+    p1 = z1 + tstar * dt1;
+  }
+  ac0 = nac0;
+  ac1 = nac1;
+  out_u = p0;
+  out_x = p1;
+  return true;
+}
+
+// cy_solve_lp1d (pyx:93-144) as used by the x_min == x_max branch of solve_stagewise_optim (pyx:631-650):
+// rows a*u + (b*x + c) <= 0 over ALL nC rows, u in [low0, high0]; objective v0*u.  Returns false if infeasible.
+template <int RPL>
+__device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double x, const double (&a)[RPL],
+                                                  const double (&b)[RPL], const double (&c)[RPL],
+                                                  const double low0, const double high0, double &out_u) {
+  double my_hi = high0, my_lo = low0;
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const double bxc = b[s] * x + c[s];
+    if (a[s] > LP_TINY) {
+      my_hi = fmin(my_hi, -bxc / a[s]);
+    } else if (a[s] < -LP_TINY) {
+      my_lo = fmax(my_lo, -bxc / a[s]);
+    }
+  }
+  const double cur_max = warp_min(my_hi);
+  const double cur_min = warp_max(my_lo);
+  if (cur_min > cur_max) return false;
+  out_u = ((fabs(v0) < LP_TINY) || (v0 < 0)) ? cur_min : cur_max;
+  return true;
+}
+
+// Load this lane's rows of one stage record (shared memory) into registers.  LP row r: r = 0,1 are the
+// x_next rows (filled by the caller), r >= 2 is static row r-2; padding rows are (0,0,-1).
+template <int RPL>
+__device__ __forceinline__ void load_rows(const double *rec, const int R, const int nC, const int lane,
+                                          double (&a)[RPL], double (&b)[RPL], double (&c)[RPL]) {
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const int r = lane + 32 * s;
+    if (r >= 2 && r < nC) {
+      a[s] = rec[r - 2];
+      b[s] = rec[R + r - 2];
+      c[s] = rec[2 * R + r - 2];
+    } else {
+      a[s] = 0.0; b[s] = 0.0; c[s] = -1.0;
+    }
+  }
+}
+
+template <int RPL>
+__device__ __forceinline__ void set_xnext_rows(const int lane, const double delta, const double xn_min,
+                                               const double xn_max, double (&a)[RPL], double (&b)[RPL],
+                                               double (&c)[RPL]) {
+  // pyx:604-620: row0 = (-2 delta, -1, x_next_min), row1 = (2 delta, 1, -x_next_max)
+  if (lane == 0) { a[0] = -2 * delta; b[0] = -1.0; c[0] = xn_min; }
+  if (lane == 1) { a[0] = 2 * delta; b[0] = 1.0; c[0] = -xn_max; }
+}
+
+template <int RPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
+            const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
+            const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags,
+            double *__restrict__ Kout, double *__restrict__ sdout, double *__restrict__ uout,
+            int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long path = (long)blockIdx.x * WARPS + warp;
+  if (path >= B) return;
+  double *buf0 = reinterpret_cast<double *>(smem_raw) + (size_t)warp * 2 * W;
+  double *buf1 = buf0 + W;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * 2 * W * sizeof(double)) + warp * 2;
+  const int N = G - 1, nC = R + 2;
+  const unsigned rec_bytes = (unsigned)(W * sizeof(double));
+  const double *rec_path = records + (size_t)path * G * W;
+  const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
+  double *Kp = Kout + (size_t)path * G * 2;
+  const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
+  double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
+  double *up = backward_only ? nullptr : uout + (size_t)path * (G > 1 ? G - 1 : 0);
+
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  unsigned n_issued = 0, n_waited = 0;  // ring of 2 buffers
+  auto issue = [&](int stage) {
+    if (lane == 0) {
+      uint64_t *bar = &bars[n_issued & 1];
+      mbar_expect_tx(bar, rec_bytes);
+      bulk_g2s((n_issued & 1) ? buf1 : buf0, rec_path + (size_t)stage * W, rec_bytes, bar);
+    }
+    ++n_issued;
+  };
+  auto acquire = [&]() -> const double * {
+    mbar_wait(&bars[n_waited & 1], (n_waited >> 1) & 1);
+    const double *p = (n_waited & 1) ? buf1 : buf0;
+    ++n_waited;
+    return p;
+  };
+
+  int n_lp2d = 0, n_lp1d = 0, n_resolve = 0, n_retry = 0;
+  double a[RPL], b[RPL], c[RPL];
+
+  // ---------------- backward pass: controllable sets, reachability_algorithm.py:166-238 ----------------
+  const double sde = sd_end ? sd_end[path] : 0.0;
+  const double sds = sd_start ? sd_start[path] : 0.0;
+  const double sdeh = sd_end_hi ? sd_end_hi[path] : sde;
+  double kn0 = sde * sde, kn1 = sdeh * sdeh;  // K[N] = [sdmin^2, sdmax^2], reachability_algorithm.py:185
+  if (lane == 0) { Kp[2 * N] = kn0; Kp[2 * N + 1] = kn1; }
+  int st = TB_STATUS_OK, fstage = -1;
+  int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0;  // active_c_up / active_c_down, initialised to zeros (pyx:526-527)
+  if (N > 0) issue(N - 1);
+  for (int i = N - 1; i >= 0; --i) {
+    const double *rec = acquire();
+    load_rows<RPL>(rec, R, nC, lane, a, b, c);
+    const double xlo = rec[3 * R], xhi = rec[3 * R + 1];
+    __syncwarp();
+    if (i > 0) issue(i - 1);
+    const double delta = gp[i + 1] - gp[i];
+    set_xnext_rows<RPL>(lane, delta, kn0, kn1, a, b, c);
+    // low/high: pyx:587-601 with x_min = x_max = NaN
+    double uu, xx;
+    // x_upper: g = (1e-9, -1) -> v = (-1e-9, 1), slot active_c_down (g[1] <= 0), reachability_algorithm.py:229-233
+    ++n_lp2d;
+    const bool ok_hi = lp2d_warp<RPL>(-1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
+                                      n_resolve);
+    const double x_upper = ok_hi ? xx : __longlong_as_double(0x7ff8000000000000LL);
+    // x_lower: g = (-1e-9, 1) -> v = (1e-9, -1), slot active_c_up, reachability_algorithm.py:234-236
+    ++n_lp2d;
+    const bool ok_lo = lp2d_warp<RPL>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+                                      n_resolve);
+    double x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
+    if (x_lower < 0) x_lower = 0;  // reachability_algorithm.py:190-191
+    if (lane == 0) { Kp[2 * i] = x_lower; Kp[2 * i + 1] = x_upper; }
+    if (!(ok_hi && ok_lo)) {
+      // reachability_algorithm.py:192-197: stop; the remaining K entries stay 0 (np.zeros)
+      st = TB_STATUS_FAIL_UNCONTROLLABLE;
+      fstage = i;
+      for (int j = lane; j < 2 * i; j += 32) Kp[j] = 0.0;
+      break;
+    }
+    kn0 = x_lower;
+    kn1 = x_upper;
+  }
+  // drain a prefetch that was issued but not consumed (failure path), so the buffers can be reused
+  while (n_waited < n_issued) (void)acquire();
+  __syncwarp();
+
+  const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  const double x_start = sds * sds;
+  if (backward_only) {
+    if (lane == 0) {
+      status[path] = st;
+      if (fail_stage) fail_stage[path] = fstage;
+    }
+    return;
+  }
+  if (st == TB_STATUS_OK) {
+    // kn0,kn1 == K[0]; admissibility check reachability_algorithm.py:290-301
+    if (x_start + ALG_SMALL < kn0 || kn1 + ALG_SMALL < x_start) { st = TB_STATUS_FAIL_UNCONTROLLABLE; fstage = 0; }
+  }
+  if (st != TB_STATUS_OK) {
+    for (int j = lane; j < G; j += 32) sdp[j] = nan_d;
+    for (int j = lane; j < N; j += 32) up[j] = nan_d;
+  } else {
+    // ---------------- forward pass, reachability_algorithm.py:303-364 ----------------
+    double x = x_start;
+    if (lane == 0) sdp[0] = sqrt(x);
+    if (N > 0) issue(0);
+    int i = 0;
+    for (; i < N; ++i) {
+      const double *rec = acquire();
+      load_rows<RPL>(rec, R, nC, lane, a, b, c);
+      __syncwarp();
+      if (i + 1 < N) issue(i + 1);
+      const double delta = gp[i + 1] - gp[i];
+      const double k0 = Kp[2 * (i + 1)], k1 = Kp[2 * (i + 1) + 1];
+      set_xnext_rows<RPL>(lane, delta, k0, k1, a, b, c);
+      int tries = 0;
+      bool ok;
+      double uopt = 0.0;
+      while (true) {
+        // _forward_step: g = (-2 delta, -1), x_min = x_max = x -> 1-D branch, v0 = 2 delta (pyx:628-636)
+        ++n_lp1d;
+        ok = lp1d_fixed_x_warp<RPL>(-(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
+        if (ok || tries >= MAX_TRIES) break;
+        x = fmax(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
+        ++tries;
+        ++n_retry;
+      }
+      if (!ok) {
+        // reachability_algorithm.py:337-342: xs[i+1:] = nan -> sd NaN -> ErrUnknown; us stay 0
+        st = TB_STATUS_ERR_UNKNOWN;
+        fstage = i;
+        if (lane == 0) sdp[i] = sqrt(x);
+        for (int j = i + 1 + lane; j < G; j += 32) sdp[j] = nan_d;
+        for (int j = i + lane; j < N; j += 32) up[j] = 0.0;
+        break;
+      }
+      double x_next = x + 2 * delta * uopt;                       // reachability_algorithm.py:352
+      x_next = fmax(x_next - ALG_TINY, 0.9999 * x_next);          // :353
+      x_next = fmin(k1, fmax(k0, x_next));                        // :354
+      if (lane == 0) {
+        up[i] = uopt;
+        sdp[i] = sqrt(x);  // x may have been shrunk by the retry rule
+        sdp[i + 1] = sqrt(x_next);
+      }
+      x = x_next;
+    }
+    while (n_waited < n_issued) (void)acquire();
+  }
+  if (lane == 0) {
+    status[path] = st;
+    if (fail_stage) fail_stage[path] = fstage;
+    if (counters) {
+      counters[path * 4 + 0] = n_lp2d;
+      counters[path * 4 + 1] = n_lp1d;
+      counters[path * 4 + 2] = n_resolve;
+      counters[path * 4 + 3] = n_retry;
+    }
+  }
+}
+
+// compute_feasible_sets, reachability_algorithm.py:131-164: X[i] = [min x, max x] over stage i alone
+// (x in [-1e4, 1e4], x_next in [-1e4, 1e4]); warm-start slots chained over i like the reference.
+template <int RPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+feasible_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
+                const int grid_shared, const int B, const int G, double *__restrict__ Xout) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long path = (long)blockIdx.x * WARPS + warp;
+  if (path >= B) return;
+  const int N = G - 1, nC = R + 2;
+  const double *rec_path = records + (size_t)path * G * W;
+  const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
+  double *Xp = Xout + (size_t)path * G * 2;
+  double a[RPL], b[RPL], c[RPL];
+  int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0, n_resolve = 0;
+  const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  for (int i = 0; i <= N; ++i) {
+    const double *rec = rec_path + (size_t)i * W;
+    load_rows<RPL>(rec, R, nC, lane, a, b, c);
+    const double xlo = fmax(rec[3 * R], -CVXPY_MAXX), xhi = fmin(rec[3 * R + 1], CVXPY_MAXX);  // pyx:598-601
+    if (i < N) {
+      const double delta = gp[i + 1] - gp[i];
+      set_xnext_rows<RPL>(lane, delta, -CVXPY_MAXX, CVXPY_MAXX, a, b, c);
+    }  // i == N: rows 0,1 stay (0,0,-1), pyx:621-625
+    double uu, xx;
+    // g_lower = (1e-9, 1): g[1] > 0 -> slot up; v = (-1e-9, -1)
+    const bool ok0 = lp2d_warp<RPL>(-1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+                                    n_resolve);
+    double x0 = ok0 ? xx : nan_d;
+    const bool ok1 = lp2d_warp<RPL>(1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
+                                    n_resolve);
+    const double x1 = ok1 ? xx : nan_d;
+    if (x0 < 0) x0 = 0;  // reachability_algorithm.py:160-162
+    if (lane == 0) { Xp[2 * i] = x0; Xp[2 * i + 1] = x1; }
+  }
+}
+
+constexpr int SCAN_WARPS = 4;
+
+template <int RPL>
+int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+  const size_t smem = (size_t)SCAN_WARPS * 2 * W * sizeof(double) + SCAN_WARPS * 2 * sizeof(uint64_t);
+  auto kern = scan_kernel<RPL, SCAN_WARPS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+  kern<<<blocks, SCAN_WARPS * 32, smem, stream>>>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi,
+                                                  flags, K, sd, u, status, fail_stage, counters);
+  return check_launch("tb_scan");
+}
+
+template <int RPL>
+int launch_feasible(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                    double *X, cudaStream_t stream) {
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+  feasible_kernel<RPL, SCAN_WARPS><<<blocks, SCAN_WARPS * 32, 0, stream>>>(records, W, R, grid, grid_shared, B, G, X);
+  return check_launch("tb_feasible_sets");
+}
+
+int check_scan_args(const char *fn, const void *records, int W, int R, const void *grid, int B, int G) {
+  if (!records || !grid || B <= 0 || G <= 0 || R < 0) { set_error("%s: bad argument", fn); return TB_ERR_ARG; }
+  if (R > MAX_ROWS) { set_error("%s: R=%d > %d rows", fn, R, MAX_ROWS); return TB_ERR_UNSUPPORTED; }
+  if (W < 3 * R + 2 || (W & 1)) { set_error("%s: record stride W=%d must be even and >= 3R+2", fn, W); return TB_ERR_ALIGN; }
+  if (((uintptr_t)records & 15) != 0) { set_error("%s: records not 16-byte aligned", fn); return TB_ERR_ALIGN; }
+  return 0;
+}
+
+}  // namespace
+}  // namespace tb
+
+extern "C" int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                          const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                          double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream) {
+  using namespace tb;
+  int rc = check_scan_args("tb_scan", records, W, R, grid, B, G);
+  if (rc) return rc;
+  const bool backward_only = (flags & TB_SCAN_BACKWARD_ONLY) != 0;
+  if (!K || !status || (!backward_only && (!sd || (G > 1 && !u)))) { set_error("tb_scan: null output"); return TB_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nC = R + 2;
+  if (nC <= 32) return launch_scan<1>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  if (nC <= 64) return launch_scan<2>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  if (nC <= 96) return launch_scan<3>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  return launch_scan<4>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+}
+
+extern "C" int tb_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                       const double *sd_start, const double *sd_end, double *K, double *sd, double *u, int *status,
+                       int *fail_stage, void *stream) {
+  return tb_scan_ex(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, nullptr, 0, K, sd, u, status, fail_stage,
+                    nullptr, stream);
+}
+
+extern "C" int tb_feasible_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                                double *X, void *stream) {
+  using namespace tb;
+  int rc = check_scan_args("tb_feasible_sets", records, W, R, grid, B, G);
+  if (rc) return rc;
+  if (!X) { set_error("tb_feasible_sets: null output"); return TB_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nC = R + 2;
+  if (nC <= 32) return launch_feasible<1>(records, W, R, grid, grid_shared, B, G, X, s);
+  if (nC <= 64) return launch_feasible<2>(records, W, R, grid, grid_shared, B, G, X, s);
+  if (nC <= 96) return launch_feasible<3>(records, W, R, grid, grid_shared, B, G, X, s);
+  return launch_feasible<4>(records, W, R, grid, grid_shared, B, G, X, s);
+}

@@ -1,0 +1,208 @@
+"""Thin tensor-level front-end of the C-ABI (toppra_b200/_lib.py -> libtoppra_b200.so).
+
+PyTorch is used for storage (device tensors), streams and H2D/D2H copies only; every number is computed by the
+hand-written sm_100a kernels in toppra_b200/csrc.  No function here has a CPU fallback."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+BC_KINDS = {"not-a-knot": 0, "clamped": 1, "natural": 2}
+
+
+def torch_mod():
+    return _lib.require_cuda()
+
+
+def as_device(x, device, dtype=None):
+    """numpy / tensor -> contiguous fp64 CUDA tensor."""
+    torch = torch_mod()
+    dtype = dtype or torch.float64
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device, non_blocking=True).contiguous()
+
+
+def default_device(device=None):
+    torch = torch_mod()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def parse_bc(bc_type, B, dof, device):
+    """scipy CubicSpline bc_type -> ((kind0, val0), (kind1, val1)) with device value tensors [B, dof] or None."""
+    if isinstance(bc_type, str):
+        if bc_type == "periodic":
+            raise NotImplementedError("toppra_b200: bc_type='periodic' is not supported on device")
+        if bc_type not in BC_KINDS:
+            raise ValueError("bc_type=%r not understood" % (bc_type,))
+        return (BC_KINDS[bc_type], None), (BC_KINDS[bc_type], None)
+    out = []
+    for side in bc_type:
+        if isinstance(side, str):
+            if side not in BC_KINDS or side == "periodic":
+                raise ValueError("bc_type=%r not understood" % (side,))
+            out.append((BC_KINDS[side], None))
+        else:
+            order, val = side
+            if order not in (1, 2):
+                raise ValueError("The specified derivative order must be 1 or 2.")
+            val = np.asarray(val, dtype=np.float64)
+            val = np.broadcast_to(val, (B, dof)) if val.ndim <= 1 else val.reshape(B, dof)
+            out.append((int(order), as_device(np.ascontiguousarray(val), device)))
+    return tuple(out)
+
+
+def spline_fit(ss, wp, bc=((0, None), (0, None))):
+    """ss: [n] or [B, n]; wp: [B, n, dof] (CUDA fp64) -> ppoly [B, 4, n-1, dof]."""
+    torch = torch_mod()
+    lib = _lib.load()
+    B, n, dof = wp.shape
+    ppoly = torch.empty((B, 4, n - 1, dof), dtype=torch.float64, device=wp.device)
+    (k0, v0), (k1, v1) = bc
+    with torch.cuda.device(wp.device):
+        rc = lib.tb_spline_fit(_lib.ptr(ss), 1 if ss.dim() == 1 else 0, _lib.ptr(wp), B, n, dof, k0, _lib.ptr(v0), k1,
+                               _lib.ptr(v1), _lib.ptr(ppoly), _lib.stream_ptr())
+    _lib.check(rc, "tb_spline_fit")
+    return ppoly
+
+
+def ppoly_eval(ppoly, breaks, s, order):
+    """ppoly [B,4,nseg,dof], breaks [nseg+1] or [B,nseg+1], s [G] or [B,G] -> [B,G,dof]."""
+    torch = torch_mod()
+    lib = _lib.load()
+    B, _, nseg, dof = ppoly.shape
+    G = s.shape[-1]
+    out = torch.empty((B, G, dof), dtype=torch.float64, device=ppoly.device)
+    with torch.cuda.device(ppoly.device):
+        rc = lib.tb_ppoly_eval(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg, dof,
+                               _lib.ptr(s), 1 if s.dim() == 1 else 0, G, int(order), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "tb_ppoly_eval")
+    return out
+
+
+def record_doubles(R):
+    return int(_lib.load().tb_record_doubles(int(R)))
+
+
+def alloc_records(B, G, R, device):
+    torch = torch_mod()
+    W = record_doubles(R)
+    return torch.empty((B, G, W), dtype=torch.float64, device=device), W
+
+
+def init_bounds(records, R):
+    torch = torch_mod()
+    B, G, W = records.shape
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_init_bounds(_lib.ptr(records), B, G, W, R, _lib.stream_ptr())
+    _lib.check(rc, "tb_init_bounds")
+
+
+def coeff_velacc(ppoly, breaks, grid, vlim, alim, interp, records, R_total, row0=0, write_xbound=1):
+    """K1.  vlim/alim: [dof,2] or [B,dof,2] device tensors (either may be None, not both)."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    G = grid.shape[-1]
+    W = records.shape[-1]
+    lims = [t for t in (vlim, alim) if t is not None]
+    shared = all(t.dim() == 2 for t in lims)
+    if not shared:
+        vlim = None if vlim is None else (vlim if vlim.dim() == 3 else vlim.expand(B, dof, 2).contiguous())
+        alim = None if alim is None else (alim if alim.dim() == 3 else alim.expand(B, dof, 2).contiguous())
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_coeff_velacc(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg, dof,
+                                         _lib.ptr(grid), 1 if grid.dim() == 1 else 0, G, _lib.ptr(vlim),
+                                         _lib.ptr(alim), 1 if shared else 0, 1 if interp else 0, _lib.ptr(records), W,
+                                         int(R_total), int(row0), int(write_xbound), _lib.stream_ptr())
+    _lib.check(rc, "tb_coeff_velacc")
+
+
+def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
+    """Generic CanonicalLinear rows.  a,b,c: [B,G,m]; F/g per F_mode (see include/toppra_b200.h)."""
+    torch = torch_mod()
+    B, G, m = a.shape
+    W = records.shape[-1]
+    if F_mode == 0:
+        k = F.shape[0]
+    elif F_mode == 1:
+        k = F.shape[2]
+    else:
+        k = 2 * m
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_rows_canlinear(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(F), _lib.ptr(g), int(F_mode),
+                                           B, G, m, k, _lib.ptr(grid), 1 if grid.dim() == 1 else 0, 1 if interp else 0,
+                                           _lib.ptr(records), W, int(R_total), int(row0), _lib.stream_ptr())
+    _lib.check(rc, "tb_rows_canlinear")
+    return 2 * k if interp else k
+
+
+def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False):
+    """K2.  Returns dict(K [B,G,2], sd [B,G], u [B,G-1], status [B] int32, fail_stage [B] int32[, counters [B,4]])."""
+    torch = torch_mod()
+    B, G, W = records.shape
+    dev = records.device
+    K = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+    sd = None if backward_only else torch.empty((B, G), dtype=torch.float64, device=dev)
+    u = None if backward_only else torch.empty((B, max(G - 1, 0)), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    fail_stage = torch.empty((B,), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B, 4), dtype=torch.int32, device=dev) if counters else None
+    u_arg = u if (u is None or u.numel() > 0) else torch.empty((1,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_scan_ex(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
+                                    _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi),
+                                    1 if backward_only else 0, _lib.ptr(K), _lib.ptr(sd),
+                                    _lib.ptr(u_arg),
+                                    _lib.ptr(status), _lib.ptr(fail_stage), _lib.ptr(cnt), _lib.stream_ptr())
+    _lib.check(rc, "tb_scan")
+    out = dict(K=K, sd=sd, u=u, status=status, fail_stage=fail_stage)
+    if counters:
+        out["counters"] = cnt
+    return out
+
+
+def feasible_sets(records, R, grid):
+    torch = torch_mod()
+    B, G, W = records.shape
+    X = torch.empty((B, G, 2), dtype=torch.float64, device=records.device)
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_feasible_sets(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
+                                          _lib.ptr(X), _lib.stream_ptr())
+    _lib.check(rc, "tb_feasible_sets")
+    return X
+
+
+def solve_velacc_host(ss, wp, grid, vlim, alim, interp=True, sd_start=None, sd_end=None, device=0):
+    """Pure C-ABI pipeline with HOST (numpy) buffers: tb_solve_velacc_host.  No torch involved."""
+    lib = _lib.load()
+    ss = np.ascontiguousarray(ss, dtype=np.float64)
+    wp = np.ascontiguousarray(wp, dtype=np.float64)
+    grid = np.ascontiguousarray(grid, dtype=np.float64)
+    B, n, dof = wp.shape
+    G = grid.shape[0]
+    alim = np.ascontiguousarray(alim, dtype=np.float64)
+    shared = alim.ndim == 2
+    if vlim is not None:
+        vlim = np.ascontiguousarray(vlim, dtype=np.float64)
+        if (vlim.ndim == 2) != shared:
+            vlim = np.ascontiguousarray(np.broadcast_to(vlim, (B, dof, 2)))
+            alim = np.ascontiguousarray(np.broadcast_to(alim, (B, dof, 2)))
+            shared = False
+    K = np.empty((B, G, 2))
+    sd = np.empty((B, G))
+    u = np.empty((B, max(G - 1, 1)))
+    status = np.empty((B,), dtype=np.int32)
+
+    def hp(arr):
+        return None if arr is None else ctypes.c_void_p(arr.ctypes.data)
+
+    s0 = None if sd_start is None else np.ascontiguousarray(np.broadcast_to(sd_start, (B,)), dtype=np.float64)
+    s1 = None if sd_end is None else np.ascontiguousarray(np.broadcast_to(sd_end, (B,)), dtype=np.float64)
+    rc = lib.tb_solve_velacc_host(int(device), hp(ss), hp(wp), B, n, dof, hp(grid), G, hp(vlim), hp(alim),
+                                  1 if shared else 0, 1 if interp else 0, hp(s0), hp(s1), hp(K), hp(sd), hp(u),
+                                  hp(status))
+    _lib.check(rc, "tb_solve_velacc_host")
+    return dict(K=K, sd=sd, u=u[:, :G - 1], status=status)

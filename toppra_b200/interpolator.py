@@ -1,0 +1,240 @@
+"""Geometric paths — same public surface as the reference `toppra/interpolator.py`
+(`AbstractGeometricPath` :125-192, `SplineInterpolator` :360-466, `propose_gridpoints` :49-122), with the spline
+fit (scipy CubicSpline restated) and the piecewise-cubic evaluation running on the GPU
+(csrc/tb_spline.cu: tb_spline_fit / tb_ppoly_eval).  `BatchSplineInterpolator` is the batched form used by
+`toppra_b200.BatchTOPPRA` (B independent paths, one launch)."""
+import logging
+from typing import Union
+
+import numpy as np
+
+from . import engine
+
+logger = logging.getLogger(__name__)
+
+
+def propose_gridpoints(path, max_err_threshold=1e-4, max_iteration=100, max_seg_length=0.05, min_nb_points=100):
+    """Generate gridpoints that sufficiently cover the given path (reference interpolator.py:49-122).
+
+    Each pass bisects every segment that is longer than `max_seg_length` or whose estimated interpolation error
+    0.5 * max|q''(mid)| * d^2 exceeds `max_err_threshold`; afterwards all segments are bisected until there are at
+    least `min_nb_points` points.  All midpoints of a pass are evaluated with ONE device call."""
+    gridpoints_ept = [path.path_interval[0], path.path_interval[1]]
+    iteration = 0
+    for iteration in range(max_iteration):
+        add_new_points = False
+        pts = np.asarray(gridpoints_ept, dtype=np.float64)
+        mids = 0.5 * (pts[:-1] + pts[1:])
+        dist = pts[1:] - pts[:-1]
+        qss_mid = np.asarray(path(mids, 2)).reshape(len(mids), -1)
+        for idx in range(len(pts) - 1):
+            if dist[idx] > max_seg_length:
+                gridpoints_ept.append(mids[idx])
+                add_new_points = True
+                continue
+            max_err = np.max(np.abs(0.5 * qss_mid[idx] * dist[idx] ** 2))
+            if max_err > max_err_threshold:
+                add_new_points = True
+                gridpoints_ept.append(mids[idx])
+                continue
+        gridpoints_ept = sorted(gridpoints_ept)
+        if not add_new_points:
+            break
+    while len(gridpoints_ept) < min_nb_points:
+        new_pts = []
+        for idx in range(len(gridpoints_ept) - 1):
+            new_pts.append(0.5 * (gridpoints_ept[idx] + gridpoints_ept[idx + 1]))
+        gridpoints_ept.extend(new_pts)
+        gridpoints_ept = sorted(gridpoints_ept)
+    if iteration == max_iteration - 1:
+        raise ValueError("Unable to find a good gridpoint for this path.")
+    return gridpoints_ept
+
+
+class AbstractGeometricPath(object):
+    """Abstract base class that represents geometric paths (reference interpolator.py:125-192)."""
+
+    def __call__(self, path_positions: Union[float, np.ndarray], order: int = 0) -> np.ndarray:
+        raise NotImplementedError
+
+    @property
+    def dof(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def path_interval(self):
+        raise NotImplementedError
+
+    @property
+    def waypoints(self):
+        return None
+
+    def eval(self, ss_sam):
+        return self(ss_sam, 0)
+
+    def evald(self, ss_sam):
+        return self(ss_sam, 1)
+
+    def evaldd(self, ss_sam):
+        return self(ss_sam, 2)
+
+
+class _DevicePPoly(object):
+    """Stand-in for the scipy PPoly objects the reference exposes as `.cspl/.cspld/.cspldd`:
+    callable, with `.c` (coefficients of this derivative order, scipy layout [k, nseg, dof]) and `.x`."""
+
+    def __init__(self, owner, order):
+        self._owner = owner
+        self._order = order
+
+    def __call__(self, s, nu=0):
+        return self._owner(s, self._order + nu)
+
+    def derivative(self, nu=1):
+        return _DevicePPoly(self._owner, self._order + nu)
+
+    @property
+    def x(self):
+        return self._owner.ss_waypoints
+
+    @property
+    def c(self):
+        c = self._owner._coefficients()
+        for _ in range(self._order):  # scipy PPoly.derivative: c'[j] = c[j] * (k - j)
+            k = c.shape[0] - 1
+            c = c[:-1] * np.arange(k, 0, -1).reshape(-1, 1, 1)
+        return c
+
+
+class BatchSplineInterpolator(object):
+    """B cubic-spline paths fitted and evaluated on the GPU.
+
+    Parameters
+    ----------
+    ss_waypoints: (n,) shared by all paths, or (B, n)
+    waypoints: (B, n, dof)
+    bc_type: as scipy.interpolate.CubicSpline ('not-a-knot', 'clamped', 'natural', or a pair of
+        (order, value) tuples with order in {1, 2}); 'periodic' is not supported.
+    device: torch device (default: current CUDA device)
+
+    `ss_waypoints` / `waypoints` may be numpy arrays (copied H2D here) or CUDA tensors (used in place)."""
+
+    def __init__(self, ss_waypoints, waypoints, bc_type="not-a-knot", device=None):
+        torch = engine.torch_mod()
+        self.device = engine.default_device(device if device is not None else
+                                            (waypoints.device if isinstance(waypoints, torch.Tensor) else None))
+        self.d_wp = engine.as_device(waypoints, self.device)
+        if self.d_wp.dim() != 3:
+            raise ValueError("waypoints must have shape (B, n, dof)")
+        self.B, self.n, self._dof = self.d_wp.shape
+        self.d_ss = engine.as_device(ss_waypoints, self.device)
+        if self.d_ss.shape[-1] != self.n or self.d_ss.dim() not in (1, 2):
+            raise ValueError("ss_waypoints must have shape (n,) or (B, n)")
+        if self.n < 2:
+            raise ValueError("at least 2 waypoints are needed")
+        self.bc_type = bc_type
+        bc = engine.parse_bc(bc_type, self.B, self._dof, self.device)
+        self.d_ppoly = engine.spline_fit(self.d_ss, self.d_wp, bc)
+
+    @property
+    def dof(self):
+        return self._dof
+
+    @property
+    def nseg(self):
+        return self.n - 1
+
+    def eval_device(self, s, order=0):
+        """s: CUDA tensor [G] (shared) or [B, G] -> CUDA tensor [B, G, dof]."""
+        if order not in (0, 1, 2):
+            raise ValueError("Invalid order %s" % order)
+        return engine.ppoly_eval(self.d_ppoly, self.d_ss, s, order)
+
+    def __call__(self, path_positions, order=0):
+        s = np.atleast_1d(np.asarray(path_positions, dtype=np.float64))
+        out = self.eval_device(engine.as_device(s, self.device), order)
+        return out.cpu().numpy()
+
+
+class SplineInterpolator(AbstractGeometricPath):
+    """Interpolate the given waypoints by cubic spline — drop-in for the reference class
+    (interpolator.py:360-466): same constructor, `__call__(s, order)`, `.dof`, `.path_interval`, `.duration`,
+    `.waypoints`, `.cspl/.cspld/.cspldd` (objects exposing `.c`, `.x` and `__call__`).
+
+    The fit (scipy CubicSpline restated) and every evaluation run on the GPU."""
+
+    def __init__(self, ss_waypoints, waypoints, bc_type="not-a-knot", device=None) -> None:
+        super(SplineInterpolator, self).__init__()
+        self.ss_waypoints = np.array(ss_waypoints, dtype=np.float64)
+        self._q_waypoints = np.array(waypoints, dtype=np.float64)
+        assert self.ss_waypoints.shape[0] == self._q_waypoints.shape[0]
+        self._scalar_dof = self._q_waypoints.ndim == 1
+        self._batch = None
+        self._c_host = None
+        if len(self.ss_waypoints) > 1:
+            wp = self._q_waypoints.reshape(len(self.ss_waypoints), -1)
+            self._batch = BatchSplineInterpolator(self.ss_waypoints, wp[None], bc_type=bc_type, device=device)
+        self.cspl = _DevicePPoly(self, 0)
+        self.cspld = _DevicePPoly(self, 1)
+        self.cspldd = _DevicePPoly(self, 2)
+
+    def _coefficients(self):
+        if self._batch is None:
+            raise ValueError("a single-waypoint path has no polynomial coefficients")
+        if self._c_host is None:
+            self._c_host = self._batch.d_ppoly[0].cpu().numpy()
+        c = self._c_host
+        return c[:, :, 0] if self._scalar_dof else c
+
+    def __call__(self, path_positions, order=0):
+        scalar_in = np.ndim(path_positions) == 0
+        s = np.atleast_1d(np.asarray(path_positions, dtype=np.float64))
+        if self._batch is None:
+            # single waypoint: constant path (reference interpolator.py:398-417)
+            if order == 0:
+                out = np.zeros((len(s), self.dof))
+                out[:, :] = self._q_waypoints[0]
+            elif order in (1, 2):
+                out = np.zeros((len(s), self.dof))
+            else:
+                raise ValueError(f"Invalid order {order}")
+        else:
+            if order not in (0, 1, 2):
+                raise ValueError(f"Invalid order {order}")
+            out = self._batch(s.reshape(-1), order)[0].reshape(s.shape + (self._batch.dof,))
+        if self._scalar_dof:
+            out = out[..., 0]
+        if scalar_in:
+            out = out[0]
+        return out
+
+    @property
+    def waypoints(self):
+        """Tuple[np.ndarray, np.ndarray]: positions and waypoints."""
+        return self.ss_waypoints, self._q_waypoints
+
+    def get_duration(self):
+        return self.duration
+
+    @property
+    def duration(self):
+        return self.ss_waypoints[-1] - self.ss_waypoints[0]
+
+    @property
+    def path_interval(self):
+        return np.array([self.ss_waypoints[0], self.ss_waypoints[-1]])
+
+    def get_path_interval(self):
+        return self.path_interval
+
+    @property
+    def dof(self):
+        if np.isscalar(self._q_waypoints[0]):
+            return 1
+        return self._q_waypoints[0].shape[0]
+
+    # device view used by the constraints / algorithms
+    def as_batch(self):
+        if self._batch is None:
+            raise ValueError("single-waypoint paths cannot be parameterised")
+        return self._batch

@@ -1,0 +1,7 @@
+"""Solver wrappers — the reference's strategy interface (`toppra/solverwrapper/solverwrapper.py:49-166`)
+with one implementation: the GPU Seidel solver."""
+from .solverwrapper import available_solvers, check_solver_availability, SolverWrapper, B200SolverWrapper
+
+seidelWrapper = B200SolverWrapper
+
+__all__ = ["available_solvers", "check_solver_availability", "SolverWrapper", "B200SolverWrapper", "seidelWrapper"]
