@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — paths/sec of batched TOPP-RA (7-DOF, 200 gridpoints, vel+accel) on N B200s vs the reference CPU
+seidel path.  Contract: see the task statement; one JSON line on stdout (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA kernels)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's own CPU path on the host cores
+
+A "step" = one pass of the hot path over one batch of `--batch` synthetic paths per GPU (BASELINE.json configs[1]:
+4096 random 7-DOF spline paths, 200 gridpoints, vel+acc): K0 spline fit -> K1 coefficient records -> K2
+backward+forward scan.  `value` times it with the inputs resident in HBM; `e2e` goes through the public API
+(BatchSplineInterpolator / BatchTOPPRA) with pinned HOST buffers, H2D and D2H inside the timed region."""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "paths/sec (7-DOF, 200 gridpoints, vel+accel)"
+UNIT = "paths/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="paths per GPU per step (BASELINE configs[1]: 4096)")
+    ap.add_argument("--gridpoints", type=int, default=200)
+    ap.add_argument("--dof", type=int, default=7)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="paths in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arms: the reference's own implementation (oracle/_ref) or, if that build is absent, the C port.
+# ----------------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def _ref_worker_init():
+    import warnings
+    warnings.filterwarnings("ignore")
+    try:  # one BLAS thread per worker process: the reference's a_j.dot(F_j.T) must not oversubscribe the cores
+        from threadpoolctl import threadpool_limits
+        _REF["blas_limit"] = threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle.ref_loader import load_reference
+    ta = load_reference()
+    import toppra.algorithm as algo
+    import toppra.constraint as constraint
+    _REF.update(ta=ta, algo=algo, constraint=constraint)
+
+
+def _ref_solve_chunk(args):
+    """Reference hot path for a chunk of paths: SplineInterpolator + TOPPRA(seidel).compute_parameterization."""
+    ss, way, vlim, alim, grid = args
+    ta, algo, constraint = _REF["ta"], _REF["algo"], _REF["constraint"]
+    n_ok = 0
+    for b in range(way.shape[0]):
+        path = ta.SplineInterpolator(ss, way[b])
+        inst = algo.TOPPRA([constraint.JointVelocityConstraint(vlim[b]), constraint.JointAccelerationConstraint(alim[b])],
+                           path, gridpoints=grid, solver_wrapper="seidel")
+        inst.compute_parameterization(0, 0)
+        n_ok += inst.problem_data.return_code == algo.ParameterizationReturnCode.Ok
+    return n_ok
+
+
+class CpuArm(object):
+    """Times the reference CPU path on all host cores (multiprocessing, one chunk of paths per task)."""
+
+    def __init__(self, dof, G):
+        from oracle.ref_loader import reference_available
+        self.kind = "reference" if reference_available() else "port"
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.G, self.dof = G, dof
+        self.pool = None
+        if self.kind == "reference":
+            import multiprocessing as mp
+            self.pool = mp.get_context("fork").Pool(self.cores, initializer=_ref_worker_init)
+        else:
+            from oracle import oracle as orc
+            self.orc = orc
+
+    def run(self, ss, way, vlim, alim, grid):
+        """Solve all given paths; returns seconds."""
+        B = way.shape[0]
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            nchunk = min(B, self.cores * 4)
+            idx = np.array_split(np.arange(B), nchunk)
+            tasks = [(ss, way[i], vlim[i], alim[i], grid) for i in idx if len(i)]
+            self.pool.map(_ref_solve_chunk, tasks, chunksize=1)
+        else:
+            c = np.stack([self.orc.cubic_spline_fit(ss, way[b]) for b in range(B)])
+            self.orc.solve_velacc_batch(c, np.tile(ss, (B, 1)), grid, vlim, alim, True, nthreads=self.cores)
+        return time.perf_counter() - t0
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from problems import make_batch_fast
+    G, dof = args.gridpoints, args.dof
+    arm = CpuArm(dof, G)
+    # bounded sample of the workload per step: ~2 s of wall time per step on this box
+    per_core = 180.0 if arm.kind == "reference" else 4000.0
+    S = args.cpu_sample or int(min(args.batch, max(arm.cores * 8, per_core * arm.cores * 2.0)))
+    ss, way, vlim, alim = make_batch_fast(S, seed=1234, dof=dof)
+    grid = np.linspace(0, 1, G)
+    for _ in range(max(args.warmup, 1)):
+        arm.run(ss, way, vlim, alim, grid)
+    secs = [arm.run(ss, way, vlim, alim, grid) for _ in range(args.steps)]
+    arm.close()
+    total = float(np.sum(secs))
+    value = S * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch %d random %d-DOF spline paths, %d gridpoints, vel+accel" % (args.batch, dof, G),
+                   "sample_paths_per_step": S, "solver": "reference seidelWrapper (Cython, -O1) via TOPPRA(..., 'seidel')"
+                   if arm.kind == "reference" else "oracle C port (reference build absent)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                         "sample": "%d paths/step x %d steps, spline fit + wrapper construction + compute_parameterization, "
+                                   "multiprocessing over %d cores" % (S, args.steps, arm.cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import toppra_b200 as ta
+    from toppra_b200 import engine
+    from problems import make_batch_fast
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B, G, dof, nway = args.batch, args.gridpoints, args.dof, 5
+    R = 4 * dof
+    ss, way, vlim, alim = make_batch_fast(B, seed=1234 + rank, dof=dof, nway=nway)  # every rank: its own shard
+    grid = np.linspace(0, 1, G)
+
+    # CPU baseline first: the worker pool is forked before this process touches CUDA
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            arm = CpuArm(dof, G)
+            S = args.cpu_sample or min(B, 4096)  # the whole cfg-2 batch: ~20 s of CPU work for the reference
+            arm.run(ss, way[:min(S, 256)], vlim[:min(S, 256)], alim[:min(S, 256)], grid)  # warm-up (imports, pool)
+            secs = arm.run(ss, way[:S], vlim[:S], alim[:S], grid)
+            arm.close()
+            cpu = {"value": S / secs, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                   "sample": "%d paths of the same batch (spline fit + wrapper construction + compute_parameterization), "
+                             "%s, %d processes" % (S, "reference TOPPRA(seidel)" if arm.kind == "reference" else "C port", arm.cores)}
+        except Exception as exc:  # never lose the GPU line
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # pinned host buffers (e2e) and device-resident inputs (value)
+    h_way = torch.as_tensor(way).pin_memory()
+    h_vlim = torch.as_tensor(vlim).pin_memory()
+    h_alim = torch.as_tensor(alim).pin_memory()
+    h_ss = torch.as_tensor(ss).pin_memory()
+    h_grid = torch.as_tensor(grid).pin_memory()
+    d_way, d_vlim, d_alim, d_ss, d_grid = (t.to(dev) for t in (h_way, h_vlim, h_alim, h_ss, h_grid))
+    h_out = {"K": torch.empty((B, G, 2), dtype=torch.float64).pin_memory(),
+             "sd": torch.empty((B, G), dtype=torch.float64).pin_memory(),
+             "sdd": torch.empty((B, G - 1), dtype=torch.float64).pin_memory(),
+             "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    W = engine.record_doubles(R)
+    records = torch.empty((B, G, W), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * B, G), dtype=torch.float64, device=dev) if world > 1 else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    k_events = []  # (k0_start, k1_start, k2_start, k2_end) per timed step
+
+    def step_device(record_kernels=False):
+        """Hot path with inputs resident in HBM: 3 kernel launches (K0, K1, K2)."""
+        e = [ev() for _ in range(4)] if record_kernels else None
+        if e: e[0].record()
+        ppoly = engine.spline_fit(d_ss, d_way)
+        if e: e[1].record()
+        engine.coeff_velacc(ppoly, d_ss, d_grid, d_vlim, d_alim, True, records, R, 0, 1)
+        if e: e[2].record()
+        out = engine.scan(records, R, d_grid)
+        if e:
+            e[3].record()
+            k_events.append(e)
+        return out
+
+    # the e2e step builds constraint objects from host limit arrays each step (their H2D copy is part of the step)
+    def step_e2e_full():
+        path = ta.BatchSplineInterpolator(h_ss.to(dev, non_blocking=True), h_way.to(dev, non_blocking=True), device=dev)
+        pc_vel = ta.constraint.JointVelocityConstraint(vlim)
+        pc_acc = ta.constraint.JointAccelerationConstraint(alim)
+        pc_vel._d_cache[str(dev)] = h_vlim.to(dev, non_blocking=True)
+        pc_acc._d_cache[str(dev)] = h_alim.to(dev, non_blocking=True)
+        inst = ta.BatchTOPPRA([pc_vel, pc_acc], path, h_grid.to(dev, non_blocking=True))
+        res = inst.compute_parameterization(0.0, 0.0)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res.sd)  # NCCL: gather the result velocities (north_star)
+        h_out["K"].copy_(res.K, non_blocking=True)
+        h_out["sd"].copy_(res.sd, non_blocking=True)
+        h_out["sdd"].copy_(res.sdd, non_blocking=True)
+        h_out["status"].copy_(res.status, non_blocking=True)
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, record_kernels=False):
+        for _ in range(warmup):
+            fn()
+            flush.zero_()
+        barrier()
+        pairs = []
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            s, e = ev(), ev()
+            s.record()
+            fn(True) if record_kernels else fn()
+            e.record()
+            pairs.append((s, e))
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in pairs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev = timed(step_device, args.steps, max(args.warmup, 3), record_kernels=True)
+    ms_e2e = timed(step_e2e_full, args.steps, max(args.warmup, 3))
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    status = h_out["status"].numpy()
+    n_ok = int((status == 0).sum())
+    total_paths = B * world
+    value = total_paths * args.steps / (ms_dev * 1e-3)
+    e2e_value = total_paths * args.steps / (ms_e2e * 1e-3)
+    k0 = float(np.mean([e[0].elapsed_time(e[1]) for e in k_events]))
+    k1 = float(np.mean([e[1].elapsed_time(e[2]) for e in k_events]))
+    k2 = float(np.mean([e[2].elapsed_time(e[3]) for e in k_events]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (K2 scan) and of K1, algorithmic bytes per SURVEY.md §8d / DESIGN.md
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    bytes_k1 = (4 * (nway - 1) * dof * 8 + G * (3 * R + 2) * 8) * B
+    bytes_k2 = (2 * G * (3 * R + 2) * 8 + G * 16 + G * 8 + (G - 1) * 8 + 8) * B
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    roof = {"kernel": "scan_kernel (K2)", "bound": "hbm", "achieved": bytes_k2 / (k2 * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": bytes_k2 / (k2 * 1e-3) / 1e9 / peak,
+            "traffic": (traffic or {}).get("scan_kernel_bytes_per_launch"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_k2, "ms_per_launch": k2,
+            "note": "K2 is a latency/issue-bound sequential scan (597 dependent LPs per path); see lp_solves_per_s"}
+    roof_k1 = {"kernel": "coeff_velacc_kernel (K1)", "bound": "hbm", "achieved": bytes_k1 / (k1 * 1e-3) / 1e9,
+               "peak": peak, "unit": "GB/s", "frac": bytes_k1 / (k1 * 1e-3) / 1e9 / peak,
+               "traffic": (traffic or {}).get("coeff_velacc_kernel_bytes_per_launch"),
+               "algorithmic_bytes_per_launch": bytes_k1, "ms_per_launch": k1}
+
+    h2d = int(h_way.numel() + h_vlim.numel() + h_alim.numel() + h_ss.numel() + h_grid.numel()) * 8
+    d2h = int(h_out["K"].numel() + h_out["sd"].numel() + h_out["sdd"].numel()) * 8 + int(h_out["status"].numel()) * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch %d random %d-DOF cubic-spline paths (5 waypoints), %d gridpoints, "
+                               "JointVelocity+JointAcceleration(interp), per GPU" % (B, dof, G),
+                   "global_batch": total_paths, "parallelism": "paths sharded over %d GPU(s), no data-path collective" % world,
+                   "l2": "256 MB buffer written between timed iterations (L2 flush)", "ok_paths_last_step": n_ok},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "BatchSplineInterpolator + BatchTOPPRA.compute_parameterization, pinned host buffers"
+                       + (", NCCL all_gather of sd" if world > 1 else "")},
+        "gpu_launches": 3 * args.steps,
+        "kernels_ms": {"K0_spline_fit": k0, "K1_coeff": k1, "K2_scan": k2},
+        "roofline": roof, "roofline_k1": roof_k1,
+        "lp_solves_per_s": 597.0 / 199 * (G - 1) * B / (k2 * 1e-3),
+        "clocks": sampler.summary(),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

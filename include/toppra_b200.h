@@ -77,7 +77,7 @@ extern "C" {
 int tb_version(void);
 const char *tb_last_error(void);
 
-/* Compiled limits: max_rows = largest R (static LP rows per stage), max_knots = largest n. */
+/* Compiled limits: max_rows = largest R (static LP rows per stage), max_knots = largest n of tb_spline_fit. */
 int tb_limits(int *max_rows, int *max_knots);
 
 /* Record stride in doubles for R static rows: 3R+2 rounded up to even. */
@@ -85,9 +85,12 @@ int tb_record_doubles(int R);
 
 /* K0 — not-a-knot / clamped / natural cubic spline through wp[B][n][dof] at ss.
  *   ss: [n] (ss_shared=1) or [B][n]; bc0/bc1: boundary values [B][dof] or NULL (= zeros);
- *   ppoly out: [B][4][n-1][dof] (scipy PPoly.c layout per path, highest power first). */
+ *   ppoly out: [B][4][n-1][dof] (scipy PPoly.c layout per path, highest power first);
+ *   workspace: device scratch of tb_spline_fit_workspace_doubles(B, n, dof) doubles (0 for short splines:
+ *   NULL allowed then). */
+int tb_spline_fit_workspace_doubles(int B, int n, int dof);
 int tb_spline_fit(const double *ss, int ss_shared, const double *wp, int B, int n, int dof, int bc0_kind,
-                  const double *bc0, int bc1_kind, const double *bc1, double *ppoly, void *stream);
+                  const double *bc0, int bc1_kind, const double *bc1, double *ppoly, double *workspace, void *stream);
 
 /* path(s, order), order in {0,1,2}.  breaks: [nseg+1] or [B][nseg+1]; s: [G] or [B][G];
  *   out: [B][G][dof]. */
@@ -143,6 +146,20 @@ int tb_feasible_sets(const double *records, int W, int R, const double *grid, in
 int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,
                double *u, int *status, int *fail_stage, int *counters, void *stream);
+
+/* Stand-alone batched LPs, one warp per LP — device counterparts of the reference's Python shims
+ * solve_lp2d / solve_lp1d (cy_seidel_solverwrapper.pyx:42-87).
+ *   tb_lp2d_batch: max v0 u + v1 x + v2  s.t. a u + b x + c <= 0 (n rows), low <= (u,x) <= high.
+ *     v [B][3]; a,b,c [B][n]; low, high [B][2]; active_in [B][2] warm-start pair (nullable = zeros);
+ *     result [B] (1 feasible / 0 infeasible); optval [B]; optvar [B][2] (NaN if infeasible);
+ *     active_out [B][2] (row indices, or -1..-4 for the box bounds low0, high0, low1, high1).
+ *   tb_lp1d_batch: max v0 x + v1  s.t. a x + b <= 0, low <= x <= high.   v [B][2]; a,b [B][n]; low, high [B];
+ *     active_out [B] (row index, -1 = low, -2 = high). */
+int tb_lp2d_batch(const double *v, const double *a, const double *b, const double *c, const double *low,
+                  const double *high, const int *active_in, int B, int n, int *result, double *optval, double *optvar,
+                  int *active_out, void *stream);
+int tb_lp1d_batch(const double *v, const double *a, const double *b, const double *low, const double *high, int B,
+                  int n, int *result, double *optval, double *optvar, int *active_out, void *stream);
 
 /* Whole pipeline with HOST buffers (K0 -> K1 -> K2, H2D/D2H inside, synchronous):
  *   ss [n] shared; wp [B][n][dof]; grid [G] shared; vlim (nullable) / alim: [dof][2] shared or [B][dof][2];

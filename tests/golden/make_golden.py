@@ -1,0 +1,243 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built by
+oracle/build_ref.sh from /root/reference) and scipy.  Run where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The fixtures pin the oracle (tests/test_oracle_vs_golden.py, CPU) and the CUDA path
+(tests/test_gpu_*.py) to the reference's own outputs; /root/reference is not needed to RUN the tests.
+Inputs follow SURVEY.md §8d (cfg 1/2, parity sets P1-P6) and the reference's own test fixtures
+(cited per case)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+warnings.filterwarnings("ignore")
+
+from oracle.ref_loader import load_reference  # noqa: E402
+from problems import make_path  # noqa: E402
+
+ta = load_reference()
+import toppra.algorithm as algo  # noqa: E402
+import toppra.constraint as constraint  # noqa: E402
+import toppra.solverwrapper.cy_seidel_solverwrapper as seidel  # noqa: E402
+from scipy.interpolate import CubicSpline  # noqa: E402
+
+REF_TESTS = "/root/reference/tests/tests"
+
+
+def solve_ref(ss, way, vlim, alim, grid, sd_start=0.0, sd_end=0.0, scheme=1, bc_type="not-a-knot"):
+    """Reference TOPPRA(seidel) on one path -> dict of everything the tests compare."""
+    path = ta.SplineInterpolator(ss, way, bc_type=bc_type)
+    pc_vel = constraint.JointVelocityConstraint(vlim)
+    pc_acc = constraint.JointAccelerationConstraint(alim, discretization_scheme=scheme)
+    inst = algo.TOPPRA([pc_vel, pc_acc], path, gridpoints=grid, solver_wrapper="seidel")
+    sdd, sd, _, K = inst.compute_parameterization(sd_start, sd_end, return_data=True)
+    G = len(grid)
+    code = inst.problem_data.return_code
+    codes = list(algo.ParameterizationReturnCode)
+    out = dict(c=path.cspl.c, K=K, status=codes.index(code),
+               sd=np.full(G, np.nan) if sd is None else sd,
+               sdd=np.full(G - 1, np.nan) if sdd is None else sdd,
+               xbound=pc_vel.compute_constraint_params(path, grid)[-1])
+    a, b, c, F, g, _, _ = pc_acc.compute_constraint_params(path, grid)
+    out.update(acc_a=a, acc_b=b, acc_F=F, acc_g=g)
+    out["qs"] = path(grid, 1)
+    out["qss"] = path(grid, 2)
+    return out, inst
+
+
+def stack(dicts):
+    return {k: np.stack([d[k] for d in dicts]) for k in dicts[0]}
+
+
+def batch_case(name, seeds, G, vel_active=False, sd_start=0.0, sd_end=0.0, scheme=1, dof=7, grid=None):
+    ss = np.linspace(0, 1, 5)
+    grid = np.linspace(0, 1, G) if grid is None else grid
+    rows, ways, vlims, alims = [], [], [], []
+    for s in seeds:
+        way, vlim, alim = make_path(s, dof=dof, vel_active=vel_active)
+        out, _ = solve_ref(ss, way, vlim, alim, grid, sd_start, sd_end, scheme)
+        rows.append(out)
+        ways.append(way); vlims.append(vlim); alims.append(alim)
+    data = stack(rows)
+    data.update(ss=ss, way=np.stack(ways), vlim=np.stack(vlims), alim=np.stack(alims), grid=grid,
+                sd_start=np.float64(sd_start), sd_end=np.float64(sd_end), scheme=np.int64(scheme),
+                seeds=np.asarray(seeds))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+    print(name, "status histogram", np.bincount(data["status"], minlength=5))
+
+
+def main():
+    # ---- cfg 1: examples/plot_kinematics.py:22-40, np.random.seed(9), 100 gridpoints ---------------------
+    np.random.seed(9)
+    dof = 7
+    way = np.random.randn(5, dof)
+    ss = np.linspace(0, 1, 5)
+    vl = 10 + np.random.rand(dof) * 20
+    al = 10 + np.random.rand(dof) * 2
+    vlim = np.vstack((-vl, vl)).T
+    alim = np.vstack((-al, al)).T
+    grid = np.linspace(0, 1, 100)
+    out, inst = solve_ref(ss, way, vlim, alim, grid)
+    out["X"] = inst.compute_feasible_sets()
+    out["K_0_05"] = inst.compute_controllable_sets(0.0, 0.5)
+    traj = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
+                       ta.SplineInterpolator(ss, way), gridpoints=grid, solver_wrapper="seidel").compute_trajectory(0, 0)
+    ts = np.linspace(0, traj.duration, 50)
+    out.update(ss=ss, way=way, vlim=vlim, alim=alim, grid=grid, traj_duration=np.float64(traj.duration),
+               traj_ts=ts, traj_q=traj(ts), traj_qd=traj(ts, 1), traj_qdd=traj(ts, 2))
+    # the example's own automatic grid
+    auto = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
+                       ta.SplineInterpolator(ss, way), solver_wrapper="seidel")
+    sdd, sd, _, K = auto.compute_parameterization(0, 0, return_data=True)
+    out.update(auto_grid=auto.gridpoints, auto_sd=sd, auto_K=K)
+    np.savez_compressed(os.path.join(HERE, "cfg1_seed9.npz"), **out)
+    print("cfg1: duration", traj.duration, "auto gridpoints", len(auto.gridpoints))
+
+    # ---- cfg 2 shape + parity-only sets --------------------------------------------------
+    batch_case("cfg2_seeds1000", range(1000, 1016), 200)
+    batch_case("p1_velocity_active", range(1000, 1016), 200, vel_active=True)
+    batch_case("p2_boundary_speeds", range(1000, 1008), 100, sd_start=0.05, sd_end=0.03)
+    batch_case("p3_inadmissible_start", range(1000, 1004), 50, sd_start=5.0)
+    batch_case("p5_grid_on_breakpoints", range(1000, 1008), 201)
+    batch_case("p6_collocation", range(1000, 1008), 100, scheme=0)
+    batch_case("dof6_g500", range(2000, 2004), 500, dof=6)
+    # non-uniform grid
+    rng = np.random.RandomState(5)
+    g = np.sort(np.r_[0.0, 1.0, rng.rand(148)])
+    batch_case("nonuniform_grid", range(1000, 1008), 150, grid=g)
+
+    # ---- P6: 2-DOF collocation golden of cpp/tests/test_algorithm.cpp:25-169 (generator script :25-57) ----
+    path = ta.SplineInterpolator([0, 1, 2, 3], [[0, 0], [1, 3], [2, 4], [0, 0]])
+    pc_vel = constraint.JointVelocityConstraint([1.0, 1.0])
+    pc_acc = constraint.JointAccelerationConstraint([0.2, 0.2], discretization_scheme=0)
+    grid = np.linspace(0, 3, 51)
+    inst = algo.TOPPRA([pc_vel, pc_acc], path, gridpoints=grid, solver_wrapper="seidel")
+    sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+    X = inst.compute_feasible_sets()
+    np.savez_compressed(os.path.join(HERE, "cpp_2dof_collocation.npz"), ss=np.array([0., 1, 2, 3]),
+                        way=np.array([[0., 0], [1, 3], [2, 4], [0, 0]]), grid=grid, c=path.cspl.c, K=K, sd=sd, sdd=sdd,
+                        X=X, vlim=np.array([[-1., 1], [-1, 1]]), alim=np.array([[-0.2, 0.2], [-0.2, 0.2]]))
+
+    # ---- LP layer: 100 seeded random LPs of tests/tests/lpsolvers/seidel/test_lp2d.py:74-95 ----------------
+    lp = dict(v=[], a=[], b=[], c=[], active_in=[], res=[], optval=[], optvar=[], active_out=[])
+    for seed in range(100):
+        d = 50
+        np.random.seed(seed)
+        seeds = np.random.randint(1000, size=7)
+        np.random.seed(seeds[0])
+        v = np.random.randn(3)
+        np.random.seed(seeds[1])
+        a, b = np.random.randn(2, d)
+        np.random.seed(seeds[2])
+        c = -np.random.rand(d) if seed % 2 == 0 else np.random.randn(d)
+        low = np.r_[-0.5, -0.9]
+        high = np.r_[0.5, 0.9]
+        np.random.seed(seeds[3])
+        active_c = np.random.choice(d, size=2)
+        res, optval, optvar, act = seidel.solve_lp2d(v, a, b, c, low, high, active_c.astype(np.int64))
+        lp["v"].append(v); lp["a"].append(a); lp["b"].append(b); lp["c"].append(c)
+        lp["active_in"].append(active_c)
+        lp["res"].append(res)
+        lp["optval"].append(optval if res else np.nan)
+        lp["optvar"].append(np.array(optvar) if res else np.full(2, np.nan))
+        lp["active_out"].append(np.array(act) if res else np.zeros(2, dtype=int))
+    lp = {k: np.asarray(val) for k, val in lp.items()}
+    lp.update(low=np.r_[-0.5, -0.9], high=np.r_[0.5, 0.9])
+    np.savez_compressed(os.path.join(HERE, "lp2d_random100.npz"), **lp)
+    print("lp2d random: feasible", int(lp["res"].sum()), "/ 100")
+
+    # ---- stage-level: tests/tests/solverwrapper/test_basic_can_linear.py:53-164 fixture (6-DOF, N=200, seed 1)
+    np.random.seed(1)
+    dof = 6
+    way_pts = np.random.randn(4, dof) * 0.6
+    path = ta.SplineInterpolator(np.linspace(0, 1, 4), way_pts)
+    vlim_ = np.random.rand(dof) * 10 + 10
+    vlim = np.vstack((-vlim_, vlim_)).T
+    alim_ = np.random.rand(dof) * 10 + 100
+    alim = np.vstack((-alim_, alim_)).T
+    grid = np.linspace(0, path.duration, 201)
+    cons = [constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)]
+    w = seidel.seidelWrapper(cons, path, grid, solve_lp1d=1)
+    cases = []
+    for i in (3, 10, 30, 40):
+        for g in (np.array([0.2, -1.0]), np.array([0.5, 1.0]), np.array([2.0, 1.0])):
+            for (x_ineq, xn_ineq) in ((( -1.0, 1.0), (0.0, 1.0)), ((0.2, 0.2), (0.0, 1.0)),
+                                      ((np.nan, np.nan), (0.05, 0.5)), ((0.0, 0.05), (np.nan, np.nan))):
+                res = np.array(w.solve_stagewise_optim(i, None, g, x_ineq[0], x_ineq[1], xn_ineq[0], xn_ineq[1]))
+                cases.append(np.r_[i, g, x_ineq, xn_ineq, res])
+    np.savez_compressed(os.path.join(HERE, "stagewise_6dof.npz"), ss=np.linspace(0, 1, 4), way=way_pts, vlim=vlim,
+                        alim=alim, grid=grid, cases=np.asarray(cases))
+
+    # ---- spline fits for the other boundary conditions (scipy) ------------------------------------------
+    rng = np.random.RandomState(3)
+    fits = {}
+    for n in (2, 3, 4, 5, 9, 20):
+        x = np.sort(rng.rand(n)) * 2.0
+        x[0] = 0.0
+        y = rng.randn(n, 3)
+        fits["x_%d" % n] = x
+        fits["y_%d" % n] = y
+        for bc in ("not-a-knot", "clamped", "natural"):
+            fits["c_%d_%s" % (n, bc)] = CubicSpline(x, y, bc_type=bc).c
+        d0, d1 = rng.randn(3), rng.randn(3)
+        fits["d0_%d" % n], fits["d1_%d" % n] = d0, d1
+        fits["c_%d_first" % n] = CubicSpline(x, y, bc_type=((1, d0), (1, d1))).c
+        fits["c_%d_mixed" % n] = CubicSpline(x, y, bc_type=((2, d0), (1, d1))).c
+    np.savez_compressed(os.path.join(HERE, "spline_fits.npz"), **fits)
+
+    # ---- P4: tiny-motion robustness suite tests/tests/retime/robustness/problem_suite_1.yaml (clamped BC) ----
+    import yaml
+    suite = yaml.safe_load(open(os.path.join(REF_TESTS, "retime/robustness/problem_suite_1.yaml")))
+    rob = {}
+    names = []
+    for key, prob in suite.items():
+        wp = np.array(prob["waypoints"], dtype=float)
+        ssw = np.linspace(prob["ss_waypoints"][0], prob["ss_waypoints"][1], len(wp))
+        vl = np.r_[prob["vlim"]].astype(float)
+        al = np.r_[prob["alim"]].astype(float)
+        for G in prob["nb_gridpoints"]:
+            grid = np.linspace(ssw[0], ssw[-1], G)
+            out, _ = solve_ref(ssw, wp, np.vstack((-vl, vl)).T, np.vstack((-al, al)).T, grid, bc_type="clamped")
+            tag = "%s_%d" % (key, G)
+            names.append(tag)
+            rob[tag + "_ss"], rob[tag + "_way"], rob[tag + "_grid"] = ssw, wp, grid
+            rob[tag + "_vlim"], rob[tag + "_alim"] = np.vstack((-vl, vl)).T, np.vstack((-al, al)).T
+            for k in ("c", "K", "sd", "sdd", "status"):
+                rob[tag + "_" + k] = out[k]
+    rob["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "p4_robustness_suite.npz"), **rob)
+    print("robustness suite:", len(names), "cases, statuses", [int(rob[n + "_status"]) for n in names])
+
+    # ---- SecondOrder (cfg-3 shape, small): synthetic closed-form torque model, SURVEY.md §8d cfg 3 -------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from problems import make_torque_problem, inv_dyn_numpy
+    outs = []
+    for seed in range(2000, 2004):
+        way, vlim, alim, taulim = make_torque_problem(seed)
+        ssw = np.linspace(0, 1, 5)
+        grid = np.linspace(0, 1, 100)
+        path = ta.SplineInterpolator(ssw, way)
+        pc_vel = constraint.JointVelocityConstraint(vlim)
+        pc_acc = constraint.JointAccelerationConstraint(alim)
+        pc_tau = constraint.SecondOrderConstraint.joint_torque_constraint(inv_dyn_numpy, taulim, np.zeros(6))
+        inst = algo.TOPPRA([pc_vel, pc_acc, pc_tau], path, gridpoints=grid, solver_wrapper="seidel")
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        a, b, c, F, g, _, _ = pc_tau.compute_constraint_params(path, grid)
+        codes = list(algo.ParameterizationReturnCode)
+        outs.append(dict(way=way, vlim=vlim, alim=alim, taulim=taulim, K=K, sd=sd, sdd=sdd, tau_a=a, tau_b=b, tau_c=c,
+                         status=codes.index(inst.problem_data.return_code)))
+    data = stack(outs)
+    data.update(ss=np.linspace(0, 1, 5), grid=np.linspace(0, 1, 100))
+    np.savez_compressed(os.path.join(HERE, "torque_dof6.npz"), **data)
+    print("torque: statuses", data["status"])
+
+
+if __name__ == "__main__":
+    main()

@@ -34,3 +34,29 @@ def make_batch_fast(B, seed=1234, dof=7, nway=5):
     vlim = np.stack((-vl, vl), axis=-1)
     alim = np.stack((-al, al), axis=-1)
     return np.linspace(0, 1, nway), way, vlim, alim
+
+
+# ---- cfg 3: synthetic closed-form torque model:
+#      tau = M(q) qdd + h(q) |qd|^2 + g(q),  M = 2 I + 0.3 cos(q_i - q_j),  h = 0.1 sin q,  g = 4.9 sin q
+def inv_dyn_numpy(q, qd, qdd):
+    q, qd, qdd = np.asarray(q), np.asarray(qd), np.asarray(qdd)
+    M = 2.0 * np.eye(len(q)) + 0.3 * np.cos(q[:, None] - q[None, :])
+    return M.dot(qdd) + 0.1 * np.sin(q) * np.dot(qd, qd) + 4.9 * np.sin(q)
+
+
+def inv_dyn_torch(q, qd, qdd):
+    """Batched form on tensors [M, dof] (same formula)."""
+    import torch
+    dof = q.shape[-1]
+    Mm = 2.0 * torch.eye(dof, dtype=q.dtype, device=q.device) + 0.3 * torch.cos(q[:, :, None] - q[:, None, :])
+    return (torch.bmm(Mm, qdd[:, :, None])[:, :, 0] + 0.1 * torch.sin(q) * (qd * qd).sum(-1, keepdim=True)
+            + 4.9 * torch.sin(q))
+
+
+def make_torque_problem(seed, dof=6, nway=5):
+    rng = np.random.RandomState(seed)
+    way = rng.randn(nway, dof)
+    vl = 10 + rng.rand(dof) * 20
+    al = 10 + rng.rand(dof) * 2
+    tl = 40 + rng.rand(dof) * 10
+    return way, np.vstack((-vl, vl)).T, np.vstack((-al, al)).T, np.vstack((-tl, tl)).T

@@ -1,0 +1,85 @@
+"""GPU (-m gpu): BASELINE.json sizes.  cfg 2 (B=4096, 7-DOF, 200 gridpoints) is checked bit-for-bit against the
+oracle (the C restatement solves 4096 paths in about a second on a few threads); the larger batch is checked
+through size-independent properties of a correct parameterisation."""
+import os
+
+import numpy as np
+import pytest
+
+from problems import make_batch, make_batch_fast
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ta():
+    import toppra_b200
+    return toppra_b200
+
+
+def _solve(ta, ss, way, vlim, alim, grid, counters=False):
+    path = ta.BatchSplineInterpolator(ss, way)
+    inst = ta.BatchTOPPRA([ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)],
+                          path, grid)
+    res = inst.compute_parameterization(0.0, 0.0, counters=counters)
+    return path, inst, res
+
+
+def test_cfg2_full_batch_vs_oracle(ta):
+    from oracle import oracle as orc
+    B, G = 4096, 200
+    ss, way, vlim, alim = make_batch(B, 1000)          # path b uses RandomState(1000 + b), SURVEY §8d cfg 2
+    grid = np.linspace(0, 1, G)
+    path, inst, res = _solve(ta, ss, way, vlim, alim, grid, counters=True)
+    h = res.to_host()
+    c = path.d_ppoly.cpu().numpy()
+    o = orc.solve_velacc_batch(c, np.tile(ss, (B, 1)), grid, vlim, alim, True, nthreads=min(16, os.cpu_count() or 1))
+    assert np.array_equal(h["status"], o["status"]) and not h["status"].any()
+    assert np.array_equal(h["K"], o["K"]) and np.array_equal(h["sd"], o["sd"]) and np.array_equal(h["sdd"], o["u"])
+    cnt = res.counters.cpu().numpy()
+    assert (cnt[:, 0] == 2 * (G - 1)).all() and (cnt[:, 1] == G - 1).all()   # 398 2-D + 199 1-D LPs per path
+
+
+def test_velocity_active_batch_vs_oracle(ta):
+    from oracle import oracle as orc
+    B, G = 512, 200
+    ss, way, vlim, alim = make_batch(B, 1000, vel_active=True)
+    grid = np.linspace(0, 1, G)
+    path, inst, res = _solve(ta, ss, way, vlim, alim, grid)
+    h = res.to_host()
+    o = orc.solve_velacc_batch(path.d_ppoly.cpu().numpy(), np.tile(ss, (B, 1)), grid, vlim, alim, True, nthreads=8)
+    assert np.array_equal(h["status"], o["status"])
+    assert np.array_equal(h["K"], o["K"]) and np.array_equal(h["sd"], o["sd"]) and np.array_equal(h["sdd"], o["u"])
+
+
+def test_large_batch_properties(ta):
+    """65536 paths (cfg-5 shard size order): properties that hold for every correct parameterisation."""
+    import torch
+    B, G = 65536, 200
+    ss, way, vlim, alim = make_batch_fast(B, seed=77)
+    grid = np.linspace(0, 1, G)
+    path, inst, res = _solve(ta, ss, way, vlim, alim, grid)
+    assert int((res.status != 0).sum()) == 0
+    K, sd, u = res.K, res.sd, res.sdd
+    x = sd * sd
+    assert bool((sd[:, 0] == 0).all()) and bool((sd[:, -1] == 0).all())
+    assert bool((K[:, :, 0] <= K[:, :, 1]).all()) and bool((K[:, :, 0] >= 0).all())
+    assert bool((x <= K[:, :, 1] * (1 + 1e-12) + 1e-15).all()) and bool((x >= K[:, :, 0] - 1e-15).all())
+    d_grid = inst.d_grid
+    qs = path.eval_device(d_grid, 1)
+    qss = path.eval_device(d_grid, 2)
+    # joint accelerations q' u + q'' x within limits at every stage (u constant on the stage)
+    acc = qs[:, :-1] * u[:, :, None] + qss[:, :-1] * x[:, :-1, None]
+    amax = torch.as_tensor(alim[:, None, :, 1], device=acc.device)
+    assert float((acc.abs() - amax).max()) < 1e-6
+    vel = qs * sd[:, :, None]
+    vmax = torch.as_tensor(vlim[:, None, :, 1], device=vel.device)
+    assert float((vel.abs() - vmax).max()) < 1e-6
+    # dynamics consistency: x_{i+1} <= x_i + 2 ds u_i (equality before the safety shrink 1e-8 / 0.9999)
+    ds = d_grid[1:] - d_grid[:-1]
+    xn = x[:, :-1] + 2 * ds * u
+    assert float((x[:, 1:] - xn).max()) <= 1e-12
+    assert float((xn - x[:, 1:]).max()) <= 1e-4 * float(xn.max()) + 2e-8
+    # determinism + independence of batch composition: first 256 paths alone give identical bits
+    _, _, res2 = _solve(ta, ss, way[:256], vlim[:256], alim[:256], grid)
+    assert torch.equal(res2.sd, sd[:256]) and torch.equal(res2.K, K[:256])

@@ -16,7 +16,9 @@ _PROTOS = {
     "tb_last_error": ([], ctypes.c_char_p),
     "tb_limits": ([ctypes.POINTER(_int), ctypes.POINTER(_int)], _int),
     "tb_record_doubles": ([_int], _int),
-    "tb_spline_fit": ([_c_dp, _int, _c_dp, _int, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, ctypes.c_void_p], _int),
+    "tb_spline_fit_workspace_doubles": ([_int, _int, _int], _int),
+    "tb_spline_fit": ([_c_dp, _int, _c_dp, _int, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, ctypes.c_void_p],
+                      _int),
     "tb_ppoly_eval": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_coeff_velacc": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _c_dp, _int, _int, _c_dp,
                          _int, _int, _int, _int, ctypes.c_void_p], _int),
@@ -27,6 +29,10 @@ _PROTOS = {
                  ctypes.c_void_p], _int),
     "tb_scan_ex": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, _c_dp, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_ip,
                     _c_ip, _c_ip, ctypes.c_void_p], _int),
+    "tb_lp2d_batch": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_ip, _int, _int, _c_ip, _c_dp, _c_dp, _c_ip,
+                       ctypes.c_void_p], _int),
+    "tb_lp1d_batch": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _c_ip, _c_dp, _c_dp, _c_ip, ctypes.c_void_p],
+                      _int),
     "tb_feasible_sets": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_solve_velacc_host": ([_int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _int, _int, _c_dp,
                               _c_dp, _c_dp, _c_dp, _c_dp, _c_ip], _int),

@@ -31,7 +31,7 @@ extern "C" int tb_version(void) { return TB_VERSION; }
 extern "C" const char *tb_last_error(void) { return tb::g_err; }
 extern "C" int tb_limits(int *max_rows, int *max_knots) {
   if (max_rows) *max_rows = tb::MAX_ROWS;
-  if (max_knots) *max_knots = tb::MAX_KNOTS;
+  if (max_knots) *max_knots = 1 << 20;  // limited by the caller-provided workspace only
   return 0;
 }
 
@@ -67,6 +67,9 @@ extern "C" int tb_solve_velacc_host(int device, const double *ss, const double *
   const size_t o_s0 = take(sizeof(double) * B), o_s1 = take(sizeof(double) * B);
   const size_t o_pp = take(sizeof(double) * (size_t)B * 4 * nseg * dof);
   const size_t o_rec = take(sizeof(double) * (size_t)B * G * W);
+  const int ws_doubles = tb_spline_fit_workspace_doubles(B, n, dof);
+  if (ws_doubles < 0) { set_error("tb_solve_velacc_host: spline too large"); return ws_doubles; }
+  const size_t o_ws = take(sizeof(double) * (size_t)(ws_doubles > 0 ? ws_doubles : 1));
   const size_t o_K = take(sizeof(double) * (size_t)B * G * 2), o_sd = take(sizeof(double) * (size_t)B * G);
   const size_t o_u = take(sizeof(double) * (size_t)B * (G > 1 ? G - 1 : 1)), o_st = take(sizeof(int) * (size_t)B);
   char *d = nullptr;
@@ -82,7 +85,7 @@ extern "C" int tb_solve_velacc_host(int device, const double *ss, const double *
   if (sd_start) TB_CUDA(cudaMemcpyAsync(d + o_s0, sd_start, sizeof(double) * B, cudaMemcpyHostToDevice, st));
   if (sd_end) TB_CUDA(cudaMemcpyAsync(d + o_s1, sd_end, sizeof(double) * B, cudaMemcpyHostToDevice, st));
   rc = tb_spline_fit((double *)(d + o_ss), 1, (double *)(d + o_wp), B, n, dof, TB_BC_NOT_A_KNOT, nullptr,
-                     TB_BC_NOT_A_KNOT, nullptr, (double *)(d + o_pp), st);
+                     TB_BC_NOT_A_KNOT, nullptr, (double *)(d + o_pp), ws_doubles > 0 ? (double *)(d + o_ws) : nullptr, st);
   if (rc) goto done;
   rc = tb_coeff_velacc((double *)(d + o_pp), (double *)(d + o_ss), 1, B, nseg, dof, (double *)(d + o_grid), 1, G,
                        vlim ? (double *)(d + o_vl) : nullptr, (double *)(d + o_al), lim_shared, interp,

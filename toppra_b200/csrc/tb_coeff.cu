@@ -20,6 +20,13 @@ namespace {
 constexpr int COEFF_THREADS = 256;
 constexpr int COEFF_CH = 32;  // gridpoints per CTA
 
+__device__ __forceinline__ int R_total_or1(int R_total) { return R_total > 0 ? R_total : 1; }
+
+// Shared-memory plan of one CTA (dof = d, VS = 6d + 3 doubles per gridpoint):
+//   raw  [(CH+1)][2d]   q'(s_i), q''(s_i) of the chunk (+1 gridpoint for the lift)
+//   vec  [CH][VS]       per gridpoint: q' | a+ | q'' | b+ | -amax | +amin | xlo | xhi | 0
+//   tab  [W]            per record column: offset into vec (bit 15 = negate, 0x7fff = column not owned)
+// Phase 2 then only does  rec[col] = +-vec[ci][tab[col]]  with 16-byte stores: no divisions, fully coalesced.
 __global__ void __launch_bounds__(COEFF_THREADS)
 coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks, const int breaks_shared,
                     const int nseg, const int dof, const double *__restrict__ grid, const int grid_shared, const int G,
@@ -27,9 +34,11 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
                     const int interp, double *__restrict__ records, const int W, const int R_total, const int row0,
                     const int write_xbound, const int nchunks) {
   extern __shared__ double sm[];
-  double *qs = sm;                                 // [(CH+1)][dof]
-  double *qss = sm + (COEFF_CH + 1) * dof;         // [(CH+1)][dof]
-  double *sgrid = qss + (COEFF_CH + 1) * dof;      // [CH+1]
+  const int VS = 6 * dof + 3;
+  double *raw = sm;                                  // [(CH+1)][2*dof]
+  double *vec = raw + (COEFF_CH + 1) * 2 * dof;      // [CH][VS]
+  double *sgrid = vec + COEFF_CH * VS;               // [CH+1]
+  unsigned short *tab = reinterpret_cast<unsigned short *>(sgrid + COEFF_CH + 1);  // [W]
   const long path = blockIdx.x / nchunks;
   const int chunk = blockIdx.x % nchunks;
   const int i0 = chunk * COEFF_CH;
@@ -39,8 +48,12 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
   const double *c = ppoly + path * 4 * nseg * dof;
   const double *x = breaks + (breaks_shared ? 0 : path * (nseg + 1));
   const double *gp = grid + (grid_shared ? 0 : path * G);
+  const double *al = alim ? alim + (lim_shared ? 0 : path * dof * 2) : nullptr;
+  const double *vl = vlim ? vlim + (lim_shared ? 0 : path * dof * 2) : nullptr;
   const int tid = threadIdx.x;
+  const int Racc = al ? (interp ? 4 : 2) * dof : 0;
 
+  // ---- phase 1: q', q'' at the chunk's gridpoints; column table ----
   for (int idx = tid; idx < nev * dof; idx += COEFF_THREADS) {
     const int ci = idx / dof, k = idx - ci * dof;
     const double s = gp[i0 + ci];
@@ -53,24 +66,53 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
       v1 = ppoly_eval1(c, nseg, dof, seg, k, ds, 1);
       v2 = ppoly_eval1(c, nseg, dof, seg, k, ds, 2);
     }
-    qs[idx] = v1;
-    qss[idx] = v2;
+    raw[ci * 2 * dof + k] = v1;
+    raw[ci * 2 * dof + dof + k] = v2;
   }
   for (int ci = tid; ci < nev; ci += COEFF_THREADS) sgrid[ci] = gp[i0 + ci];
+  for (int w = tid; w < W; w += COEFF_THREADS) {
+    unsigned short code = 0x7fff;  // not owned by this call: leave untouched
+    const int kind = w / R_total_or1(R_total), r = w - kind * R_total - row0;
+    if (kind < 3 && R_total > 0 && r >= 0 && r < Racc) {
+      const int blk = r / dof, k = r - blk * dof;
+      const int neg = blk & 1, second = blk >> 1;
+      if (kind == 0) code = (unsigned short)((second ? dof + k : k) | (neg << 15));
+      else if (kind == 1) code = (unsigned short)((second ? 3 * dof + k : 2 * dof + k) | (neg << 15));
+      else code = (unsigned short)(neg ? 5 * dof + k : 4 * dof + k);
+    } else if (w >= 3 * R_total) {
+      if (write_xbound) code = (unsigned short)(w == 3 * R_total ? 6 * dof : (w == 3 * R_total + 1 ? 6 * dof + 1 : 6 * dof + 2));
+    }
+    tab[w] = code;
+  }
   __syncthreads();
 
+  // ---- phase 1b: per-gridpoint value vectors ----
+  for (int idx = tid; idx < npts * dof; idx += COEFF_THREADS) {
+    const int ci = idx / dof, k = idx - ci * dof;
+    const int gi = i0 + ci;
+    double *v = vec + ci * VS;
+    const double a = raw[ci * 2 * dof + k], b = raw[ci * 2 * dof + dof + k];
+    double ap = a, bp = b;  // last gridpoint duplicates itself, linear_constraint.py:171,175
+    if (gi < N) {
+      const double delta = sgrid[ci + 1] - sgrid[ci];
+      ap = raw[(ci + 1) * 2 * dof + k] + (2 * delta) * raw[(ci + 1) * 2 * dof + dof + k];  // linear_constraint.py:170
+      bp = raw[(ci + 1) * 2 * dof + dof + k];
+    }
+    v[k] = a; v[dof + k] = ap; v[2 * dof + k] = b; v[3 * dof + k] = bp;
+    if (al) {
+      v[4 * dof + k] = 0.0 - al[k * 2 + 1];       // F.c - g with c = 0, g = [amax; -amin]
+      v[5 * dof + k] = 0.0 - (-al[k * 2 + 0]);
+    }
+  }
   double *rec0 = records + (path * G + i0) * (long)W;
-  const double *al = alim ? alim + (lim_shared ? 0 : path * dof * 2) : nullptr;
-
   // velocity bound -> xbound slots.  fp32 running min/max exactly like _CythonUtils.pyx:41-58.
   if (write_xbound && tid < npts) {
     const int ci = tid;
     double xlo = VAR_MIN, xhi = VAR_MAX;  // seidelWrapper low_arr/high_arr init, pyx:477-478
-    if (vlim) {
-      const double *vl = vlim + (lim_shared ? 0 : path * dof * 2);
+    if (vl) {
       float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
       for (int k = 0; k < dof; ++k) {
-        const double q = qs[ci * dof + k];
+        const double q = raw[ci * 2 * dof + k];
         if (q > 0) {
           const double hi = vl[k * 2 + 1] / q, lo = vl[k * 2 + 0] / q;
           sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
@@ -91,47 +133,37 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
         xhi = fmin(VAR_MAX, xhi);
       }
     }
-    double *rec = rec0 + (long)ci * W;
-    if (write_xbound == 3) {
+    if (write_xbound == 3) {  // intersect with what the record already holds
+      const double *rec = rec0 + (long)ci * W;
       xlo = fmax(rec[3 * R_total], xlo);
       xhi = fmin(rec[3 * R_total + 1], xhi);
     }
-    rec[3 * R_total] = xlo;
-    rec[3 * R_total + 1] = xhi;
-    for (int j = 3 * R_total + 2; j < W; ++j) rec[j] = 0.0;
+    double *v = vec + ci * VS;
+    v[6 * dof] = xlo; v[6 * dof + 1] = xhi; v[6 * dof + 2] = 0.0;
   }
+  __syncthreads();
 
-  // acceleration rows: F = blkdiag([I;-I],[I;-I]), g = [amax;-amin;amax;-amin]  (SURVEY.md §8 a')
-  if (!al) return;  // velocity-only call
-  const int Racc = (interp ? 4 : 2) * dof;
-  const int per_pt = 3 * Racc;
-  for (int o = tid; o < npts * per_pt; o += COEFF_THREADS) {
-    const int ci = o / per_pt;
-    const int rem = o - ci * per_pt;
-    const int kind = rem / Racc;  // 0: a, 1: b, 2: c
-    const int r = rem - kind * Racc;
-    const int blk = r / dof, k = r - blk * dof;
-    const int gi = i0 + ci;
-    double val;
-    if (kind == 2) {
-      val = (blk & 1) ? (0.0 - (-al[k * 2 + 0])) : (0.0 - al[k * 2 + 1]);
+  // ---- phase 2: stream the records out, two columns (16 bytes) per thread and iteration ----
+  const int Wh = W >> 1;
+  const int total = npts * Wh;
+  int ci = tid / Wh, j = tid - ci * Wh;
+  const int dq = COEFF_THREADS / Wh, dr = COEFF_THREADS - dq * Wh;
+  for (int p = tid; p < total; p += COEFF_THREADS) {
+    const unsigned short c0 = tab[2 * j], c1 = tab[2 * j + 1];
+    const double *v = vec + ci * VS;
+    double *dst = rec0 + (long)ci * W + 2 * j;
+    if (c0 != 0x7fff && c1 != 0x7fff) {
+      double2 o;
+      o.x = v[c0 & 0x7fff]; o.y = v[c1 & 0x7fff];
+      if (c0 & 0x8000) o.x = -o.x;
+      if (c1 & 0x8000) o.y = -o.y;
+      *reinterpret_cast<double2 *>(dst) = o;
     } else {
-      double base;
-      if (blk < 2) {
-        base = (kind == 0) ? qs[ci * dof + k] : qss[ci * dof + k];
-      } else if (gi < N) {
-        if (kind == 0) {
-          const double delta = sgrid[ci + 1] - sgrid[ci];
-          base = qs[(ci + 1) * dof + k] + (2 * delta) * qss[(ci + 1) * dof + k];  // linear_constraint.py:170
-        } else {
-          base = qss[(ci + 1) * dof + k];
-        }
-      } else {  // last gridpoint duplicates itself, linear_constraint.py:171,175
-        base = (kind == 0) ? qs[ci * dof + k] : qss[ci * dof + k];
-      }
-      val = (blk & 1) ? -base : base;
+      if (c0 != 0x7fff) { const double t = v[c0 & 0x7fff]; dst[0] = (c0 & 0x8000) ? -t : t; }
+      if (c1 != 0x7fff) { const double t = v[c1 & 0x7fff]; dst[1] = (c1 & 0x8000) ? -t : t; }
     }
-    rec0[(long)ci * W + kind * R_total + row0 + r] = val;
+    ci += dq; j += dr;
+    if (j >= Wh) { j -= Wh; ++ci; }
   }
 }
 
@@ -224,8 +256,13 @@ extern "C" int tb_coeff_velacc(const double *ppoly, const double *breaks, int br
   const int nchunks = (G + COEFF_CH - 1) / COEFF_CH;
   const long blocks = (long)B * nchunks;
   if (blocks > 0x7fffffffL) { set_error("tb_coeff_velacc: batch too large for one launch"); return TB_ERR_UNSUPPORTED; }
-  const size_t smem = (size_t)((COEFF_CH + 1) * dof * 2 + COEFF_CH + 1) * sizeof(double);
-  if (smem > 48 * 1024) { set_error("tb_coeff_velacc: dof=%d too large", dof); return TB_ERR_UNSUPPORTED; }
+  if (6 * dof + 3 >= 0x7fff) { set_error("tb_coeff_velacc: dof=%d too large", dof); return TB_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)((COEFF_CH + 1) * dof * 2 + COEFF_CH * (6 * dof + 3) + COEFF_CH + 1) * sizeof(double) +
+                      (size_t)W * sizeof(unsigned short) + 16;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(coeff_velacc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tb_coeff_velacc: dof=%d too large for shared memory", dof); return TB_ERR_UNSUPPORTED; }
+  }
   coeff_velacc_kernel<<<(unsigned)blocks, COEFF_THREADS, smem, (cudaStream_t)stream>>>(
       ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, vlim, alim, lim_shared, interp, records, W,
       R_total, row0, write_xbound, nchunks);

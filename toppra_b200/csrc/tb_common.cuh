@@ -22,7 +22,6 @@ constexpr double JVEL_MAXSD = 1e8;
 constexpr double CVXPY_MAXX = 10000.0;
 
 constexpr int MAX_ROWS = 126;   // R <= 126 -> nC = R + 2 <= 128 = 4 rows per lane
-constexpr int MAX_KNOTS = 64;   // spline knots per path handled by the fit kernel
 
 constexpr unsigned FULL = 0xffffffffu;
 

@@ -18,6 +18,7 @@
 // mbarrier complete_tx), double-buffered one stage ahead of the solve.
 // Compiled with -fmad=false: no FMA contraction, same roundings as the x86-64 reference.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "tb_common.cuh"
 
@@ -54,15 +55,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   } while (!ok);
 }
 
+// Order-preserving map double -> uint64 (no NaN inputs): a < b  <=>  dkey(a) < dkey(b)  (and -0.0 < +0.0).
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  const long long b = __double_as_longlong(v);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  long long b = (long long)k;
+  b ^= ((~b) >> 63) | (long long)0x8000000000000000ULL;
+  return __longlong_as_double(b);
+}
+// Warp-wide min / max of doubles (no NaNs) with two 32-bit redux.sync each instead of five shuffle rounds:
+// first the high words of the ordered keys, then the low words among the lanes that tie on the high word.
 __device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
-  return v;
+  const unsigned long long k = dkey(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(FULL, hi);
+  const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+  return dunkey(((unsigned long long)mh << 32) | ml);
 }
 __device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-  return v;
+  const unsigned long long k = dkey(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_max_sync(FULL, hi);
+  const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+  return dunkey(((unsigned long long)mh << 32) | ml);
 }
 
 // Position of LP row r in Seidel's processing order, cy_seidel_solverwrapper.pyx:252-264:
@@ -86,10 +103,29 @@ __device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
 
 constexpr int BOXBASE = 1 << 20;
 
+// One projected constraint of the 1-D sub-problem (pyx:326-347): classify and compute its limit on t.
+//   cls 1: t <= tt (denom > TINY), cls 2: t >= tt (denom < -TINY), cls 0: dropped; bad: parallel & infeasible.
+__device__ __forceinline__ void project_item(const bool part, const double aj, const double bj, const double cj,
+                                             const double dt0, const double dt1, const double z0, const double z1,
+                                             int &cls, double &tt, bool &bad) {
+  const double denom = dt0 * aj + dt1 * bj;
+  const double num = cj + z1 * bj + z0 * aj;
+  const bool up = denom > LP_TINY, dn = denom < -LP_TINY;
+  const double t = -num / denom;  // unconditional: no divergence; discarded unless up|dn
+  const bool usable = part && (up || dn) && (t == t);  // a NaN limit never updates the running min/max (pyx:115-124)
+  cls = usable ? (up ? 1 : 2) : 0;
+  tt = t;
+  bad = bad || (part && !(up || dn) && (num > LP_SMALL));
+}
+
 // cy_solve_lp2d (pyx:149-390) on one warp.  Lane `lane` holds LP rows r = lane + 32*s, s < RPL
 // (padding rows must be (0, 0, -1)).  maximise v0*u + v1*x  s.t.  a u + b x + c <= 0, low <= (u,x) <= high.
 // ac0/ac1: in = warm-start pair (active_c of the previous solve of this slot), out = new active pair
 // (updated only when feasible, like pyx:673-676,690-691).  Returns false when infeasible.
+//
+// Per violated row k (one "re-solve"): the earlier rows and the four box rows are projected onto line k, one item
+// per lane.  The box rows ride on lanes whose own row does not take part in this re-solve (rows at or after k,
+// padding lanes); only if fewer than four such lanes exist they fall back to an extra item slot.
 template <int RPL>
 __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL], const int nC,
@@ -108,16 +144,16 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
     const int r = lane + 32 * s;
     pos[s] = (r < nC) ? row_pos(r, valid, ac0, ac1) : INT_MAX;
   }
+  const unsigned lt_mask = (1u << lane) - 1u;
   int kpos = -1;
-  constexpr int IPL = RPL + 1;  // item slots per lane: nC rows + 4 box rows <= 32 * IPL
-  const int nitems = nC + 4;
   while (true) {
     // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
     int mypos = INT_MAX;
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
       const double val = a[s] * p0 + b[s] * p1 + c[s];
-      if (!(val < LP_TINY) && pos[s] > kpos && pos[s] != INT_MAX) mypos = min(mypos, pos[s]);
+      const bool cand = !(val < LP_TINY) && (pos[s] > kpos) && (pos[s] != INT_MAX);
+      mypos = cand ? min(mypos, pos[s]) : mypos;
     }
     const int knew = __reduce_min_sync(FULL, mypos);
     if (knew == INT_MAX) break;
@@ -133,54 +169,53 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
     ak = __shfl_sync(FULL, ak, krow & 31);
     bk = __shfl_sync(FULL, bk, krow & 31);
     ck = __shfl_sync(FULL, ck, krow & 31);
-    // project the origin onto line k, pyx:290-295
+    // project the origin onto line k, pyx:290-295: z = (-a c, -b c) / (a^2 + b^2).  One division sequence for
+    // both components: odd lanes divide the second numerator.
     const double nrm = ak * ak + bk * bk;
-    const double z0 = (-ak * ck) / nrm;
-    const double z1 = (-bk * ck) / nrm;
+    const double zq = ((lane & 1) ? (-bk * ck) : (-ak * ck)) / nrm;
+    const double z0 = __shfl_sync(FULL, zq, 0);
+    const double z1 = __shfl_sync(FULL, zq, 1);
     const double dt0 = -bk, dt1 = ak;
     const double v1d = dt0 * v0 + dt1 * v1;
     // project the earlier rows and the four box rows onto the line, pyx:298-347
-    double tt[IPL];
-    int cls[IPL], key[IPL];
+    double tt[RPL + 1];
+    int cls[RPL + 1], key[RPL + 1];
     bool bad = false;
+    const bool idle0 = !(pos[0] < kpos);  // this lane's slot-0 row does not take part (row k, later rows, padding)
+    const unsigned idle = __ballot_sync(FULL, idle0);
+    const bool box_inline = __popc(idle) >= 4;  // warp-uniform
+    {
+      // slot 0: own row, or (on the first four idle lanes) box row m = rank
+      const int rank = __popc(idle & lt_mask);
+      const bool isbox = box_inline && idle0 && rank < 4;
+      const int m = rank;  // 0: low0 <= u, 1: u <= high0, 2: low1 <= x, 3: x <= high1
+      const double ba = (m == 0) ? -1.0 : ((m == 1) ? 1.0 : 0.0);
+      const double bb = (m == 2) ? -1.0 : ((m == 3) ? 1.0 : 0.0);
+      const double bc = (m == 0) ? low0 : ((m == 1) ? -high0 : ((m == 2) ? low1 : -high1));
+      const double aj = isbox ? ba : a[0], bj = isbox ? bb : b[0], cj = isbox ? bc : c[0];
+      key[0] = isbox ? BOXBASE + m : pos[0];
+      project_item(isbox || !idle0, aj, bj, cj, dt0, dt1, z0, z1, cls[0], tt[0], bad);
+    }
 #pragma unroll
-    for (int s = 0; s < IPL; ++s) {
-      cls[s] = 0; tt[s] = 0.0; key[s] = INT_MAX;
-      if (32 * s >= nitems) continue;  // warp-uniform
-      const int it = lane + 32 * s;
-      const int sa = (s < RPL) ? s : RPL - 1;
-      double aj, bj, cj;
-      bool part;
-      if (s < RPL && it < nC) {
-        aj = a[sa]; bj = b[sa]; cj = c[sa];
-        part = pos[sa] < kpos;
-        key[s] = pos[sa];
-      } else {
-        const int m = it - nC;  // 0: low0 <= u, 1: u <= high0, 2: low1 <= x, 3: x <= high1
-        part = (m >= 0) && (m < 4);
-        aj = (m == 0) ? -1.0 : ((m == 1) ? 1.0 : 0.0);
-        bj = (m == 2) ? -1.0 : ((m == 3) ? 1.0 : 0.0);
-        cj = (m == 0) ? low0 : ((m == 1) ? -high0 : ((m == 2) ? low1 : -high1));
-        key[s] = BOXBASE + m;
-      }
-      if (part) {
-        const double denom = dt0 * aj + dt1 * bj;
-        const double num = cj + z1 * bj + z0 * aj;
-        if (denom > LP_TINY) {
-          cls[s] = 1; tt[s] = -num / denom;   // t <= tt
-        } else if (denom < -LP_TINY) {
-          cls[s] = 2; tt[s] = -num / denom;   // t >= tt
-        } else if (num > LP_SMALL) {
-          bad = true;                          // parallel and infeasible, pyx:342-344
-        }
-      }
+    for (int s = 1; s < RPL; ++s) {
+      key[s] = pos[s];
+      project_item(pos[s] < kpos, a[s], b[s], c[s], dt0, dt1, z0, z1, cls[s], tt[s], bad);
+    }
+    cls[RPL] = 0; tt[RPL] = 0.0; key[RPL] = INT_MAX;
+    if (!box_inline) {  // rare: (almost) every row takes part -> box rows in an extra slot on lanes 0..3
+      const int m = lane;
+      const double ba = (m == 0) ? -1.0 : ((m == 1) ? 1.0 : 0.0);
+      const double bb = (m == 2) ? -1.0 : ((m == 3) ? 1.0 : 0.0);
+      const double bc = (m == 0) ? low0 : ((m == 1) ? -high0 : ((m == 2) ? low1 : -high1));
+      key[RPL] = BOXBASE + m;
+      project_item(m < 4, ba, bb, bc, dt0, dt1, z0, z1, cls[RPL], tt[RPL], bad);
     }
     // 1-D LP on the line with bounds +-INF, pyx:350 -> cy_solve_lp1d pyx:93-144
     double my_hi = LP_INF, my_lo = -LP_INF;
 #pragma unroll
-    for (int s = 0; s < IPL; ++s) {
-      if (cls[s] == 1) my_hi = fmin(my_hi, tt[s]);
-      if (cls[s] == 2) my_lo = fmax(my_lo, tt[s]);
+    for (int s = 0; s <= RPL; ++s) {
+      my_hi = (cls[s] == 1 && tt[s] < my_hi) ? tt[s] : my_hi;
+      my_lo = (cls[s] == 2 && tt[s] > my_lo) ? tt[s] : my_lo;
     }
     const double cur_max = warp_min(my_hi);
     const double cur_min = warp_max(my_lo);
@@ -193,8 +228,7 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
     const int want = pick_min ? 2 : 1;
     int mykey = INT_MAX;
 #pragma unroll
-    for (int s = 0; s < IPL; ++s)
-      if (cls[s] == want && tt[s] == tstar) mykey = min(mykey, key[s]);
+    for (int s = 0; s <= RPL; ++s) mykey = (cls[s] == want && tt[s] == tstar) ? min(mykey, key[s]) : mykey;
     const int akey = __reduce_min_sync(FULL, mykey);
     nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
     p0 = z0 + tstar * dt0;  // pyx:362-363
@@ -217,11 +251,10 @@ __device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double 
 #pragma unroll
   for (int s = 0; s < RPL; ++s) {
     const double bxc = b[s] * x + c[s];
-    if (a[s] > LP_TINY) {
-      my_hi = fmin(my_hi, -bxc / a[s]);
-    } else if (a[s] < -LP_TINY) {
-      my_lo = fmax(my_lo, -bxc / a[s]);
-    }
+    const bool up = a[s] > LP_TINY, dn = a[s] < -LP_TINY;
+    const double t = -bxc / a[s];
+    my_hi = (up && t < my_hi) ? t : my_hi;
+    my_lo = (dn && t > my_lo) ? t : my_lo;
   }
   const double cur_max = warp_min(my_hi);
   const double cur_min = warp_max(my_lo);
@@ -257,8 +290,8 @@ __device__ __forceinline__ void set_xnext_rows(const int lane, const double delt
   if (lane == 1) { a[0] = 2 * delta; b[0] = 1.0; c[0] = -xn_max; }
 }
 
-template <int RPL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int RPL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
             const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
             const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags,
@@ -464,6 +497,82 @@ feasible_kernel(const double *__restrict__ records, const int W, const int R, co
   }
 }
 
+// Batched stand-alone LPs (one warp per LP): the device counterparts of the reference's Python shims
+// solve_lp2d / solve_lp1d (cy_seidel_solverwrapper.pyx:42-87).  Used by B200SolverWrapper.solve_stagewise_optim
+// and by the LP-level known-answer / differential tests.
+template <int RPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+lp2d_batch_kernel(const double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ b,
+                  const double *__restrict__ c, const double *__restrict__ low, const double *__restrict__ high,
+                  const int *__restrict__ active_in, const int B, const int n, int *__restrict__ result,
+                  double *__restrict__ optval, double *__restrict__ optvar, int *__restrict__ active_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long p = (long)blockIdx.x * WARPS + warp;
+  if (p >= B) return;
+  double ra[RPL], rb[RPL], rc[RPL];
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const int r = lane + 32 * s;
+    if (r < n) { ra[s] = a[p * n + r]; rb[s] = b[p * n + r]; rc[s] = c[p * n + r]; }
+    else { ra[s] = 0.0; rb[s] = 0.0; rc[s] = -1.0; }
+  }
+  int ac0 = active_in ? active_in[p * 2] : 0, ac1 = active_in ? active_in[p * 2 + 1] : 0;
+  int n_resolve = 0;
+  double uu = 0.0, xx = 0.0;
+  const double v0 = v[p * 3], v1 = v[p * 3 + 1], v2 = v[p * 3 + 2];
+  const bool ok = lp2d_warp<RPL>(v0, v1, ra, rb, rc, n, low[p * 2], high[p * 2], low[p * 2 + 1], high[p * 2 + 1], ac0,
+                                 ac1, uu, xx, lane, n_resolve);
+  if (lane == 0) {
+    result[p] = ok ? 1 : 0;
+    const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+    optvar[p * 2] = ok ? uu : nan_d;
+    optvar[p * 2 + 1] = ok ? xx : nan_d;
+    optval[p] = ok ? (uu * v0 + xx * v1 + v2) : nan_d;  // pyx:389
+    active_out[p * 2] = ac0;
+    active_out[p * 2 + 1] = ac1;
+  }
+}
+
+// cy_solve_lp1d with the active index (pyx:93-144): max v0 x + v1, a x + b <= 0, low <= x <= high.
+__global__ void lp1d_batch_kernel(const double *__restrict__ v, const double *__restrict__ a,
+                                  const double *__restrict__ b, const double *__restrict__ low,
+                                  const double *__restrict__ high, const int B, const int n,
+                                  int *__restrict__ result, double *__restrict__ optval,
+                                  double *__restrict__ optvar, int *__restrict__ active_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long p = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (p >= B) return;
+  double my_hi = high[p], my_lo = low[p];
+  int hi_idx = INT_MAX, lo_idx = INT_MAX;  // first row index attaining the bound (strict improvement only)
+  for (int r = lane; r < n; r += 32) {
+    const double ar = a[p * n + r], br = b[p * n + r];
+    if (ar > LP_TINY) {
+      const double cx = -br / ar;
+      if (cx < my_hi) { my_hi = cx; hi_idx = r; }
+    } else if (ar < -LP_TINY) {
+      const double cx = -br / ar;
+      if (cx > my_lo) { my_lo = cx; lo_idx = r; }
+    }
+  }
+  const double cur_max = warp_min(my_hi), cur_min = warp_max(my_lo);
+  // sequential semantics: the first row (lowest index) that reaches the final value wins; -2/-1 if none improved
+  int hk = (hi_idx != INT_MAX && my_hi == cur_max) ? hi_idx : INT_MAX;
+  int lk = (lo_idx != INT_MAX && my_lo == cur_min) ? lo_idx : INT_MAX;
+  hk = __reduce_min_sync(FULL, hk);
+  lk = __reduce_min_sync(FULL, lk);
+  if (lane == 0) {
+    const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+    const double v0 = v[p * 2], v1 = v[p * 2 + 1];
+    if (cur_min > cur_max) {
+      result[p] = 0; optval[p] = nan_d; optvar[p] = nan_d; active_out[p] = 0;
+    } else if (fabs(v0) < LP_TINY || v0 < 0) {
+      result[p] = 1; optvar[p] = cur_min; optval[p] = v0 * cur_min + v1; active_out[p] = (lk == INT_MAX) ? -1 : lk;
+    } else {
+      result[p] = 1; optvar[p] = cur_max; optval[p] = v0 * cur_max + v1; active_out[p] = (hk == INT_MAX) ? -2 : hk;
+    }
+  }
+}
+
 constexpr int SCAN_WARPS = 4;
 
 template <int RPL>
@@ -471,7 +580,11 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
                 const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
                 double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
   const size_t smem = (size_t)SCAN_WARPS * 2 * W * sizeof(double) + SCAN_WARPS * 2 * sizeof(uint64_t);
-  auto kern = scan_kernel<RPL, SCAN_WARPS>;
+  // Two register budgets for the common nC <= 32 case: 7 CTAs/SM (72 regs, 28 warps/SM: the 4096-path batch of
+  // BASELINE cfg 2 fits one wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
+  static const char *occ_env = getenv("TB_SCAN_OCC");
+  const bool dense = occ_env ? (occ_env[0] == 'd') : true;
+  auto kern = (RPL == 1 && dense) ? scan_kernel<RPL, SCAN_WARPS, (RPL == 1 ? 7 : 1)> : scan_kernel<RPL, SCAN_WARPS, 1>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -536,4 +649,39 @@ extern "C" int tb_feasible_sets(const double *records, int W, int R, const doubl
   if (nC <= 64) return launch_feasible<2>(records, W, R, grid, grid_shared, B, G, X, s);
   if (nC <= 96) return launch_feasible<3>(records, W, R, grid, grid_shared, B, G, X, s);
   return launch_feasible<4>(records, W, R, grid, grid_shared, B, G, X, s);
+}
+
+extern "C" int tb_lp2d_batch(const double *v, const double *a, const double *b, const double *c, const double *low,
+                             const double *high, const int *active_in, int B, int n, int *result, double *optval,
+                             double *optvar, int *active_out, void *stream) {
+  using namespace tb;
+  if (!v || !low || !high || !result || !optval || !optvar || !active_out || B <= 0 || n < 0 || (n > 0 && (!a || !b || !c))) {
+    set_error("tb_lp2d_batch: bad argument");
+    return TB_ERR_ARG;
+  }
+  if (n > MAX_ROWS + 2) { set_error("tb_lp2d_batch: n=%d > %d rows", n, MAX_ROWS + 2); return TB_ERR_UNSUPPORTED; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+#define TB_LAUNCH_LP2D(RPL) \
+  lp2d_batch_kernel<RPL, SCAN_WARPS><<<blocks, SCAN_WARPS * 32, 0, s>>>(v, a, b, c, low, high, active_in, B, n, result, optval, optvar, active_out)
+  if (n <= 32) TB_LAUNCH_LP2D(1);
+  else if (n <= 64) TB_LAUNCH_LP2D(2);
+  else if (n <= 96) TB_LAUNCH_LP2D(3);
+  else TB_LAUNCH_LP2D(4);
+#undef TB_LAUNCH_LP2D
+  return check_launch("tb_lp2d_batch");
+}
+
+extern "C" int tb_lp1d_batch(const double *v, const double *a, const double *b, const double *low, const double *high,
+                             int B, int n, int *result, double *optval, double *optvar, int *active_out,
+                             void *stream) {
+  using namespace tb;
+  if (!v || !low || !high || !result || !optval || !optvar || !active_out || B <= 0 || n < 0 || (n > 0 && (!a || !b))) {
+    set_error("tb_lp1d_batch: bad argument");
+    return TB_ERR_ARG;
+  }
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+  lp1d_batch_kernel<<<blocks, SCAN_WARPS * 32, 0, (cudaStream_t)stream>>>(v, a, b, low, high, B, n, result, optval, optvar,
+                                                                         active_out);
+  return check_launch("tb_lp1d_batch");
 }

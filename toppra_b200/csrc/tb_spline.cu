@@ -15,6 +15,8 @@ namespace tb {
 
 namespace {
 
+constexpr int LOCAL_KNOTS = 16;  // splines up to this many knots are fitted entirely in thread-local storage
+
 __global__ void ppoly_eval_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks,
                                   const int breaks_shared, const long B, const int nseg, const int dof,
                                   const double *__restrict__ s, const int s_shared, const int G, const int order,
@@ -68,7 +70,8 @@ __device__ void dgtsv_like(const int n, double *dl, double *d, double *du, doubl
 __global__ void spline_fit_kernel(const double *__restrict__ ss, const int ss_shared, const double *__restrict__ wp,
                                   const long B, const int n, const int dof, const int bc0_kind,
                                   const double *__restrict__ bc0, const int bc1_kind,
-                                  const double *__restrict__ bc1, double *__restrict__ ppoly) {
+                                  const double *__restrict__ bc1, double *__restrict__ ppoly,
+                                  double *__restrict__ workspace) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * dof) return;
   const int k = (int)(idx % dof);
@@ -77,7 +80,14 @@ __global__ void spline_fit_kernel(const double *__restrict__ ss, const int ss_sh
   const double *y = wp + p * n * dof;
   double *c = ppoly + p * 4 * (n - 1) * dof;
   const int nseg = n - 1;
-  double dx[MAX_KNOTS], slope[MAX_KNOTS], s[MAX_KNOTS], dl[MAX_KNOTS], dd[MAX_KNOTS], du[MAX_KNOTS];
+  // scratch: thread-local arrays for short splines, caller workspace [B*dof][6][n] for long ones
+  double l_dx[LOCAL_KNOTS], l_slope[LOCAL_KNOTS], l_s[LOCAL_KNOTS], l_dl[LOCAL_KNOTS], l_dd[LOCAL_KNOTS],
+      l_du[LOCAL_KNOTS];
+  double *dx = l_dx, *slope = l_slope, *s = l_s, *dl = l_dl, *dd = l_dd, *du = l_du;
+  if (n > LOCAL_KNOTS) {
+    double *w = workspace + idx * 6 * (long)n;
+    dx = w; slope = w + n; s = w + 2 * (long)n; dl = w + 3 * (long)n; dd = w + 4 * (long)n; du = w + 5 * (long)n;
+  }
   for (int i = 0; i < nseg; ++i) {
     dx[i] = x[i + 1] - x[i];
     slope[i] = (y[(i + 1) * dof + k] - y[i * dof + k]) / dx[i];
@@ -151,17 +161,29 @@ __global__ void spline_fit_kernel(const double *__restrict__ ss, const int ss_sh
 }  // namespace
 }  // namespace tb
 
+extern "C" int tb_spline_fit_workspace_doubles(int B, int n, int dof) {
+  if (B <= 0 || n < 2 || dof <= 0) return TB_ERR_ARG;
+  if (n <= tb::LOCAL_KNOTS) return 0;
+  const long need = (long)B * dof * 6 * n;
+  return need > 0x7fffffffL ? TB_ERR_UNSUPPORTED : (int)need;
+}
+
 extern "C" int tb_spline_fit(const double *ss, int ss_shared, const double *wp, int B, int n, int dof, int bc0_kind,
-                             const double *bc0, int bc1_kind, const double *bc1, double *ppoly, void *stream) {
+                             const double *bc0, int bc1_kind, const double *bc1, double *ppoly, double *workspace,
+                             void *stream) {
   using namespace tb;
   if (!ss || !wp || !ppoly || B <= 0 || dof <= 0) { set_error("tb_spline_fit: bad argument"); return TB_ERR_ARG; }
-  if (n < 2 || n > MAX_KNOTS) { set_error("tb_spline_fit: n=%d outside [2,%d]", n, MAX_KNOTS); return TB_ERR_UNSUPPORTED; }
+  if (n < 2) { set_error("tb_spline_fit: n=%d < 2", n); return TB_ERR_ARG; }
+  if (n > LOCAL_KNOTS && !workspace) {
+    set_error("tb_spline_fit: n=%d > %d needs a workspace of tb_spline_fit_workspace_doubles() doubles", n, LOCAL_KNOTS);
+    return TB_ERR_ARG;
+  }
   if (bc0_kind < 0 || bc0_kind > 2 || bc1_kind < 0 || bc1_kind > 2) { set_error("tb_spline_fit: bad bc kind"); return TB_ERR_ARG; }
   const long total = (long)B * dof;
   const int threads = 128;
   const long blocks = (total + threads - 1) / threads;
   spline_fit_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(ss, ss_shared, wp, B, n, dof, bc0_kind, bc0,
-                                                                           bc1_kind, bc1, ppoly);
+                                                                           bc1_kind, bc1, ppoly, workspace);
   return check_launch("tb_spline_fit");
 }
 

@@ -62,9 +62,13 @@ def spline_fit(ss, wp, bc=((0, None), (0, None))):
     B, n, dof = wp.shape
     ppoly = torch.empty((B, 4, n - 1, dof), dtype=torch.float64, device=wp.device)
     (k0, v0), (k1, v1) = bc
+    nws = lib.tb_spline_fit_workspace_doubles(B, n, dof)
+    if nws < 0:
+        raise ValueError("spline_fit: batch too large for one call (B=%d, n=%d, dof=%d)" % (B, n, dof))
+    ws = torch.empty((nws,), dtype=torch.float64, device=wp.device) if nws > 0 else None
     with torch.cuda.device(wp.device):
         rc = lib.tb_spline_fit(_lib.ptr(ss), 1 if ss.dim() == 1 else 0, _lib.ptr(wp), B, n, dof, k0, _lib.ptr(v0), k1,
-                               _lib.ptr(v1), _lib.ptr(ppoly), _lib.stream_ptr())
+                               _lib.ptr(v1), _lib.ptr(ppoly), _lib.ptr(ws), _lib.stream_ptr())
     _lib.check(rc, "tb_spline_fit")
     return ppoly
 
@@ -206,3 +210,48 @@ def solve_velacc_host(ss, wp, grid, vlim, alim, interp=True, sd_start=None, sd_e
                                   hp(status))
     _lib.check(rc, "tb_solve_velacc_host")
     return dict(K=K, sd=sd, u=u[:, :G - 1], status=status)
+
+
+def lp2d_batch(v, a, b, c, low, high, active_c=None):
+    """Batched 2-variable LPs on device (tb_lp2d_batch).  Inputs numpy or tensors: v [B,3], a/b/c [B,n],
+    low/high [B,2], active_c [B,2] int.  Returns numpy (result [B], optval [B], optvar [B,2], active [B,2])."""
+    torch = torch_mod()
+    dev = default_device()
+    v = as_device(v, dev)
+    B = v.shape[0]
+    a, b, c = (as_device(t, dev).reshape(B, -1) for t in (a, b, c))
+    n = a.shape[1]
+    low, high = as_device(low, dev), as_device(high, dev)
+    act = None if active_c is None else as_device(np.asarray(active_c), dev, torch.int32)
+    result = torch.empty((B,), dtype=torch.int32, device=dev)
+    optval = torch.empty((B,), dtype=torch.float64, device=dev)
+    optvar = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    active = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_lp2d_batch(_lib.ptr(v), _lib.ptr(a) if n else None, _lib.ptr(b) if n else None,
+                                       _lib.ptr(c) if n else None, _lib.ptr(low), _lib.ptr(high), _lib.ptr(act), B, n,
+                                       _lib.ptr(result), _lib.ptr(optval), _lib.ptr(optvar), _lib.ptr(active),
+                                       _lib.stream_ptr())
+    _lib.check(rc, "tb_lp2d_batch")
+    return result.cpu().numpy(), optval.cpu().numpy(), optvar.cpu().numpy(), active.cpu().numpy()
+
+
+def lp1d_batch(v, a, b, low, high):
+    """Batched 1-variable LPs on device (tb_lp1d_batch).  v [B,2], a/b [B,n], low/high [B]."""
+    torch = torch_mod()
+    dev = default_device()
+    v = as_device(v, dev)
+    B = v.shape[0]
+    a, b = (as_device(t, dev).reshape(B, -1) for t in (a, b))
+    n = a.shape[1]
+    low, high = as_device(low, dev), as_device(high, dev)
+    result = torch.empty((B,), dtype=torch.int32, device=dev)
+    optval = torch.empty((B,), dtype=torch.float64, device=dev)
+    optvar = torch.empty((B,), dtype=torch.float64, device=dev)
+    active = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_lp1d_batch(_lib.ptr(v), _lib.ptr(a) if n else None, _lib.ptr(b) if n else None,
+                                       _lib.ptr(low), _lib.ptr(high), B, n, _lib.ptr(result), _lib.ptr(optval),
+                                       _lib.ptr(optvar), _lib.ptr(active), _lib.stream_ptr())
+    _lib.check(rc, "tb_lp1d_batch")
+    return result.cpu().numpy(), optval.cpu().numpy(), optvar.cpu().numpy(), active.cpu().numpy()

@@ -73,6 +73,9 @@ class B200SolverWrapper(SolverWrapper):
         self.nC = self.R + 2
         self._solve_lp1d = solve_lp1d
         self._params = None
+        self._rows_host = None
+        self.active_c_up = np.zeros(2, dtype=np.int32)    # warm-start slots, pyx:526-527
+        self.active_c_down = np.zeros(2, dtype=np.int32)
 
     @property
     def params(self):
@@ -94,6 +97,42 @@ class B200SolverWrapper(SolverWrapper):
         out["low"] = np.stack((np.full(G, -1e8), rec[:, 3 * R]), axis=1)
         out["high"] = np.stack((np.full(G, 1e8), rec[:, 3 * R + 1]), axis=1)
         return out
+
+    def solve_stagewise_optim(self, i, H, g, x_min, x_max, x_next_min, x_next_max):
+        """One stage LP, reference semantics (cy_seidel_solverwrapper.pyx:549-697): min g.[u,x] subject to the
+        stage-i rows, x_min <= x <= x_max, x_next_min <= x + 2 delta_i u <= x_next_max (NaN = bound absent).
+        Returns [u, x] or [nan, nan] when infeasible.  One small launch per call (tb_lp1d_batch / tb_lp2d_batch)."""
+        assert 0 <= i <= self.N
+        if self._rows_host is None:
+            self._rows_host = self.rows()
+        rows = self._rows_host
+        a, b, c = rows["a"][i].copy(), rows["b"][i].copy(), rows["c"][i].copy()
+        low, high = rows["low"][i].copy(), rows["high"][i].copy()
+        if not np.isnan(x_min):
+            low[1] = max(low[1], x_min)
+        if not np.isnan(x_max):
+            high[1] = min(high[1], x_max)
+        a[0:2], b[0:2], c[0:2] = 0.0, 0.0, -1.0
+        if i < self.N:
+            if not np.isnan(x_next_min):
+                a[0], b[0], c[0] = -2 * self.deltas[i], -1.0, x_next_min
+            if not np.isnan(x_next_max):
+                a[1], b[1], c[1] = 2 * self.deltas[i], 1.0, -x_next_max
+        g = np.asarray(g, dtype=np.float64)
+        if x_min == x_max and self._solve_lp1d:
+            v = np.array([[-g[0], -g[1] * x_min]])
+            res, _, optvar, act = engine.lp1d_batch(v, a[None], (b * x_min + c)[None], low[0:1], high[0:1])
+            if res[0] == 0:
+                return np.array([np.nan, np.nan])
+            (self.active_c_up if g[1] > 0 else self.active_c_down)[0] = act[0]
+            return np.array([optvar[0], x_min])
+        slot = self.active_c_up if g[1] > 0 else self.active_c_down
+        v = np.array([[-g[0], -g[1], 0.0]])
+        res, _, optvar, act = engine.lp2d_batch(v, a[None], b[None], c[None], low[None], high[None], slot[None])
+        if res[0] == 0:
+            return np.array([np.nan, np.nan])
+        slot[:] = act[0]
+        return optvar[0].copy()
 
     # ---- whole-pass entry points ---------------------------------------------------------------------
     def _scalar(self, v):
