@@ -1,0 +1,55 @@
+"""CPU: the N > 1 path (contiguous sharding + result gather) with world_size-2 gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from toppra_b200.distributed import gather_results, shard_range, shard_sizes
+
+
+def test_shard_range_covers_batch():
+    for B in (1, 2, 7, 4096, 4097, 1000003):
+        for world in (1, 2, 3, 8):
+            edges = [shard_range(B, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == B
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            assert max(shard_sizes(B, world)) - min(shard_sizes(B, world)) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, B, G, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(B, rank, world)
+    # stand-in for the per-rank kernel outputs: values that encode the global path index
+    idx = torch.arange(lo, hi, dtype=torch.float64)
+    local = dict(sd=idx[:, None] + torch.arange(G, dtype=torch.float64)[None, :] / 1000.0,
+                 K=torch.stack((idx, idx + 0.5), dim=1)[:, None, :].expand(hi - lo, G, 2).contiguous(),
+                 status=(torch.arange(lo, hi) % 4).to(torch.int32))
+    full = gather_results(local, B)
+    ok = (full["sd"].shape == (B, G) and full["K"].shape == (B, G, 2) and full["status"].shape == (B,)
+          and torch.equal(full["sd"][:, 0], torch.arange(B, dtype=torch.float64))
+          and torch.equal(full["K"][:, 3, 1], torch.arange(B, dtype=torch.float64) + 0.5)
+          and torch.equal(full["status"], (torch.arange(B) % 4).to(torch.int32)))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [8, 9])
+def test_gather_world2_gloo(B):
+    world = 2
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, 5, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

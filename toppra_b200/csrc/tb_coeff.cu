@@ -18,15 +18,17 @@ namespace tb {
 namespace {
 
 constexpr int COEFF_THREADS = 256;
-constexpr int COEFF_CH = 32;  // gridpoints per CTA
+constexpr int COEFF_CH_SMALL = 32, COEFF_CH_LARGE = 64;  // gridpoints per CTA
 
 __device__ __forceinline__ int R_total_or1(int R_total) { return R_total > 0 ? R_total : 1; }
 
-// Shared-memory plan of one CTA (dof = d, VS = 6d + 3 doubles per gridpoint):
+// Shared-memory plan of one CTA (dof = d, VS = 6d + 3 doubles per gridpoint, CH gridpoints per CTA):
 //   raw  [(CH+1)][2d]   q'(s_i), q''(s_i) of the chunk (+1 gridpoint for the lift)
+//   cand [CH][2d]       velocity-bound candidates vlim/q' per joint (upper, lower)
 //   vec  [CH][VS]       per gridpoint: q' | a+ | q'' | b+ | -amax | +amin | xlo | xhi | 0
 //   tab  [W]            per record column: offset into vec (bit 15 = negate, 0x7fff = column not owned)
 // Phase 2 then only does  rec[col] = +-vec[ci][tab[col]]  with 16-byte stores: no divisions, fully coalesced.
+template <int CH>
 __global__ void __launch_bounds__(COEFF_THREADS)
 coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks, const int breaks_shared,
                     const int nseg, const int dof, const double *__restrict__ grid, const int grid_shared, const int G,
@@ -36,15 +38,17 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
   extern __shared__ double sm[];
   const int VS = 6 * dof + 3;
   double *raw = sm;                                  // [(CH+1)][2*dof]
-  double *vec = raw + (COEFF_CH + 1) * 2 * dof;      // [CH][VS]
-  double *sgrid = vec + COEFF_CH * VS;               // [CH+1]
-  unsigned short *tab = reinterpret_cast<unsigned short *>(sgrid + COEFF_CH + 1);  // [W]
+  double *cand = raw + (CH + 1) * 2 * dof;           // [CH][2*dof]
+  double *vec = cand + CH * 2 * dof;                 // [CH][VS]
+  double *sgrid = vec + CH * VS;                     // [CH+1]
+  double *sx = sgrid + CH + 1;                       // [nseg+1] breakpoints
+  unsigned short *tab = reinterpret_cast<unsigned short *>(sx + nseg + 1);  // [W]
   const long path = blockIdx.x / nchunks;
   const int chunk = blockIdx.x % nchunks;
-  const int i0 = chunk * COEFF_CH;
+  const int i0 = chunk * CH;
   const int N = G - 1;
-  const int npts = min(COEFF_CH, G - i0);          // gridpoints written by this CTA
-  const int nev = min(COEFF_CH + 1, G - i0);       // gridpoints evaluated (one extra for the lift)
+  const int npts = min(CH, G - i0);          // gridpoints written by this CTA
+  const int nev = min(CH + 1, G - i0);       // gridpoints evaluated (one extra for the lift)
   const double *c = ppoly + path * 4 * nseg * dof;
   const double *x = breaks + (breaks_shared ? 0 : path * (nseg + 1));
   const double *gp = grid + (grid_shared ? 0 : path * G);
@@ -53,23 +57,9 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
   const int tid = threadIdx.x;
   const int Racc = al ? (interp ? 4 : 2) * dof : 0;
 
-  // ---- phase 1: q', q'' at the chunk's gridpoints; column table ----
-  for (int idx = tid; idx < nev * dof; idx += COEFF_THREADS) {
-    const int ci = idx / dof, k = idx - ci * dof;
-    const double s = gp[i0 + ci];
-    const int seg = find_interval(x, nseg, s);
-    double v1, v2;
-    if (seg < 0) {
-      v1 = v2 = __longlong_as_double(0x7ff8000000000000LL);
-    } else {
-      const double ds = s - x[seg];
-      v1 = ppoly_eval1(c, nseg, dof, seg, k, ds, 1);
-      v2 = ppoly_eval1(c, nseg, dof, seg, k, ds, 2);
-    }
-    raw[ci * 2 * dof + k] = v1;
-    raw[ci * 2 * dof + dof + k] = v2;
-  }
+  // ---- phase 0: gridpoints and breakpoints of this chunk; column table ----
   for (int ci = tid; ci < nev; ci += COEFF_THREADS) sgrid[ci] = gp[i0 + ci];
+  for (int q = tid; q <= nseg; q += COEFF_THREADS) sx[q] = x[q];
   for (int w = tid; w < W; w += COEFF_THREADS) {
     unsigned short code = 0x7fff;  // not owned by this call: leave untouched
     const int kind = w / R_total_or1(R_total), r = w - kind * R_total - row0;
@@ -86,7 +76,35 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
   }
   __syncthreads();
 
+  // ---- phase 1: q', q'' at the chunk's gridpoints (+ per-joint velocity-bound candidates) ----
+  const double inf_d = __longlong_as_double(0x7ff0000000000000LL);
+  for (int idx = tid; idx < nev * dof; idx += COEFF_THREADS) {
+    const int ci = idx / dof, k = idx - ci * dof;
+    const double s = sgrid[ci];
+    const int seg = find_interval(sx, nseg, s);
+    double v1, v2;
+    if (seg < 0) {
+      v1 = v2 = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+      const double ds = s - sx[seg];
+      v1 = ppoly_eval1(c, nseg, dof, seg, k, ds, 1);
+      v2 = ppoly_eval1(c, nseg, dof, seg, k, ds, 2);
+    }
+    raw[ci * 2 * dof + k] = v1;
+    raw[ci * 2 * dof + dof + k] = v2;
+    if (vl && write_xbound && ci < npts) {
+      // _CythonUtils.pyx:44-50: q' > 0: (vmax/q', vmin/q'); q' < 0: (vmin/q', vmax/q'); q' == 0 (or NaN): no update
+      const bool posq = v1 > 0, negq = v1 < 0;
+      const double qd = (posq || negq) ? v1 : 1.0;
+      const double r1 = vl[k * 2 + 1] / qd, r0 = vl[k * 2 + 0] / qd;
+      cand[ci * 2 * dof + k] = posq ? r1 : (negq ? r0 : inf_d);          // candidate for sdmax
+      cand[ci * 2 * dof + dof + k] = posq ? r0 : (negq ? r1 : -inf_d);   // candidate for sdmin
+    }
+  }
+  __syncthreads();
+
   // ---- phase 1b: per-gridpoint value vectors ----
+  double *rec0 = records + (path * G + i0) * (long)W;
   for (int idx = tid; idx < npts * dof; idx += COEFF_THREADS) {
     const int ci = idx / dof, k = idx - ci * dof;
     const int gi = i0 + ci;
@@ -103,43 +121,33 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
       v[4 * dof + k] = 0.0 - al[k * 2 + 1];       // F.c - g with c = 0, g = [amax; -amin]
       v[5 * dof + k] = 0.0 - (-al[k * 2 + 0]);
     }
-  }
-  double *rec0 = records + (path * G + i0) * (long)W;
-  // velocity bound -> xbound slots.  fp32 running min/max exactly like _CythonUtils.pyx:41-58.
-  if (write_xbound && tid < npts) {
-    const int ci = tid;
-    double xlo = VAR_MIN, xhi = VAR_MAX;  // seidelWrapper low_arr/high_arr init, pyx:477-478
-    if (vl) {
-      float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
-      for (int k = 0; k < dof; ++k) {
-        const double q = raw[ci * 2 * dof + k];
-        if (q > 0) {
-          const double hi = vl[k * 2 + 1] / q, lo = vl[k * 2 + 0] / q;
-          sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
-          sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);
-        } else if (q < 0) {
-          const double hi = vl[k * 2 + 0] / q, lo = vl[k * 2 + 1] / q;
-          sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
-          sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);
+    if (k == 0 && write_xbound) {
+      // velocity bound of this gridpoint: fp32 running min/max over the joints exactly like _CythonUtils.pyx:41-58
+      double xlo = VAR_MIN, xhi = VAR_MAX;  // seidelWrapper low_arr/high_arr init, pyx:477-478
+      if (vl) {
+        float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
+        for (int kk = 0; kk < dof; ++kk) {
+          const double hi = cand[ci * 2 * dof + kk], lo = cand[ci * 2 * dof + dof + kk];
+          sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);  // float64_min, stored to a C float
+          sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);  // float64_max
+        }
+        const float up = __fmul_rn(sdmax, sdmax);                          // powf(sdmax, 2) in fp32
+        const double lo_d = ((double)sdmin >= 0.0) ? (double)sdmin : 0.0;  // float64_max(sdmin, 0.)
+        xlo = lo_d * lo_d;
+        xhi = (double)up;
+        if (write_xbound != 2) {
+          // pyx:517-520: low = max(VAR_MIN, xbound_lo), high = min(VAR_MAX, xbound_hi)
+          xlo = fmax(VAR_MIN, xlo);
+          xhi = fmin(VAR_MAX, xhi);
         }
       }
-      const float up = __fmul_rn(sdmax, sdmax);                          // powf(sdmax, 2) in fp32
-      const double lo_d = ((double)sdmin >= 0.0) ? (double)sdmin : 0.0;  // float64_max(sdmin, 0.)
-      xlo = lo_d * lo_d;
-      xhi = (double)up;
-      if (write_xbound != 2) {
-        // pyx:517-520: low = max(VAR_MIN, xbound_lo), high = min(VAR_MAX, xbound_hi)
-        xlo = fmax(VAR_MIN, xlo);
-        xhi = fmin(VAR_MAX, xhi);
+      if (write_xbound == 3) {  // intersect with what the record already holds
+        const double *rec = rec0 + (long)ci * W;
+        xlo = fmax(rec[3 * R_total], xlo);
+        xhi = fmin(rec[3 * R_total + 1], xhi);
       }
+      v[6 * dof] = xlo; v[6 * dof + 1] = xhi; v[6 * dof + 2] = 0.0;
     }
-    if (write_xbound == 3) {  // intersect with what the record already holds
-      const double *rec = rec0 + (long)ci * W;
-      xlo = fmax(rec[3 * R_total], xlo);
-      xhi = fmin(rec[3 * R_total + 1], xhi);
-    }
-    double *v = vec + ci * VS;
-    v[6 * dof] = xlo; v[6 * dof + 1] = xhi; v[6 * dof + 2] = 0.0;
   }
   __syncthreads();
 
@@ -157,7 +165,7 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
       o.x = v[c0 & 0x7fff]; o.y = v[c1 & 0x7fff];
       if (c0 & 0x8000) o.x = -o.x;
       if (c1 & 0x8000) o.y = -o.y;
-      *reinterpret_cast<double2 *>(dst) = o;
+      __stcs(reinterpret_cast<double2 *>(dst), o);  // streaming store: written once, read later by K2
     } else {
       if (c0 != 0x7fff) { const double t = v[c0 & 0x7fff]; dst[0] = (c0 & 0x8000) ? -t : t; }
       if (c1 != 0x7fff) { const double t = v[c1 & 0x7fff]; dst[1] = (c1 & 0x8000) ? -t : t; }
@@ -253,17 +261,19 @@ extern "C" int tb_coeff_velacc(const double *ppoly, const double *breaks, int br
     return TB_ERR_ARG;
   }
   if (R_total > MAX_ROWS) { set_error("tb_coeff_velacc: R=%d > %d", R_total, MAX_ROWS); return TB_ERR_UNSUPPORTED; }
-  const int nchunks = (G + COEFF_CH - 1) / COEFF_CH;
+  if (6 * dof + 3 >= 0x7fff) { set_error("tb_coeff_velacc: dof=%d too large", dof); return TB_ERR_UNSUPPORTED; }
+  const int CH = (G > 96) ? COEFF_CH_LARGE : COEFF_CH_SMALL;
+  const int nchunks = (G + CH - 1) / CH;
   const long blocks = (long)B * nchunks;
   if (blocks > 0x7fffffffL) { set_error("tb_coeff_velacc: batch too large for one launch"); return TB_ERR_UNSUPPORTED; }
-  if (6 * dof + 3 >= 0x7fff) { set_error("tb_coeff_velacc: dof=%d too large", dof); return TB_ERR_UNSUPPORTED; }
-  const size_t smem = (size_t)((COEFF_CH + 1) * dof * 2 + COEFF_CH * (6 * dof + 3) + COEFF_CH + 1) * sizeof(double) +
+  const size_t smem = (size_t)((CH + 1) * dof * 2 + CH * dof * 2 + CH * (6 * dof + 3) + CH + 1 + nseg + 1) * sizeof(double) +
                       (size_t)W * sizeof(unsigned short) + 16;
+  auto kern = (CH == COEFF_CH_LARGE) ? coeff_velacc_kernel<COEFF_CH_LARGE> : coeff_velacc_kernel<COEFF_CH_SMALL>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(coeff_velacc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tb_coeff_velacc: dof=%d too large for shared memory", dof); return TB_ERR_UNSUPPORTED; }
   }
-  coeff_velacc_kernel<<<(unsigned)blocks, COEFF_THREADS, smem, (cudaStream_t)stream>>>(
+  kern<<<(unsigned)blocks, COEFF_THREADS, smem, (cudaStream_t)stream>>>(
       ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, vlim, alim, lim_shared, interp, records, W,
       R_total, row0, write_xbound, nchunks);
   return check_launch("tb_coeff_velacc");

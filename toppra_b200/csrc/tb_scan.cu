@@ -52,34 +52,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!ok) __nanosleep(64);  // the copy is still in flight: do not burn issue slots other warps could use
   } while (!ok);
 }
 
-// Order-preserving map double -> uint64 (no NaN inputs): a < b  <=>  dkey(a) < dkey(b)  (and -0.0 < +0.0).
-__device__ __forceinline__ unsigned long long dkey(double v) {
-  const long long b = __double_as_longlong(v);
-  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
-}
-__device__ __forceinline__ double dunkey(unsigned long long k) {
-  long long b = (long long)k;
-  b ^= ((~b) >> 63) | (long long)0x8000000000000000ULL;
-  return __longlong_as_double(b);
-}
-// Warp-wide min / max of doubles (no NaNs) with two 32-bit redux.sync each instead of five shuffle rounds:
-// first the high words of the ordered keys, then the low words among the lanes that tie on the high word.
+// Warp-wide min / max of doubles (no NaNs) with two 32-bit redux.sync each instead of five shuffle rounds.
+// Order-preserving map double -> (khi, klo): flip all bits of negative numbers, the sign bit of the others; then
+// reduce the high words, and the low words among the lanes that tie on the high word.
 __device__ __forceinline__ double warp_min(double v) {
-  const unsigned long long k = dkey(v);
-  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-  const unsigned mh = __reduce_min_sync(FULL, hi);
-  const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
-  return dunkey(((unsigned long long)mh << 32) | ml);
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int m = hi >> 31;  // 0 or -1
+  const unsigned khi = (unsigned)(hi ^ (m | (int)0x80000000)), klo = (unsigned)(lo ^ m);
+  const unsigned mh = __reduce_min_sync(FULL, khi);
+  const unsigned ml = __reduce_min_sync(FULL, khi == mh ? klo : 0xffffffffu);
+  const int m2 = ((int)~mh) >> 31;  // -1 if the winner is negative
+  return __hiloint2double((int)(mh ^ (unsigned)(m2 | (int)0x80000000)), (int)(ml ^ (unsigned)m2));
 }
 __device__ __forceinline__ double warp_max(double v) {
-  const unsigned long long k = dkey(v);
-  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-  const unsigned mh = __reduce_max_sync(FULL, hi);
-  const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-  return dunkey(((unsigned long long)mh << 32) | ml);
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int m = hi >> 31;
+  const unsigned khi = (unsigned)(hi ^ (m | (int)0x80000000)), klo = (unsigned)(lo ^ m);
+  const unsigned mh = __reduce_max_sync(FULL, khi);
+  const unsigned ml = __reduce_max_sync(FULL, khi == mh ? klo : 0u);
+  const int m2 = ((int)~mh) >> 31;
+  return __hiloint2double((int)(mh ^ (unsigned)(m2 | (int)0x80000000)), (int)(ml ^ (unsigned)m2));
 }
 
 // Position of LP row r in Seidel's processing order, cy_seidel_solverwrapper.pyx:252-264:
@@ -102,20 +98,31 @@ __device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
 }
 
 constexpr int BOXBASE = 1 << 20;
+constexpr int SCAN_NBUF = 4;  // record buffers per warp (3 stages of look-ahead)
 
-// One projected constraint of the 1-D sub-problem (pyx:326-347): classify and compute its limit on t.
-//   cls 1: t <= tt (denom > TINY), cls 2: t >= tt (denom < -TINY), cls 0: dropped; bad: parallel & infeasible.
+// One projected constraint of the 1-D sub-problem (pyx:326-347): its limit on t as an upper bound `thi` (denom >
+// TINY) or a lower bound `tlo` (denom < -TINY); +-LP_INF = no limit of that kind (the 1-D LP's own bounds);
+// bad: parallel & infeasible.  The divisor of unused lanes is replaced by 1 so that the IEEE division never
+// leaves its fast path for a value that is thrown away (x/0 would take the slow-path subroutine).
 __device__ __forceinline__ void project_item(const bool part, const double aj, const double bj, const double cj,
                                              const double dt0, const double dt1, const double z0, const double z1,
-                                             int &cls, double &tt, bool &bad) {
+                                             double &thi, double &tlo, bool &bad) {
   const double denom = dt0 * aj + dt1 * bj;
   const double num = cj + z1 * bj + z0 * aj;
-  const bool up = denom > LP_TINY, dn = denom < -LP_TINY;
-  const double t = -num / denom;  // unconditional: no divergence; discarded unless up|dn
-  const bool usable = part && (up || dn) && (t == t);  // a NaN limit never updates the running min/max (pyx:115-124)
-  cls = usable ? (up ? 1 : 2) : 0;
-  tt = t;
+  const bool up = part && (denom > LP_TINY), dn = part && (denom < -LP_TINY);
+  const double t = -num / ((up || dn) ? denom : 1.0);
+  // `cur_x < cur_max` / `cur_x > cur_min` (pyx:115-124): a limit at or beyond the sentinel, or NaN, never wins
+  thi = (up && t < LP_INF) ? t : LP_INF;
+  tlo = (dn && t > -LP_INF) ? t : -LP_INF;
   bad = bad || (part && !(up || dn) && (num > LP_SMALL));
+}
+
+// (aj, bj, cj) of box row m: 0: low0 <= u, 1: u <= high0, 2: low1 <= x, 3: x <= high1   (pyx:300-318)
+__device__ __forceinline__ void box_row(const int m, const double low0, const double high0, const double low1,
+                                        const double high1, double &aj, double &bj, double &cj) {
+  aj = __hiloint2double((m == 0) ? (int)0xBFF00000 : ((m == 1) ? 0x3FF00000 : 0), 0);
+  bj = __hiloint2double((m == 2) ? (int)0xBFF00000 : ((m == 3) ? 0x3FF00000 : 0), 0);
+  cj = (m < 2) ? ((m == 0) ? low0 : -high0) : ((m == 2) ? low1 : -high1);
 }
 
 // cy_solve_lp2d (pyx:149-390) on one warp.  Lane `lane` holds LP rows r = lane + 32*s, s < RPL
@@ -178,44 +185,41 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
     const double dt0 = -bk, dt1 = ak;
     const double v1d = dt0 * v0 + dt1 * v1;
     // project the earlier rows and the four box rows onto the line, pyx:298-347
-    double tt[RPL + 1];
-    int cls[RPL + 1], key[RPL + 1];
+    double thi[RPL], tlo[RPL];
+    int key[RPL];
     bool bad = false;
     const bool idle0 = !(pos[0] < kpos);  // this lane's slot-0 row does not take part (row k, later rows, padding)
     const unsigned idle = __ballot_sync(FULL, idle0);
     const bool box_inline = __popc(idle) >= 4;  // warp-uniform
     {
       // slot 0: own row, or (on the first four idle lanes) box row m = rank
-      const int rank = __popc(idle & lt_mask);
-      const bool isbox = box_inline && idle0 && rank < 4;
-      const int m = rank;  // 0: low0 <= u, 1: u <= high0, 2: low1 <= x, 3: x <= high1
-      const double ba = (m == 0) ? -1.0 : ((m == 1) ? 1.0 : 0.0);
-      const double bb = (m == 2) ? -1.0 : ((m == 3) ? 1.0 : 0.0);
-      const double bc = (m == 0) ? low0 : ((m == 1) ? -high0 : ((m == 2) ? low1 : -high1));
-      const double aj = isbox ? ba : a[0], bj = isbox ? bb : b[0], cj = isbox ? bc : c[0];
+      const int m = __popc(idle & lt_mask);
+      const bool isbox = box_inline && idle0 && m < 4;
+      double ba, bb, bc;
+      box_row(m, low0, high0, low1, high1, ba, bb, bc);
       key[0] = isbox ? BOXBASE + m : pos[0];
-      project_item(isbox || !idle0, aj, bj, cj, dt0, dt1, z0, z1, cls[0], tt[0], bad);
+      project_item(isbox || !idle0, isbox ? ba : a[0], isbox ? bb : b[0], isbox ? bc : c[0], dt0, dt1, z0, z1, thi[0],
+                   tlo[0], bad);
     }
 #pragma unroll
     for (int s = 1; s < RPL; ++s) {
       key[s] = pos[s];
-      project_item(pos[s] < kpos, a[s], b[s], c[s], dt0, dt1, z0, z1, cls[s], tt[s], bad);
-    }
-    cls[RPL] = 0; tt[RPL] = 0.0; key[RPL] = INT_MAX;
-    if (!box_inline) {  // rare: (almost) every row takes part -> box rows in an extra slot on lanes 0..3
-      const int m = lane;
-      const double ba = (m == 0) ? -1.0 : ((m == 1) ? 1.0 : 0.0);
-      const double bb = (m == 2) ? -1.0 : ((m == 3) ? 1.0 : 0.0);
-      const double bc = (m == 0) ? low0 : ((m == 1) ? -high0 : ((m == 2) ? low1 : -high1));
-      key[RPL] = BOXBASE + m;
-      project_item(m < 4, ba, bb, bc, dt0, dt1, z0, z1, cls[RPL], tt[RPL], bad);
+      project_item(pos[s] < kpos, a[s], b[s], c[s], dt0, dt1, z0, z1, thi[s], tlo[s], bad);
     }
     // 1-D LP on the line with bounds +-INF, pyx:350 -> cy_solve_lp1d pyx:93-144
-    double my_hi = LP_INF, my_lo = -LP_INF;
+    double my_hi = thi[0], my_lo = tlo[0];
 #pragma unroll
-    for (int s = 0; s <= RPL; ++s) {
-      my_hi = (cls[s] == 1 && tt[s] < my_hi) ? tt[s] : my_hi;
-      my_lo = (cls[s] == 2 && tt[s] > my_lo) ? tt[s] : my_lo;
+    for (int s = 1; s < RPL; ++s) {
+      my_hi = (thi[s] < my_hi) ? thi[s] : my_hi;
+      my_lo = (tlo[s] > my_lo) ? tlo[s] : my_lo;
+    }
+    double xhi_t = LP_INF, xlo_t = -LP_INF;  // extra item slot, only when the box rows could not ride inline
+    if (!box_inline) {  // rare: (almost) every row takes part -> box rows on lanes 0..3
+      double ba, bb, bc;
+      box_row(lane, low0, high0, low1, high1, ba, bb, bc);
+      project_item(lane < 4, ba, bb, bc, dt0, dt1, z0, z1, xhi_t, xlo_t, bad);
+      my_hi = (xhi_t < my_hi) ? xhi_t : my_hi;
+      my_lo = (xlo_t > my_lo) ? xlo_t : my_lo;
     }
     const double cur_max = warp_min(my_hi);
     const double cur_min = warp_max(my_lo);
@@ -224,11 +228,12 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
     const bool pick_min = (fabs(v1d) < LP_TINY) || (v1d < 0);
     const double tstar = pick_min ? cur_min : cur_max;
     // optimum on the +-INF sentinel (1-D active index -1/-2) counts as infeasible, pyx:376-383
-    if (pick_min ? !(tstar > -LP_INF) : !(tstar < LP_INF)) return false;
-    const int want = pick_min ? 2 : 1;
+    if (tstar == (pick_min ? -LP_INF : LP_INF)) return false;
+    // active item = first (lowest key) item that attains the optimum; tstar is finite here, sentinels never match
     int mykey = INT_MAX;
 #pragma unroll
-    for (int s = 0; s <= RPL; ++s) mykey = (cls[s] == want && tt[s] == tstar) ? min(mykey, key[s]) : mykey;
+    for (int s = 0; s < RPL; ++s) mykey = ((pick_min ? tlo[s] : thi[s]) == tstar) ? min(mykey, key[s]) : mykey;
+    if (!box_inline) mykey = ((pick_min ? xlo_t : xhi_t) == tstar) ? min(mykey, BOXBASE + lane) : mykey;
     const int akey = __reduce_min_sync(FULL, mykey);
     nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
     p0 = z0 + tstar * dt0;  // pyx:362-363
@@ -252,7 +257,7 @@ __device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double 
   for (int s = 0; s < RPL; ++s) {
     const double bxc = b[s] * x + c[s];
     const bool up = a[s] > LP_TINY, dn = a[s] < -LP_TINY;
-    const double t = -bxc / a[s];
+    const double t = -bxc / ((up || dn) ? a[s] : 1.0);  // unused lanes divide by 1: stay on the division fast path
     my_hi = (up && t < my_hi) ? t : my_hi;
     my_lo = (dn && t > my_lo) ? t : my_lo;
   }
@@ -301,9 +306,8 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long path = (long)blockIdx.x * WARPS + warp;
   if (path >= B) return;
-  double *buf0 = reinterpret_cast<double *>(smem_raw) + (size_t)warp * 2 * W;
-  double *buf1 = buf0 + W;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * 2 * W * sizeof(double)) + warp * 2;
+  double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * SCAN_NBUF * W;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double)) + warp * SCAN_NBUF;
   const int N = G - 1, nC = R + 2;
   const unsigned rec_bytes = (unsigned)(W * sizeof(double));
   const double *rec_path = records + (size_t)path * G * W;
@@ -314,28 +318,31 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   double *up = backward_only ? nullptr : uout + (size_t)path * (G > 1 ? G - 1 : 0);
 
   if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int q = 0; q < SCAN_NBUF; ++q) mbar_init(&bars[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
 
-  unsigned n_issued = 0, n_waited = 0;  // ring of 2 buffers
+  // Ring of SCAN_NBUF record buffers: up to SCAN_NBUF-1 bulk copies in flight per warp.  The forward pass solves a
+  // stage in well under the HBM round trip, so one stage of look-ahead is not enough there.
+  unsigned n_issued = 0, n_waited = 0;
   auto issue = [&](int stage) {
     if (lane == 0) {
-      uint64_t *bar = &bars[n_issued & 1];
-      mbar_expect_tx(bar, rec_bytes);
-      bulk_g2s((n_issued & 1) ? buf1 : buf0, rec_path + (size_t)stage * W, rec_bytes, bar);
+      const unsigned q = n_issued % SCAN_NBUF;
+      mbar_expect_tx(&bars[q], rec_bytes);
+      bulk_g2s(bufs + (size_t)q * W, rec_path + (size_t)stage * W, rec_bytes, &bars[q]);
     }
     ++n_issued;
   };
   auto acquire = [&]() -> const double * {
-    mbar_wait(&bars[n_waited & 1], (n_waited >> 1) & 1);
-    const double *p = (n_waited & 1) ? buf1 : buf0;
+    const unsigned q = n_waited % SCAN_NBUF;
+    mbar_wait(&bars[q], (n_waited / SCAN_NBUF) & 1);
     ++n_waited;
-    return p;
+    return bufs + (size_t)q * W;
   };
+  constexpr int AHEAD = SCAN_NBUF - 1;
 
   int n_lp2d = 0, n_lp1d = 0, n_resolve = 0, n_retry = 0;
   double a[RPL], b[RPL], c[RPL];
@@ -348,13 +355,13 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   if (lane == 0) { Kp[2 * N] = kn0; Kp[2 * N + 1] = kn1; }
   int st = TB_STATUS_OK, fstage = -1;
   int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0;  // active_c_up / active_c_down, initialised to zeros (pyx:526-527)
-  if (N > 0) issue(N - 1);
+  for (int q = 0; q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
   for (int i = N - 1; i >= 0; --i) {
     const double *rec = acquire();
     load_rows<RPL>(rec, R, nC, lane, a, b, c);
     const double xlo = rec[3 * R], xhi = rec[3 * R + 1];
     __syncwarp();
-    if (i > 0) issue(i - 1);
+    if (i - AHEAD >= 0) issue(i - AHEAD);
     const double delta = gp[i + 1] - gp[i];
     set_xnext_rows<RPL>(lane, delta, kn0, kn1, a, b, c);
     // low/high: pyx:587-601 with x_min = x_max = NaN
@@ -405,13 +412,13 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     // ---------------- forward pass, reachability_algorithm.py:303-364 ----------------
     double x = x_start;
     if (lane == 0) sdp[0] = sqrt(x);
-    if (N > 0) issue(0);
+    for (int q = 0; q < AHEAD && q < N; ++q) issue(q);
     int i = 0;
     for (; i < N; ++i) {
       const double *rec = acquire();
       load_rows<RPL>(rec, R, nC, lane, a, b, c);
       __syncwarp();
-      if (i + 1 < N) issue(i + 1);
+      if (i + AHEAD < N) issue(i + AHEAD);
       const double delta = gp[i + 1] - gp[i];
       const double k0 = Kp[2 * (i + 1)], k1 = Kp[2 * (i + 1) + 1];
       set_xnext_rows<RPL>(lane, delta, k0, k1, a, b, c);
@@ -579,7 +586,7 @@ template <int RPL>
 int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                 const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
                 double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
-  const size_t smem = (size_t)SCAN_WARPS * 2 * W * sizeof(double) + SCAN_WARPS * 2 * sizeof(uint64_t);
+  const size_t smem = (size_t)SCAN_WARPS * SCAN_NBUF * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t);
   // Two register budgets for the common nC <= 32 case: 7 CTAs/SM (72 regs, 28 warps/SM: the 4096-path batch of
   // BASELINE cfg 2 fits one wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
   static const char *occ_env = getenv("TB_SCAN_OCC");
