@@ -23,26 +23,30 @@ constexpr int COEFF_CH_SMALL = 32, COEFF_CH_LARGE = 64;  // gridpoints per CTA
 __device__ __forceinline__ int R_total_or1(int R_total) { return R_total > 0 ? R_total : 1; }
 
 // Shared-memory plan of one CTA (dof = d, VS = 6d + 3 doubles per gridpoint, CH gridpoints per CTA):
+//   dco  [nseg][d][5]   derivative coefficients of the path's PPoly: q' = (3c0, 2c1, c2), q'' = (6c0, 2c1)
 //   raw  [(CH+1)][2d]   q'(s_i), q''(s_i) of the chunk (+1 gridpoint for the lift)
 //   cand [CH][2d]       velocity-bound candidates vlim/q' per joint (upper, lower)
 //   vec  [CH][VS]       per gridpoint: q' | a+ | q'' | b+ | -amax | +amin | xlo | xhi | 0
 //   tab  [W]            per record column: offset into vec (bit 15 = negate, 0x7fff = column not owned)
-// Phase 2 then only does  rec[col] = +-vec[ci][tab[col]]  with 16-byte stores: no divisions, fully coalesced.
+// Phase 2: every thread owns one 16-byte column pair and walks down the gridpoints:
+//   rec[ci][col] = +-vec[ci][tab[col]]  -> two shared loads + one coalesced 16-byte store per iteration.
 template <int CH>
 __global__ void __launch_bounds__(COEFF_THREADS)
 coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks, const int breaks_shared,
                     const int nseg, const int dof, const double *__restrict__ grid, const int grid_shared, const int G,
                     const double *__restrict__ vlim, const double *__restrict__ alim, const int lim_shared,
                     const int interp, double *__restrict__ records, const int W, const int R_total, const int row0,
-                    const int write_xbound, const int nchunks) {
+                    const int write_xbound, const int nchunks, const int pp_in_smem) {
   extern __shared__ double sm[];
   const int VS = 6 * dof + 3;
   double *raw = sm;                                  // [(CH+1)][2*dof]
   double *cand = raw + (CH + 1) * 2 * dof;           // [CH][2*dof]
   double *vec = cand + CH * 2 * dof;                 // [CH][VS]
   double *sgrid = vec + CH * VS;                     // [CH+1]
-  double *sx = sgrid + CH + 1;                       // [nseg+1] breakpoints
-  unsigned short *tab = reinterpret_cast<unsigned short *>(sx + nseg + 1);  // [W]
+  // long splines (many waypoints): breakpoints and coefficients stay in global memory (L1/L2)
+  double *sx_s = sgrid + CH + 1;                     // [nseg+1] breakpoints
+  double *dco = sx_s + (pp_in_smem ? nseg + 1 : 0);  // [nseg][dof][5]
+  unsigned short *tab = reinterpret_cast<unsigned short *>(dco + (pp_in_smem ? nseg * dof * 5 : 0));  // [W]
   const long path = blockIdx.x / nchunks;
   const int chunk = blockIdx.x % nchunks;
   const int i0 = chunk * CH;
@@ -57,9 +61,17 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
   const int tid = threadIdx.x;
   const int Racc = al ? (interp ? 4 : 2) * dof : 0;
 
-  // ---- phase 0: gridpoints and breakpoints of this chunk; column table ----
+  // ---- phase 0: gridpoints, breakpoints, derivative coefficients, column table ----
   for (int ci = tid; ci < nev; ci += COEFF_THREADS) sgrid[ci] = gp[i0 + ci];
-  for (int q = tid; q <= nseg; q += COEFF_THREADS) sx[q] = x[q];
+  const double *sx = pp_in_smem ? sx_s : x;
+  for (int q = tid; pp_in_smem && q <= nseg; q += COEFF_THREADS) sx_s[q] = x[q];
+  for (int q = tid; pp_in_smem && q < nseg * dof; q += COEFF_THREADS) {
+    // scipy PPoly.derivative: c'[j] = c[j] * (k - j); cspldd = cspld.derivative() (interpolator.py:419-421)
+    const double c0 = c[q], c1 = c[nseg * dof + q], c2 = c[2 * nseg * dof + q];
+    const double d0 = c0 * 3.0, d1 = c1 * 2.0, d2 = c2 * 1.0;
+    double *o = dco + q * 5;
+    o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d0 * 2.0; o[4] = d1 * 1.0;
+  }
   for (int w = tid; w < W; w += COEFF_THREADS) {
     unsigned short code = 0x7fff;  // not owned by this call: leave untouched
     const int kind = w / R_total_or1(R_total), r = w - kind * R_total - row0;
@@ -86,9 +98,23 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
     if (seg < 0) {
       v1 = v2 = __longlong_as_double(0x7ff8000000000000LL);
     } else {
+      // scipy evaluate_poly1: res = 0; z = 1; for each power: res += c * z; z *= ds
       const double ds = s - sx[seg];
-      v1 = ppoly_eval1(c, nseg, dof, seg, k, ds, 1);
-      v2 = ppoly_eval1(c, nseg, dof, seg, k, ds, 2);
+      double oloc[5];
+      const double *o = dco + (seg * dof + k) * 5;
+      if (!pp_in_smem) {
+        const int q = seg * dof + k;
+        const double c0 = c[q], c1 = c[nseg * dof + q], c2 = c[2 * nseg * dof + q];
+        oloc[0] = c0 * 3.0; oloc[1] = c1 * 2.0; oloc[2] = c2 * 1.0; oloc[3] = oloc[0] * 2.0; oloc[4] = oloc[1] * 1.0;
+        o = oloc;
+      }
+      double z = ds;
+      v1 = 0.0 + o[2];
+      v1 = v1 + o[1] * z;
+      z = z * ds;
+      v1 = v1 + o[0] * z;
+      v2 = 0.0 + o[4];
+      v2 = v2 + o[3] * ds;
     }
     raw[ci * 2 * dof + k] = v1;
     raw[ci * 2 * dof + dof + k] = v2;
@@ -151,27 +177,39 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
   }
   __syncthreads();
 
-  // ---- phase 2: stream the records out, two columns (16 bytes) per thread and iteration ----
+  // ---- phase 2: stream the records out; thread -> fixed 16-byte column pair, loop over gridpoints ----
   const int Wh = W >> 1;
-  const int total = npts * Wh;
-  int ci = tid / Wh, j = tid - ci * Wh;
-  const int dq = COEFF_THREADS / Wh, dr = COEFF_THREADS - dq * Wh;
-  for (int p = tid; p < total; p += COEFF_THREADS) {
+  const int ngrp = COEFF_THREADS / Wh;  // gridpoints written per sweep (threads beyond ngrp * Wh idle)
+  const int g = tid / Wh, j = tid - g * Wh;
+  if (ngrp > 0 && g < ngrp) {
     const unsigned short c0 = tab[2 * j], c1 = tab[2 * j + 1];
-    const double *v = vec + ci * VS;
-    double *dst = rec0 + (long)ci * W + 2 * j;
-    if (c0 != 0x7fff && c1 != 0x7fff) {
-      double2 o;
-      o.x = v[c0 & 0x7fff]; o.y = v[c1 & 0x7fff];
-      if (c0 & 0x8000) o.x = -o.x;
-      if (c1 & 0x8000) o.y = -o.y;
-      __stcs(reinterpret_cast<double2 *>(dst), o);  // streaming store: written once, read later by K2
-    } else {
-      if (c0 != 0x7fff) { const double t = v[c0 & 0x7fff]; dst[0] = (c0 & 0x8000) ? -t : t; }
-      if (c1 != 0x7fff) { const double t = v[c1 & 0x7fff]; dst[1] = (c1 & 0x8000) ? -t : t; }
+    const int o0 = c0 & 0x7fff, o1 = c1 & 0x7fff;
+    const bool n0 = (c0 & 0x8000) != 0, n1 = (c1 & 0x8000) != 0;
+    const bool own0 = c0 != 0x7fff, own1 = c1 != 0x7fff;
+    double *dst = rec0 + (long)g * W + 2 * j;
+    const double *v = vec + g * VS;
+    if (own0 && own1) {
+      for (int ci = g; ci < npts; ci += ngrp, dst += (long)ngrp * W, v += ngrp * VS) {
+        double2 o;
+        o.x = n0 ? -v[o0] : v[o0];
+        o.y = n1 ? -v[o1] : v[o1];
+        __stcs(reinterpret_cast<double2 *>(dst), o);  // streaming store: written once, read later by K2
+      }
+    } else if (own0 || own1) {
+      for (int ci = g; ci < npts; ci += ngrp, dst += (long)ngrp * W, v += ngrp * VS) {
+        if (own0) dst[0] = n0 ? -v[o0] : v[o0];
+        if (own1) dst[1] = n1 ? -v[o1] : v[o1];
+      }
     }
-    ci += dq; j += dr;
-    if (j >= Wh) { j -= Wh; ++ci; }
+  } else if (ngrp == 0) {  // records wider than 2 * COEFF_THREADS columns: column loop per gridpoint
+    for (int ci = 0; ci < npts; ++ci)
+      for (int w = tid; w < W; w += COEFF_THREADS) {
+        const unsigned short cw = tab[w];
+        if (cw != 0x7fff) {
+          const double t = vec[ci * VS + (cw & 0x7fff)];
+          rec0[(long)ci * W + w] = (cw & 0x8000) ? -t : t;
+        }
+      }
   }
 }
 
@@ -266,8 +304,10 @@ extern "C" int tb_coeff_velacc(const double *ppoly, const double *breaks, int br
   const int nchunks = (G + CH - 1) / CH;
   const long blocks = (long)B * nchunks;
   if (blocks > 0x7fffffffL) { set_error("tb_coeff_velacc: batch too large for one launch"); return TB_ERR_UNSUPPORTED; }
-  const size_t smem = (size_t)((CH + 1) * dof * 2 + CH * dof * 2 + CH * (6 * dof + 3) + CH + 1 + nseg + 1) * sizeof(double) +
-                      (size_t)W * sizeof(unsigned short) + 16;
+  const size_t pp_doubles = (size_t)nseg + 1 + (size_t)nseg * dof * 5;
+  const int pp_in_smem = pp_doubles * sizeof(double) <= 32 * 1024;
+  const size_t smem = (size_t)((CH + 1) * dof * 2 + CH * dof * 2 + CH * (6 * dof + 3) + CH + 1 +
+                               (pp_in_smem ? pp_doubles : 0)) * sizeof(double) + (size_t)W * sizeof(unsigned short) + 16;
   auto kern = (CH == COEFF_CH_LARGE) ? coeff_velacc_kernel<COEFF_CH_LARGE> : coeff_velacc_kernel<COEFF_CH_SMALL>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -275,7 +315,7 @@ extern "C" int tb_coeff_velacc(const double *ppoly, const double *breaks, int br
   }
   kern<<<(unsigned)blocks, COEFF_THREADS, smem, (cudaStream_t)stream>>>(
       ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, vlim, alim, lim_shared, interp, records, W,
-      R_total, row0, write_xbound, nchunks);
+      R_total, row0, write_xbound, nchunks, pp_in_smem);
   return check_launch("tb_coeff_velacc");
 }
 

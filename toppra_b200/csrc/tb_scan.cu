@@ -221,12 +221,13 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
       my_hi = (xhi_t < my_hi) ? xhi_t : my_hi;
       my_lo = (xlo_t > my_lo) ? xlo_t : my_lo;
     }
-    const double cur_max = warp_min(my_hi);
-    const double cur_min = warp_max(my_lo);
-    if (__any_sync(FULL, bad)) return false;
-    if (cur_min > cur_max) return false;
+    // The objective's sign decides which end of [cur_min, cur_max] is the optimum (pyx:130-143); only that end is
+    // reduced exactly (max lo = -min(-lo)); "cur_min > cur_max" (pyx:126-128) is a vote against the other side.
     const bool pick_min = (fabs(v1d) < LP_TINY) || (v1d < 0);
-    const double tstar = pick_min ? cur_min : cur_max;
+    const double red = warp_min(pick_min ? -my_lo : my_hi);
+    const double tstar = pick_min ? -red : red;
+    const bool cross = pick_min ? (my_hi < tstar) : (my_lo > tstar);
+    if (__any_sync(FULL, bad || cross)) return false;
     // optimum on the +-INF sentinel (1-D active index -1/-2) counts as infeasible, pyx:376-383
     if (tstar == (pick_min ? -LP_INF : LP_INF)) return false;
     // active item = first (lowest key) item that attains the optimum; tstar is finite here, sentinels never match
@@ -261,10 +262,12 @@ __device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double 
     my_hi = (up && t < my_hi) ? t : my_hi;
     my_lo = (dn && t > my_lo) ? t : my_lo;
   }
-  const double cur_max = warp_min(my_hi);
-  const double cur_min = warp_max(my_lo);
-  if (cur_min > cur_max) return false;
-  out_u = ((fabs(v0) < LP_TINY) || (v0 < 0)) ? cur_min : cur_max;
+  // exact reduction of the optimal end only; infeasibility (cur_min > cur_max) as a vote against the other side
+  const bool pick_min = (fabs(v0) < LP_TINY) || (v0 < 0);
+  const double red = warp_min(pick_min ? -my_lo : my_hi);
+  const double ustar = pick_min ? -red : red;
+  if (__any_sync(FULL, pick_min ? (my_hi < ustar) : (my_lo > ustar))) return false;
+  out_u = ustar;
   return true;
 }
 
@@ -410,8 +413,9 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     for (int j = lane; j < N; j += 32) up[j] = nan_d;
   } else {
     // ---------------- forward pass, reachability_algorithm.py:303-364 ----------------
+    // sd = sqrt(x) is applied in one coalesced sweep after the pass; until then sd[] holds x
     double x = x_start;
-    if (lane == 0) sdp[0] = sqrt(x);
+    if (lane == 0) sdp[0] = x;
     for (int q = 0; q < AHEAD && q < N; ++q) issue(q);
     int i = 0;
     for (; i < N; ++i) {
@@ -438,7 +442,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
         // reachability_algorithm.py:337-342: xs[i+1:] = nan -> sd NaN -> ErrUnknown; us stay 0
         st = TB_STATUS_ERR_UNKNOWN;
         fstage = i;
-        if (lane == 0) sdp[i] = sqrt(x);
+        if (lane == 0) sdp[i] = x;
         for (int j = i + 1 + lane; j < G; j += 32) sdp[j] = nan_d;
         for (int j = i + lane; j < N; j += 32) up[j] = 0.0;
         break;
@@ -448,12 +452,14 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       x_next = fmin(k1, fmax(k0, x_next));                        // :354
       if (lane == 0) {
         up[i] = uopt;
-        sdp[i] = sqrt(x);  // x may have been shrunk by the retry rule
-        sdp[i + 1] = sqrt(x_next);
+        if (tries) sdp[i] = x;  // x was shrunk by the retry rule
+        sdp[i + 1] = x_next;
       }
       x = x_next;
     }
     while (n_waited < n_issued) (void)acquire();
+    __syncwarp();
+    for (int j = lane; j < G; j += 32) sdp[j] = sqrt(sdp[j]);  // reachability_algorithm.py:365
   }
   if (lane == 0) {
     status[path] = st;
