@@ -151,12 +151,16 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
       // velocity bound of this gridpoint: fp32 running min/max over the joints exactly like _CythonUtils.pyx:41-58
       double xlo = VAR_MIN, xhi = VAR_MAX;  // seidelWrapper low_arr/high_arr init, pyx:477-478
       if (vl) {
-        float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
+        // The reference keeps the running min/max in C floats: s <- (float)min(cand_k, (double)s), k = 0..dof-1,
+        // s_0 = 1e8f (_CythonUtils.pyx:41-50).  Round-to-nearest is monotone and idempotent, so that chain equals
+        // (float)min(1e8, min_k cand_k) (likewise for the max): reduce in fp64, round once.
+        double mhi = JVEL_MAXSD, mlo = -JVEL_MAXSD;
         for (int kk = 0; kk < dof; ++kk) {
           const double hi = cand[ci * 2 * dof + kk], lo = cand[ci * 2 * dof + dof + kk];
-          sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);  // float64_min, stored to a C float
-          sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);  // float64_max
+          mhi = (hi <= mhi) ? hi : mhi;
+          mlo = (lo >= mlo) ? lo : mlo;
         }
+        const float sdmax = __double2float_rn(mhi), sdmin = __double2float_rn(mlo);
         const float up = __fmul_rn(sdmax, sdmax);                          // powf(sdmax, 2) in fp32
         const double lo_d = ((double)sdmin >= 0.0) ? (double)sdmin : 0.0;  // float64_max(sdmin, 0.)
         xlo = lo_d * lo_d;
