@@ -75,28 +75,76 @@ def _ref_solve_chunk(args):
     return n_ok
 
 
-class CpuArm(object):
-    """Times the reference CPU path on all host cores (multiprocessing, one chunk of paths per task)."""
+def _cgroup_cpu_limit():
+    """CPU quota of this container (cgroup v2 cpu.max / v1 cfs quota), or None."""
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            return max(1, int(float(q) / float(p) + 0.5))
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return max(1, int(q / p + 0.5))
+    except Exception:
+        pass
+    return None
 
-    def __init__(self, dof, G):
+
+class CpuArm(object):
+    """Times the reference CPU path on the host cores (multiprocessing, one chunk of paths per task).
+
+    The number of worker processes is calibrated (a few candidates up to the visible CPU count, best throughput on
+    a small sample wins): on shared hosts the visible CPUs exceed what the container may actually use, and an
+    oversubscribed pool would understate the reference."""
+
+    def __init__(self, dof, G, calibrate=None):
         from oracle.ref_loader import reference_available
         self.kind = "reference" if reference_available() else "port"
-        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.visible = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        quota = _cgroup_cpu_limit()
+        self.cores = min(self.visible, quota) if quota else self.visible
         self.G, self.dof = G, dof
         self.pool = None
+        self.note = "visible cpus %d%s" % (self.visible, (", cgroup quota %d" % quota) if quota else "")
         if self.kind == "reference":
-            import multiprocessing as mp
-            self.pool = mp.get_context("fork").Pool(self.cores, initializer=_ref_worker_init)
+            if calibrate is not None:
+                self._calibrate(*calibrate)
+            self._make_pool(self.cores)
         else:
             from oracle import oracle as orc
             self.orc = orc
+
+    def _make_pool(self, n):
+        import multiprocessing as mp
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+        self.pool = mp.get_context("fork").Pool(n, initializer=_ref_worker_init)
+        self.nproc = n
+
+    def _calibrate(self, ss, way, vlim, alim, grid):
+        cands = sorted({c for c in (4, 8, 16, 32, 64, 128, self.cores) if c <= self.cores}) or [1]
+        best, best_rate, log = cands[-1], 0.0, []
+        for n in cands:
+            self._make_pool(n)
+            S = min(way.shape[0], max(64, 8 * n))
+            self.run(ss, way[:min(S, 4 * n)], vlim[:min(S, 4 * n)], alim[:min(S, 4 * n)], grid)  # import warm-up
+            rate = S / self.run(ss, way[:S], vlim[:S], alim[:S], grid)
+            log.append("%d:%.0f" % (n, rate))
+            if rate > best_rate:
+                best, best_rate = n, rate
+        self.cores = best
+        self.note += "; pool-size calibration (procs:paths/s) " + " ".join(log)
 
     def run(self, ss, way, vlim, alim, grid):
         """Solve all given paths; returns seconds."""
         B = way.shape[0]
         t0 = time.perf_counter()
         if self.kind == "reference":
-            nchunk = min(B, self.cores * 4)
+            nchunk = min(B, self.nproc * 4)
             idx = np.array_split(np.arange(B), nchunk)
             tasks = [(ss, way[i], vlim[i], alim[i], grid) for i in idx if len(i)]
             self.pool.map(_ref_solve_chunk, tasks, chunksize=1)
@@ -117,12 +165,13 @@ def run_reference(args):
         return
     from problems import make_batch_fast
     G, dof = args.gridpoints, args.dof
-    arm = CpuArm(dof, G)
-    # bounded sample of the workload per step: ~2 s of wall time per step on this box
-    per_core = 180.0 if arm.kind == "reference" else 4000.0
-    S = args.cpu_sample or int(min(args.batch, max(arm.cores * 8, per_core * arm.cores * 2.0)))
-    ss, way, vlim, alim = make_batch_fast(S, seed=1234, dof=dof)
     grid = np.linspace(0, 1, G)
+    ss, way, vlim, alim = make_batch_fast(args.batch, seed=1234, dof=dof)
+    arm = CpuArm(dof, G, calibrate=(ss, way, vlim, alim, grid))
+    # bounded sample of the workload per step: ~2 s of wall time per step on this box
+    per_core = 150.0 if arm.kind == "reference" else 4000.0
+    S = args.cpu_sample or int(min(args.batch, max(arm.cores * 8, per_core * arm.cores * 2.0)))
+    way, vlim, alim = way[:S], vlim[:S], alim[:S]
     for _ in range(max(args.warmup, 1)):
         arm.run(ss, way, vlim, alim, grid)
     secs = [arm.run(ss, way, vlim, alim, grid) for _ in range(args.steps)]
@@ -138,7 +187,7 @@ def run_reference(args):
                    if arm.kind == "reference" else "oracle C port (reference build absent)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                          "sample": "%d paths/step x %d steps, spline fit + wrapper construction + compute_parameterization, "
-                                   "multiprocessing over %d cores" % (S, args.steps, arm.cores)},
+                                   "multiprocessing over %d processes (%s)" % (S, args.steps, arm.cores, arm.note)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,14 +257,14 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            arm = CpuArm(dof, G)
+            arm = CpuArm(dof, G, calibrate=(ss, way, vlim, alim, grid))
             S = args.cpu_sample or min(B, 4096)  # the whole cfg-2 batch: ~20 s of CPU work for the reference
             arm.run(ss, way[:min(S, 256)], vlim[:min(S, 256)], alim[:min(S, 256)], grid)  # warm-up (imports, pool)
             secs = arm.run(ss, way[:S], vlim[:S], alim[:S], grid)
             arm.close()
             cpu = {"value": S / secs, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                    "sample": "%d paths of the same batch (spline fit + wrapper construction + compute_parameterization), "
-                             "%s, %d processes" % (S, "reference TOPPRA(seidel)" if arm.kind == "reference" else "C port", arm.cores)}
+                             "%s, %d processes (%s)" % (S, "reference TOPPRA(seidel)" if arm.kind == "reference" else "C port", arm.cores, arm.note)}
         except Exception as exc:  # never lose the GPU line
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
 

@@ -304,3 +304,45 @@ def test_host_buffer_cabi_entry(ta, golden):
     assert _eq(out["status"], g["status"]) and _eq(out["K"], g["K"]) and _eq(out["sd"], g["sd"]) and _eq(out["u"], g["sdd"])
     out = ta.engine.solve_velacc_host(g["ss"], g["way"], g["grid"], g["vlim"][0], g["alim"][0], True)
     assert _eq(out["K"][0], g["K"][0])
+
+
+def test_custom_linear_constraint_generic_rows(ta, orc, golden):
+    """A user-defined CanonicalLinear constraint with a NON-identical F (like the reference's test constraint in
+    tests/tests/solverwrapper/test_basic_can_linear.py:18-50): rows F_i a_i, F_i b_i, F_i c_i - g_i are assembled on
+    the device from the host 7-tuple.  Checked against the oracle fed with numpy-assembled rows (tolerance 1e-12:
+    the dot-product order of numpy's BLAS is not pinned)."""
+    g = golden("cfg1_seed9")
+    path = ta.SplineInterpolator(g["ss"], g["way"])
+    grid = g["grid"]
+    N, dof = len(grid) - 1, 7
+    rng = np.random.RandomState(0)
+
+    class Custom(ta.constraint.LinearConstraint):
+        def __init__(self):
+            super().__init__()
+            self.dof = dof
+            self.identical = False
+            self._format_string = ""
+
+        def get_dof(self):
+            return dof
+
+        def compute_constraint_params(self, path_, gridpoints):
+            qs, qss = path_(gridpoints, 1), path_(gridpoints, 2)
+            G = len(gridpoints)
+            F = np.tile(np.vstack((np.eye(dof), -np.eye(dof)))[None], (G, 1, 1)) * (1 + 0.1 * rng.rand(G, 1, 1))
+            gg = np.tile(np.r_[g["alim"][:, 1], -g["alim"][:, 0]][None], (G, 1)) * 1.5
+            xb = np.stack((np.zeros(G), np.full(G, 0.9)), axis=1)
+            return qs, qss, 0.01 * np.ones_like(qs), F, gg, None, xb
+
+    cons = [ta.constraint.JointVelocityConstraint(g["vlim"]), Custom()]
+    inst = ta.algorithm.TOPPRA(cons, path, gridpoints=grid, solver_wrapper="seidel")
+    sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+    a, b, c, F, gg, _, xb = cons[1]._host_params(inst.solver_wrapper.ctx)
+    rows = np.stack((np.einsum("gkm,gm->gk", F, a), np.einsum("gkm,gm->gk", F, b), np.einsum("gkm,gm->gk", F, c) - gg), axis=1)
+    xbound = np.stack((np.maximum(g["xbound"][:, 0], xb[:, 0]), np.minimum(np.minimum(g["xbound"][:, 1], 1e8), xb[:, 1])), axis=1)
+    o = orc.solve_rows(rows, xbound, grid, 0, 0)
+    assert o["status"] == 0 and inst.problem_data.return_code == ta.algorithm.ParameterizationReturnCode.Ok
+    np.testing.assert_allclose(K, o["K"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(sd, o["sd"], rtol=1e-12, atol=1e-14)
+    assert np.all(sd ** 2 <= 0.9 + 1e-12)

@@ -10,15 +10,19 @@ from .exceptions import BadInputVelocities
 from .interpolator import BatchSplineInterpolator
 
 
-def build_records(ctx, constraints):
+def build_records(ctx, constraints, out=None):
     """Stage records [B, G, W] for a list of CanonicalLinear constraints (= seidelWrapper.__init__,
-    cy_seidel_solverwrapper.pyx:425-531).  Returns (records, R)."""
+    cy_seidel_solverwrapper.pyx:425-531).  Returns (records, R).  `out`: optional preallocated buffer whose first
+    ctx.B records are (re)used (chunked solves)."""
     for c in constraints:
         if c.get_constraint_type() != ConstraintType.CanonicalLinear:
             raise NotImplementedError("only CanonicalLinear constraints can be turned into LP rows")
     rows = [c.num_rows(ctx) for c in constraints]
     R = int(sum(rows))
-    records, _ = engine.alloc_records(ctx.B, ctx.G, R, ctx.device)
+    if out is not None:
+        records = out[:ctx.B]
+    else:
+        records, _ = engine.alloc_records(ctx.B, ctx.G, R, ctx.device)
     kinds = [type(c) for c in constraints]
     if (len(constraints) == 2 and JointVelocityConstraint in kinds and JointAccelerationConstraint in kinds):
         # headline case: one fused K1 launch writes the velocity bound and the acceleration rows
@@ -28,8 +32,8 @@ def build_records(ctx, constraints):
             if ctx.bpath.dof != c.get_dof():
                 raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
                     c.get_dof(), ctx.bpath.dof))
-        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, vel.device_limits(ctx.device),
-                            acc.device_limits(ctx.device), acc.interpolation, records, R, 0, 1)
+        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, ctx.limits(vel.device_limits(ctx.device)),
+                            ctx.limits(acc.device_limits(ctx.device)), acc.interpolation, records, R, 0, 1)
         return records, R
     engine.init_bounds(records, R)
     row0 = 0
@@ -79,7 +83,7 @@ class BatchTOPPRA(object):
     gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
     """
 
-    def __init__(self, constraint_list, path, gridpoints):
+    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=16 << 30):
         if not isinstance(path, BatchSplineInterpolator):
             raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
         torch = engine.torch_mod()
@@ -99,6 +103,10 @@ class BatchTOPPRA(object):
         self.ctx = RecordContext(path, self.d_grid, grid_host, None)
         self.records = None
         self.R = None
+        # Stage records cost 8 * (3R + 2) * G bytes per path (138 KB at 7-DOF / 200 gridpoints): batches whose
+        # records exceed `max_record_bytes` are solved in chunks through one reused record buffer.
+        self.max_record_bytes = int(max_record_bytes)
+        self._grid_host = grid_host
 
     @property
     def B(self):
@@ -126,12 +134,44 @@ class BatchTOPPRA(object):
             return None  # kernels treat NULL as zeros
         return engine.as_device(np.ascontiguousarray(arr), self.device)
 
+    def chunk_size(self):
+        """Paths per chunk so that the record buffer stays within max_record_bytes."""
+        rows = sum(c.num_rows(self.ctx) for c in self.constraints)
+        per_path = 8 * engine.record_doubles(rows) * self.G
+        return max(1, min(self.B, self.max_record_bytes // per_path))
+
     def compute_parameterization(self, sd_start=0.0, sd_end=0.0, counters=False):
-        """Backward + forward pass for all paths (K2).  Returns a BatchResult (device tensors)."""
-        if self.records is None:
-            self.setup()
-        out = engine.scan(self.records, self.R, self.d_grid, self._vel_tensor(sd_start), self._vel_tensor(sd_end),
-                          counters=counters)
+        """Backward + forward pass for all paths (K1 + K2).  Returns a BatchResult (device tensors).
+        Large batches run in chunks of `chunk_size()` paths (K1 -> K2 per chunk, one record buffer)."""
+        torch = engine.torch_mod()
+        s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
+        nchunk = self.chunk_size()
+        if nchunk >= self.B:
+            if self.records is None:
+                self.setup()
+            return BatchResult(engine.scan(self.records, self.R, self.d_grid, s0, s1, counters=counters))
+        B, G, dev = self.B, self.G, self.device
+        out = dict(K=torch.empty((B, G, 2), dtype=torch.float64, device=dev),
+                   sd=torch.empty((B, G), dtype=torch.float64, device=dev),
+                   u=torch.empty((B, G - 1), dtype=torch.float64, device=dev),
+                   status=torch.empty((B,), dtype=torch.int32, device=dev),
+                   fail_stage=torch.empty((B,), dtype=torch.int32, device=dev))
+        if counters:
+            out["counters"] = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        buf = None
+        for lo in range(0, B, nchunk):
+            hi = min(B, lo + nchunk)
+            grid = self.d_grid if self.d_grid.dim() == 1 else self.d_grid[lo:hi]
+            ctx = RecordContext(self.path.chunk(lo, hi), grid, self._grid_host, None, lo, hi)
+            if buf is None:
+                buf, self.R = build_records(ctx, self.constraints)
+                rec = buf
+            else:
+                rec, _ = build_records(ctx, self.constraints, out=buf)
+            part = engine.scan(rec, self.R, grid, None if s0 is None else s0[lo:hi], None if s1 is None else s1[lo:hi],
+                               counters=counters)
+            for key in out:
+                out[key][lo:hi] = part[key]
         return BatchResult(out)
 
     def compute_controllable_sets(self, sdmin, sdmax):

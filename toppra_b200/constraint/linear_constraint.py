@@ -67,14 +67,20 @@ class LinearConstraint(Constraint):
 class RecordContext(object):
     """What a constraint needs to write its rows: the (batched) device path, the gridpoints on device and host."""
 
-    def __init__(self, bpath, d_grid, grid_host, path=None):
-        self.bpath = bpath          # BatchSplineInterpolator
+    def __init__(self, bpath, d_grid, grid_host, path=None, lo=0, hi=None):
+        self.bpath = bpath          # BatchSplineInterpolator (or a chunk view of one)
         self.d_grid = d_grid        # CUDA tensor [G] (shared) or [B, G]
         self.grid_host = grid_host  # numpy [G] (shared grids only) or None
         self.path = path            # the user's single path object (B == 1) or None
         self.B = bpath.B
         self.G = d_grid.shape[-1]
         self.device = bpath.device
+        self.lo = lo                # this context covers paths [lo, hi) of the full batch (chunked solves)
+        self.hi = self.B if hi is None else hi
+
+    def limits(self, t):
+        """Per-path limit tensors [Bfull, dof, 2] are sliced to this chunk; shared ones pass through."""
+        return t[self.lo:self.hi] if (t is not None and t.dim() == 3) else t
 
 
 def canlinear_colloc_to_interpolate(a, b, c, F, g, xbound, ubound, gridpoints, identical=False):

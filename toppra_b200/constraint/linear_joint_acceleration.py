@@ -50,7 +50,7 @@ class JointAccelerationConstraint(LinearConstraint):
         dof = self.dof
         R = self.num_rows(ctx)
         records, _ = engine.alloc_records(1, ctx.G, R, ctx.device)
-        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, None, self.device_limits(ctx.device),
+        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, None, ctx.limits(self.device_limits(ctx.device)),
                             self.interpolation, records, R, 0, 0)
         rec = records[0].cpu().numpy()
         arow, brow = rec[:, 0:R], rec[:, R:2 * R]
@@ -81,5 +81,5 @@ class JointAccelerationConstraint(LinearConstraint):
         if ctx.bpath.dof != self.dof:
             raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
                 self.dof, ctx.bpath.dof))
-        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, None, self.device_limits(ctx.device),
+        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, None, ctx.limits(self.device_limits(ctx.device)),
                             self.interpolation, records, R_total, row0, 0)

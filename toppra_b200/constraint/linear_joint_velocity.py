@@ -65,7 +65,7 @@ class JointVelocityConstraint(LinearConstraint):
         ctx = single_path_context(path, gridpoints)
         records, _ = engine.alloc_records(1, ctx.G, 0, ctx.device)
         # raw xbound of _create_velocity_constraint (no clipping to the solver box): write_xbound = 2
-        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, self.device_limits(ctx.device), None,
+        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, ctx.limits(self.device_limits(ctx.device)), None,
                             False, records, 0, 0, 2)
         xbound = records[0, :, 0:2].cpu().numpy().copy()
         return None, None, None, None, None, None, xbound
@@ -78,5 +78,5 @@ class JointVelocityConstraint(LinearConstraint):
         if ctx.bpath.dof != self.get_dof():
             raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
                 self.get_dof(), ctx.bpath.dof))
-        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, self.device_limits(ctx.device), None,
+        engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, ctx.limits(self.device_limits(ctx.device)), None,
                             False, records, R_total, 0, 3)

@@ -139,6 +139,8 @@ class SecondOrderConstraint(LinearConstraint):
         if self._eye_form is not None:
             g = self._eye_form[0]
             gd = engine.as_device(g, ctx.device)
+            if g.ndim == 2:
+                gd = gd[ctx.lo:ctx.hi].contiguous()
             mode = 2 if g.ndim == 1 else 3
             engine.rows_canlinear(a, b, c, None, gd, mode, ctx.d_grid, self.interpolation, records, R_total, row0)
         else:

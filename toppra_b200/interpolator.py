@@ -155,6 +155,16 @@ class BatchSplineInterpolator(object):
         out = self.eval_device(engine.as_device(s, self.device), order)
         return out.cpu().numpy()
 
+    def chunk(self, lo, hi):
+        """View of paths [lo, hi) sharing this object's device buffers (used by chunked batch solves)."""
+        view = object.__new__(BatchSplineInterpolator)
+        view.device, view.n, view._dof, view.bc_type = self.device, self.n, self._dof, self.bc_type
+        view.B = hi - lo
+        view.d_wp = self.d_wp[lo:hi]
+        view.d_ss = self.d_ss if self.d_ss.dim() == 1 else self.d_ss[lo:hi]
+        view.d_ppoly = self.d_ppoly[lo:hi]
+        return view
+
 
 class SplineInterpolator(AbstractGeometricPath):
     """Interpolate the given waypoints by cubic spline — drop-in for the reference class
