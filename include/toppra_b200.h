@@ -132,6 +132,19 @@ int tb_scan(const double *records, int W, int R, const double *grid, int grid_sh
             const double *sd_start, const double *sd_end, double *K, double *sd, double *u, int *status,
             int *fail_stage, void *stream);
 
+/* K2r — the same passes for a problem with ONE robustified constraint (RobustLinearConstraint,
+ * toppra/constraint/conic_constraint.py:47-124): rows [conic_row0, conic_row0 + conic_rows) of every record are
+ * robust rows  a u + b x + c + ||diag(ru, rx, rc) [u, x, 1]||_2 <= 0  with the ellipsoid axes
+ * ellipsoid_host3 = (ru, rx, rc) (HOST pointer, 3 doubles); the other rows are linear.  Stage problems follow
+ * ecosWrapper.solve_stagewise_optim (toppra/solverwrapper/ecos_solverwrapper.py:90-207): absent x / x_next bounds are
+ * -/+1000, x <= min(1e4, xbound_hi).  The reference solves them with ECOS (third party, interior point): results
+ * agree with it only to solver tolerance — parity for this entry is unpinned.
+ * flags / outputs as tb_scan_ex; counters[.][0] = evaluations of the feasible-u interval, [3] = forward retries. */
+int tb_scan_robust(const double *records, int W, int R, int conic_row0, int conic_rows, const double *ellipsoid_host3,
+                   const double *grid, int grid_shared, int B, int G, const double *sd_start, const double *sd_end,
+                   int flags, double *K, double *sd, double *u, int *status, int *fail_stage, int *counters,
+                   void *stream);
+
 /* Feasible sets X[B][G][2] (compute_feasible_sets). */
 int tb_feasible_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                      double *X, void *stream);
@@ -143,6 +156,7 @@ int tb_feasible_sets(const double *records, int W, int R, const double *grid, in
  *   counters (nullable): device [B][4] int32 = (2-D LP solves, 1-D LP solves, projected re-solves,
  *                        forward retries) — instrumentation for profiling. */
 #define TB_SCAN_BACKWARD_ONLY 1
+#define TB_SCAN_FEASIBLE_SETS 2 /* tb_scan_robust only: K receives the feasible sets X (compute_feasible_sets) */
 int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,
                double *u, int *status, int *fail_stage, int *counters, void *stream);

@@ -19,8 +19,8 @@ STATUS_NAMES = ["Ok", "ErrUnknown", "ErrShortPath", "FailUncontrollable", "ErrFo
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "toppra_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("toppra_oracle.c", "toppra_robust_oracle.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so", "-B"], stdout=subprocess.DEVNULL)
     return so
 
@@ -256,3 +256,23 @@ def solve_velacc_batch(c, x, grid, vlim, alim, interp=True, sd_start=None, sd_en
                                  1 if interp else 0, s0p, s1p, K.ctypes.data_as(_dp), sd.ctypes.data_as(_dp),
                                  u.ctypes.data_as(_dp), status.ctypes.data_as(_ip), int(nthreads))
     return dict(K=K, sd=sd, u=u, status=status)
+
+
+def solve_rows_robust(rows, xbound, grid, conic_row0, conic_rows, ellipsoid, sd_start=0.0, sd_end=0.0):
+    """Robust (conic) TOPP-RA over explicit rows — oracle/toppra_robust_oracle.c (parity UNPINNED: problem
+    definition only, see that file's header)."""
+    rows, rp = _d(rows)
+    grid, gp = _d(grid)
+    G, _, R = rows.shape
+    xp = None
+    if xbound is not None:
+        xbound, xp = _d(xbound)
+    ell, ep = _d(ellipsoid)
+    K = np.zeros((G, 2))
+    sd = np.zeros(G)
+    u = np.zeros(G - 1)
+    nev = ctypes.c_long()
+    st = lib().orc_solve_rows_robust(rp, xp, gp, G, R, int(conic_row0), int(conic_rows), ep, ctypes.c_double(sd_start),
+                                     ctypes.c_double(sd_end), K.ctypes.data_as(_dp), sd.ctypes.data_as(_dp),
+                                     u.ctypes.data_as(_dp), ctypes.byref(nev))
+    return dict(K=K, sd=sd, u=u, status=int(st), n_eval=nev.value)

@@ -33,6 +33,8 @@ _PROTOS = {
                        ctypes.c_void_p], _int),
     "tb_lp1d_batch": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _c_ip, _c_dp, _c_dp, _c_ip, ctypes.c_void_p],
                       _int),
+    "tb_scan_robust": ([_c_dp, _int, _int, _int, _int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _c_dp, _int, _c_dp, _c_dp,
+                        _c_dp, _c_ip, _c_ip, _c_ip, ctypes.c_void_p], _int),
     "tb_feasible_sets": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_solve_velacc_host": ([_int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _int, _int, _c_dp,
                               _c_dp, _c_dp, _c_dp, _c_dp, _c_ip], _int),

@@ -24,17 +24,24 @@ class ReachabilityAlgorithm(ParameterizationAlgorithm):
         super(ReachabilityAlgorithm, self).__init__(constraint_list, path, gridpoints=gridpoints,
                                                     parametrizer=parametrizer, **kwargs)
         has_conic = any(c.get_constraint_type() == ConstraintType.CanonicalConic for c in constraint_list)
+        solver_wrapper_given = solver_wrapper
         if solver_wrapper is None:
             logger.info("Solver wrapper not supplied. Choose solver wrapper automatically!")
             solver_wrapper = "seidel"
         name = solver_wrapper.lower()
         valid = [s for s, avail in available_solvers(output_msg=False) if avail]
         if has_conic:
-            raise exceptions.ToppraError("Solverwrapper not available: conic constraints are not supported yet.")
-        assert name in ["cvxpy", "qpoases", "ecos", "hotqpoases", "seidel", "b200"], \
-            "Solver {:} not found".format(solver_wrapper)
-        if name not in valid:
-            raise NotImplementedError("Solver wrapper {:} not found!".format(solver_wrapper))
+            # reference :78-84: conic problems need a conic solver ("ecos"/"cvxpy").  Those names (and "b200") map
+            # to the GPU conic scan (csrc/tb_robust.cu); "seidel" keeps the reference's assertion.
+            if solver_wrapper_given is None:
+                name = "b200"
+            assert name in ["cvxpy", "ecos", "b200"], \
+                "Problem has conic constraints, solver {:} is not suitable".format(solver_wrapper)
+        else:
+            assert name in ["cvxpy", "qpoases", "ecos", "hotqpoases", "seidel", "b200"], \
+                "Solver {:} not found".format(solver_wrapper)
+            if name not in valid:
+                raise NotImplementedError("Solver wrapper {:} not found!".format(solver_wrapper))
         self.solver_wrapper = B200SolverWrapper(self.constraints, self.path, self.gridpoints)
 
     def compute_feasible_sets(self):

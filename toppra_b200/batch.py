@@ -10,13 +10,37 @@ from .exceptions import BadInputVelocities
 from .interpolator import BatchSplineInterpolator
 
 
+def conic_info(ctx, constraints):
+    """(row0, nrows, ellipsoid) of the robust constraint of the list, or None."""
+    row0 = 0
+    for c in constraints:
+        n = c.num_rows(ctx)
+        if c.get_constraint_type() == ConstraintType.CanonicalConic:
+            return row0, n, c.ellipsoid()
+        row0 += n
+    return None
+
+
+def scan_any(records, R, grid, conic, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False,
+             counters=False):
+    """K2 for purely linear problems, K2r when a robust constraint is present."""
+    if conic is None:
+        return engine.scan(records, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters)
+    if sd_end_hi is not None:
+        raise NotImplementedError("robust problems: compute_controllable_sets needs sdmin == sdmax")
+    return engine.scan_robust(records, R, conic[0], conic[1], conic[2], grid, sd_start, sd_end, backward_only, counters)
+
+
 def build_records(ctx, constraints, out=None):
     """Stage records [B, G, W] for a list of CanonicalLinear constraints (= seidelWrapper.__init__,
     cy_seidel_solverwrapper.pyx:425-531).  Returns (records, R).  `out`: optional preallocated buffer whose first
     ctx.B records are (re)used (chunked solves)."""
+    conic = [c for c in constraints if c.get_constraint_type() == ConstraintType.CanonicalConic]
+    if len(conic) > 1:
+        raise NotImplementedError("toppra_b200: at most one robust (conic) constraint per problem")
     for c in constraints:
-        if c.get_constraint_type() != ConstraintType.CanonicalLinear:
-            raise NotImplementedError("only CanonicalLinear constraints can be turned into LP rows")
+        if c.get_constraint_type() not in (ConstraintType.CanonicalLinear, ConstraintType.CanonicalConic):
+            raise NotImplementedError("constraint type %s cannot be turned into stage rows" % c.get_constraint_type())
     rows = [c.num_rows(ctx) for c in constraints]
     R = int(sum(rows))
     if out is not None:
@@ -107,6 +131,7 @@ class BatchTOPPRA(object):
         # records exceed `max_record_bytes` are solved in chunks through one reused record buffer.
         self.max_record_bytes = int(max_record_bytes)
         self._grid_host = grid_host
+        self.conic = conic_info(self.ctx, self.constraints)
 
     @property
     def B(self):
@@ -149,7 +174,7 @@ class BatchTOPPRA(object):
         if nchunk >= self.B:
             if self.records is None:
                 self.setup()
-            return BatchResult(engine.scan(self.records, self.R, self.d_grid, s0, s1, counters=counters))
+            return BatchResult(scan_any(self.records, self.R, self.d_grid, self.conic, s0, s1, counters=counters))
         B, G, dev = self.B, self.G, self.device
         out = dict(K=torch.empty((B, G, 2), dtype=torch.float64, device=dev),
                    sd=torch.empty((B, G), dtype=torch.float64, device=dev),
@@ -168,8 +193,8 @@ class BatchTOPPRA(object):
                 rec = buf
             else:
                 rec, _ = build_records(ctx, self.constraints, out=buf)
-            part = engine.scan(rec, self.R, grid, None if s0 is None else s0[lo:hi], None if s1 is None else s1[lo:hi],
-                               counters=counters)
+            part = scan_any(rec, self.R, grid, self.conic, None if s0 is None else s0[lo:hi],
+                            None if s1 is None else s1[lo:hi], counters=counters)
             for key in out:
                 out[key][lo:hi] = part[key]
         return BatchResult(out)
@@ -181,13 +206,17 @@ class BatchTOPPRA(object):
         lo = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmin, dtype=np.float64), (self.B,)))
         hi = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmax, dtype=np.float64), (self.B,)))
         assert np.all(lo <= hi) and np.all(0 <= lo)
-        out = engine.scan(self.records, self.R, self.d_grid, None, engine.as_device(lo, self.device),
-                          engine.as_device(hi, self.device), backward_only=True)
+        same = bool(np.all(lo == hi))
+        out = scan_any(self.records, self.R, self.d_grid, self.conic, None, engine.as_device(lo, self.device),
+                       None if same else engine.as_device(hi, self.device), backward_only=True)
         return out["K"], out["status"]
 
     def compute_feasible_sets(self):
         if self.records is None:
             self.setup()
+        if self.conic is not None:
+            return engine.scan_robust(self.records, self.R, self.conic[0], self.conic[1], self.conic[2], self.d_grid,
+                                      feasible_sets=True)["K"]
         return engine.feasible_sets(self.records, self.R, self.d_grid)
 
 

@@ -4,7 +4,8 @@ from .linear_constraint import LinearConstraint, canlinear_colloc_to_interpolate
 from .linear_joint_acceleration import JointAccelerationConstraint
 from .linear_joint_velocity import JointVelocityConstraint
 from .linear_second_order import SecondOrderConstraint
+from .conic_constraint import ConicConstraint, RobustLinearConstraint
 
 __all__ = ["ConstraintType", "DiscretizationType", "Constraint", "LinearConstraint",
            "canlinear_colloc_to_interpolate", "JointAccelerationConstraint", "JointVelocityConstraint",
-           "SecondOrderConstraint", "RecordContext"]
+           "SecondOrderConstraint", "RecordContext", "ConicConstraint", "RobustLinearConstraint"]

@@ -168,6 +168,35 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     return out
 
 
+def scan_robust(records, R, conic_row0, conic_rows, ellipsoid, grid, sd_start=None, sd_end=None, backward_only=False,
+                counters=False, feasible_sets=False):
+    """K2r: like scan() with rows [conic_row0, conic_row0+conic_rows) robustified by the ellipsoid (ru, rx, rc)."""
+    torch = torch_mod()
+    B, G, W = records.shape
+    dev = records.device
+    backward_only = backward_only or feasible_sets
+    K = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+    sd = None if backward_only else torch.empty((B, G), dtype=torch.float64, device=dev)
+    u = None if backward_only else torch.empty((B, max(G - 1, 1)), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    fail_stage = torch.empty((B,), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B, 4), dtype=torch.int32, device=dev) if counters else None
+    ell = np.ascontiguousarray(ellipsoid, dtype=np.float64)
+    assert ell.shape == (3,)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_scan_robust(_lib.ptr(records), W, int(R), int(conic_row0), int(conic_rows),
+                                        ctypes.c_void_p(ell.ctypes.data), _lib.ptr(grid), 1 if grid.dim() == 1 else 0,
+                                        B, G, _lib.ptr(sd_start), _lib.ptr(sd_end),
+                                        2 if feasible_sets else (1 if backward_only else 0),
+                                        _lib.ptr(K), _lib.ptr(sd), _lib.ptr(u), _lib.ptr(status), _lib.ptr(fail_stage),
+                                        _lib.ptr(cnt), _lib.stream_ptr())
+    _lib.check(rc, "tb_scan_robust")
+    out = dict(K=K, sd=sd, u=None if u is None else u[:, :max(G - 1, 0)], status=status, fail_stage=fail_stage)
+    if counters:
+        out["counters"] = cnt
+    return out
+
+
 def feasible_sets(records, R, grid):
     torch = torch_mod()
     B, G, W = records.shape

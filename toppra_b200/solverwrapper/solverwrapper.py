@@ -64,18 +64,23 @@ class B200SolverWrapper(SolverWrapper):
     """GPU implementation of the reference `seidelWrapper` (Seidel's LP, solve_lp1d=True)."""
 
     def __init__(self, constraint_list, path, path_discretization, solve_lp1d=True):
-        from ..batch import build_records
+        from ..batch import build_records, conic_info
         super(B200SolverWrapper, self).__init__(constraint_list, path, path_discretization)
         bpath = path.as_batch()
         grid = np.ascontiguousarray(self.path_discretization, dtype=np.float64)
         self.ctx = RecordContext(bpath, engine.as_device(grid, bpath.device), grid, path)
         self.records, self.R = build_records(self.ctx, constraint_list)
+        self.conic = conic_info(self.ctx, constraint_list)
         self.nC = self.R + 2
         self._solve_lp1d = solve_lp1d
         self._params = None
         self._rows_host = None
         self.active_c_up = np.zeros(2, dtype=np.int32)    # warm-start slots, pyx:526-527
         self.active_c_down = np.zeros(2, dtype=np.int32)
+
+    def _no_conic(self, what):
+        if self.conic is not None:
+            raise NotImplementedError("%s is not available for problems with a robust (conic) constraint" % what)
 
     @property
     def params(self):
@@ -103,6 +108,7 @@ class B200SolverWrapper(SolverWrapper):
         stage-i rows, x_min <= x <= x_max, x_next_min <= x + 2 delta_i u <= x_next_max (NaN = bound absent).
         Returns [u, x] or [nan, nan] when infeasible.  One small launch per call (tb_lp1d_batch / tb_lp2d_batch)."""
         assert 0 <= i <= self.N
+        self._no_conic("solve_stagewise_optim")
         if self._rows_host is None:
             self._rows_host = self.rows()
         rows = self._rows_host
@@ -139,8 +145,9 @@ class B200SolverWrapper(SolverWrapper):
         return engine.as_device(np.array([float(v)]), self.ctx.device)
 
     def parameterize(self, sd_start, sd_end, counters=False):
-        out = engine.scan(self.records, self.R, self.ctx.d_grid, self._scalar(sd_start), self._scalar(sd_end),
-                          counters=counters)
+        from ..batch import scan_any
+        out = scan_any(self.records, self.R, self.ctx.d_grid, self.conic, self._scalar(sd_start), self._scalar(sd_end),
+                       counters=counters)
         res = dict(K=out["K"][0].cpu().numpy(), sd=out["sd"][0].cpu().numpy(), u=out["u"][0].cpu().numpy(),
                    status=int(out["status"][0].item()), fail_stage=int(out["fail_stage"][0].item()))
         if counters:
@@ -148,9 +155,13 @@ class B200SolverWrapper(SolverWrapper):
         return res
 
     def controllable_sets(self, sdmin, sdmax):
-        out = engine.scan(self.records, self.R, self.ctx.d_grid, None, self._scalar(sdmin), self._scalar(sdmax),
-                          backward_only=True)
+        from ..batch import scan_any
+        out = scan_any(self.records, self.R, self.ctx.d_grid, self.conic, None, self._scalar(sdmin),
+                       None if sdmin == sdmax else self._scalar(sdmax), backward_only=True)
         return out["K"][0].cpu().numpy(), int(out["status"][0].item())
 
     def feasible_sets(self):
+        if self.conic is not None:
+            return engine.scan_robust(self.records, self.R, self.conic[0], self.conic[1], self.conic[2],
+                                      self.ctx.d_grid, feasible_sets=True)["K"][0].cpu().numpy()
         return engine.feasible_sets(self.records, self.R, self.ctx.d_grid)[0].cpu().numpy()
