@@ -175,6 +175,17 @@ int tb_lp2d_batch(const double *v, const double *a, const double *b, const doubl
 int tb_lp1d_batch(const double *v, const double *a, const double *b, const double *low, const double *high, int B,
                   int n, int *result, double *optval, double *optvar, int *active_out, void *stream);
 
+/* K3 — output trajectory under the constant-acceleration assumption (ParametrizeConstAccel,
+ * toppra/parametrizer.py:23-158).
+ *   tb_time_grid: t_grid [B][G] time stamps of the gridpoints (t_0 = 0), us (nullable) [B][G-1] path accelerations,
+ *                 from sd [B][G]; the duration of path b is t_grid[b][G-1].
+ *   tb_constaccel_eval: out [B][M][dof] = q(t) (order 0), qd(t) (1), qdd(t) (2) at times ts [M] (ts_shared=1) or [B][M]. */
+int tb_time_grid(const double *sd, const double *grid, int grid_shared, int B, int G, double *t_grid, double *us,
+                 void *stream);
+int tb_constaccel_eval(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof, const double *grid,
+                       int grid_shared, const double *sd, const double *t_grid, const double *us, int B, int G,
+                       const double *ts, int ts_shared, int M, int order, double *out, void *stream);
+
 /* Whole pipeline with HOST buffers (K0 -> K1 -> K2, H2D/D2H inside, synchronous):
  *   ss [n] shared; wp [B][n][dof]; grid [G] shared; vlim (nullable) / alim: [dof][2] shared or [B][dof][2];
  *   outputs (host): K [B][G][2], sd [B][G], u [B][G-1], status [B].  device: CUDA device ordinal. */

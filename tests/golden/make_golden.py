@@ -92,6 +92,13 @@ def main():
     ts = np.linspace(0, traj.duration, 50)
     out.update(ss=ss, way=way, vlim=vlim, alim=alim, grid=grid, traj_duration=np.float64(traj.duration),
                traj_ts=ts, traj_q=traj(ts), traj_qd=traj(ts, 1), traj_qdd=traj(ts, 2))
+    # constant-acceleration output (ParametrizeConstAccel, parametrizer.py:23-158)
+    ca = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
+                     ta.SplineInterpolator(ss, way), gridpoints=grid, solver_wrapper="seidel",
+                     parametrizer="ParametrizeConstAccel").compute_trajectory(0, 0)
+    ca_ts = np.linspace(0, ca.duration, 64)
+    out.update(ca_duration=np.float64(ca.duration), ca_ts=ca_ts, ca_q=ca(ca_ts), ca_qd=ca(ca_ts, 1), ca_qdd=ca(ca_ts, 2),
+               ca_tgrid=ca._ts, ca_us=ca._us)
     # the example's own automatic grid
     auto = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
                        ta.SplineInterpolator(ss, way), solver_wrapper="seidel")

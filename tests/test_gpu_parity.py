@@ -346,3 +346,28 @@ def test_custom_linear_constraint_generic_rows(ta, orc, golden):
     np.testing.assert_allclose(K, o["K"], rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(sd, o["sd"], rtol=1e-12, atol=1e-14)
     assert np.all(sd ** 2 <= 0.9 + 1e-12)
+
+
+def test_const_accel_parametrizer_on_device(ta, golden):
+    """K3: time stamps bit-exact (sequential sum like the reference); q/qd/qdd at sample times."""
+    g = golden("cfg1_seed9")
+    path = ta.SplineInterpolator(g["ss"], g["way"])
+    inst = ta.algorithm.TOPPRA(_cons(ta, g), path, gridpoints=g["grid"], parametrizer="ParametrizeConstAccel")
+    traj = inst.compute_trajectory(0, 0)
+    assert _eq(traj._ts, g["ca_tgrid"]) and _eq(traj._us, g["ca_us"]) and traj.duration == float(g["ca_duration"])
+    # evaluation: same formulas, the reference evaluates q(s) with scipy at s computed in numpy -> rounding-level
+    np.testing.assert_allclose(traj(g["ca_ts"]), g["ca_q"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(traj(g["ca_ts"], 1), g["ca_qd"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(traj(g["ca_ts"], 2), g["ca_qdd"], rtol=1e-10, atol=1e-10)
+    assert traj(0.5).shape == (7,) and traj.dof == 7
+    # batched form: durations of a whole batch in one launch
+    gb = golden("cfg2_seeds1000")
+    bpath = ta.BatchSplineInterpolator(gb["ss"], gb["way"])
+    res = ta.BatchTOPPRA(_cons(ta, gb), bpath, gb["grid"]).compute_parameterization(0, 0)
+    bp = ta.BatchParametrizeConstAccel(bpath, gb["grid"], res.sd)
+    dur = bp.durations.cpu().numpy()
+    ref = np.array([np.sum(2 * np.diff(gb["grid"]) / (gb["sd"][b][1:] + gb["sd"][b][:-1])) for b in range(len(dur))])
+    np.testing.assert_allclose(dur, ref, rtol=1e-13)
+    q_end = bp(np.stack([np.array([0.0, d]) for d in dur]), 0).cpu().numpy()
+    np.testing.assert_allclose(q_end[:, 0], gb["way"][:, 0], atol=1e-12)
+    np.testing.assert_allclose(q_end[:, 1], gb["way"][:, -1], atol=1e-9)

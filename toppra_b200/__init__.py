@@ -8,7 +8,7 @@ import logging
 
 from . import constants, exceptions
 from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, SplineInterpolator, propose_gridpoints)
-from .parametrizer import ParametrizeConstAccel, ParametrizeSpline
+from .parametrizer import BatchParametrizeConstAccel, ParametrizeConstAccel, ParametrizeSpline
 from . import constraint
 from . import solverwrapper
 from . import algorithm
@@ -19,5 +19,5 @@ __version__ = "0.1.0"
 logging.getLogger("toppra_b200").addHandler(logging.NullHandler())
 
 __all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "SplineInterpolator", "propose_gridpoints",
-           "ParametrizeConstAccel", "ParametrizeSpline", "constraint", "solverwrapper", "algorithm", "BatchResult",
+           "ParametrizeConstAccel", "ParametrizeSpline", "BatchParametrizeConstAccel", "constraint", "solverwrapper", "algorithm", "BatchResult",
            "BatchTOPPRA", "solve_batch", "constants", "exceptions"]

@@ -35,6 +35,9 @@ _PROTOS = {
                       _int),
     "tb_scan_robust": ([_c_dp, _int, _int, _int, _int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _c_dp, _int, _c_dp, _c_dp,
                         _c_dp, _c_ip, _c_ip, _c_ip, ctypes.c_void_p], _int),
+    "tb_time_grid": ([_c_dp, _c_dp, _int, _int, _int, _c_dp, _c_dp, ctypes.c_void_p], _int),
+    "tb_constaccel_eval": ([_c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _int, _int, _c_dp, _int,
+                            _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_feasible_sets": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_solve_velacc_host": ([_int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _int, _int, _c_dp,
                               _c_dp, _c_dp, _c_dp, _c_dp, _c_ip], _int),

@@ -284,3 +284,32 @@ def lp1d_batch(v, a, b, low, high):
                                        _lib.ptr(optvar), _lib.ptr(active), _lib.stream_ptr())
     _lib.check(rc, "tb_lp1d_batch")
     return result.cpu().numpy(), optval.cpu().numpy(), optvar.cpu().numpy(), active.cpu().numpy()
+
+
+def time_grid(sd, grid):
+    """K3: const-accel time stamps.  sd [B,G], grid [G] or [B,G] -> (t_grid [B,G], us [B,G-1])."""
+    torch = torch_mod()
+    B, G = sd.shape
+    t = torch.empty((B, G), dtype=torch.float64, device=sd.device)
+    us = torch.empty((B, G - 1), dtype=torch.float64, device=sd.device)
+    with torch.cuda.device(sd.device):
+        rc = _lib.load().tb_time_grid(_lib.ptr(sd), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G, _lib.ptr(t),
+                                      _lib.ptr(us), _lib.stream_ptr())
+    _lib.check(rc, "tb_time_grid")
+    return t, us
+
+
+def constaccel_eval(ppoly, breaks, grid, sd, t_grid, us, ts, order):
+    """K3: q / qd / qdd at times ts ([M] shared or [B,M]) -> [B,M,dof]."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    G = sd.shape[1]
+    M = ts.shape[-1]
+    out = torch.empty((B, M, dof), dtype=torch.float64, device=sd.device)
+    with torch.cuda.device(sd.device):
+        rc = _lib.load().tb_constaccel_eval(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, nseg, dof,
+                                            _lib.ptr(grid), 1 if grid.dim() == 1 else 0, _lib.ptr(sd), _lib.ptr(t_grid),
+                                            _lib.ptr(us), B, G, _lib.ptr(ts), 1 if ts.dim() == 1 else 0, M, int(order),
+                                            _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "tb_constaccel_eval")
+    return out

@@ -7,6 +7,7 @@ import logging
 
 import numpy as np
 
+from . import engine
 from .constants import TINY
 from .exceptions import ToppraError
 from .interpolator import AbstractGeometricPath, SplineInterpolator
@@ -14,9 +15,34 @@ from .interpolator import AbstractGeometricPath, SplineInterpolator
 logger = logging.getLogger(__name__)
 
 
+class BatchParametrizeConstAccel(object):
+    """Output trajectories of B paths under the piecewise-constant path-acceleration assumption, on the GPU
+    (csrc/tb_param.cu).  path: BatchSplineInterpolator; gridpoints: CUDA tensor [G] or [B, G]; velocities: sd [B, G]."""
+
+    def __init__(self, path, gridpoints, velocities):
+        self._path = path
+        self.d_grid = engine.as_device(gridpoints, path.device)
+        self.d_sd = engine.as_device(velocities, path.device)
+        self.t_grid, self.us = engine.time_grid(self.d_sd, self.d_grid)
+
+    @property
+    def durations(self):
+        """CUDA tensor [B]: duration of every trajectory."""
+        return self.t_grid[:, -1]
+
+    def __call__(self, ts, order=0):
+        """ts: [M] (shared) or [B, M] times -> CUDA tensor [B, M, dof] of q (order 0), qd (1) or qdd (2)."""
+        if order not in (0, 1, 2):
+            raise ToppraError(f"Order {order} is not supported.")
+        ts = engine.as_device(ts, self._path.device)
+        return engine.constaccel_eval(self._path.d_ppoly, self._path.d_ss, self.d_grid, self.d_sd, self.t_grid,
+                                      self.us, ts, order)
+
+
 class ParametrizeConstAccel(AbstractGeometricPath):
-    """Output trajectory under the piecewise-constant path-acceleration assumption:
-    on [s_i, s_{i+1}]  u_i = (x_{i+1} - x_i) / (2 ds),  t_{i+1} = t_i + 2 ds / (sd_i + sd_{i+1})."""
+    """Output trajectory under the piecewise-constant path-acceleration assumption (reference
+    parametrizer.py:23-158): on [s_i, s_{i+1}]  u_i = (x_{i+1} - x_i) / (2 ds),
+    t_{i+1} = t_i + 2 ds / (sd_i + sd_{i+1}).  Time stamps and evaluation run on the GPU (csrc/tb_param.cu)."""
 
     def __init__(self, path, gridpoints, velocities):
         self._path = path
@@ -26,13 +52,9 @@ class ParametrizeConstAccel(AbstractGeometricPath):
         assert self._ss.shape[0] == self._velocities.shape[0]
         assert len(self._ss.shape) == 1
         assert np.all(self._velocities >= 0)
-        ds = np.diff(self._ss)
-        self._us = 0.5 * (self._xs[1:] - self._xs[:-1]) / ds
-        dts = 2 * ds / (self._velocities[:-1] + self._velocities[1:])
-        ts = np.zeros(len(self._ss))
-        for i in range(len(dts)):  # sequential sum keeps the reference's rounding order
-            ts[i + 1] = ts[i] + dts[i]
-        self._ts = ts
+        self._batch = BatchParametrizeConstAccel(path.as_batch(), self._ss, self._velocities[None])
+        self._ts = self._batch.t_grid[0].cpu().numpy()
+        self._us = self._batch.us[0].cpu().numpy()
 
     @property
     def dof(self):
@@ -46,28 +68,14 @@ class ParametrizeConstAccel(AbstractGeometricPath):
     def duration(self):
         return self.path_interval[1] - self.path_interval[0]
 
-    def _eval_params(self, ts):
-        idx = np.searchsorted(self._ts, ts, side="right") - 1
-        idx = np.where(idx == len(self._us), idx - 1, idx)
-        dt = ts - self._ts[idx]
-        us = self._us[idx]
-        vs = self._velocities[idx] + dt * us
-        ss = self._ss[idx] + dt * self._velocities[idx] + 0.5 * dt ** 2 * us
-        return ss, vs, us
-
     def __call__(self, ts, order=0):
         scalar = isinstance(ts, (int, float))
         ts = np.array([ts], dtype=float) if scalar else np.asarray(ts, dtype=float)
-        ss, vs, us = self._eval_params(ts)
-        if order == 0:
-            out = self._path(ss)
-        elif order == 1:
-            out = np.multiply(self._path(ss, 1), vs[:, np.newaxis])
-        elif order == 2:
-            out = (np.multiply(self._path(ss, 2), vs[:, np.newaxis] ** 2)
-                   + np.multiply(self._path(ss, 1), us[:, np.newaxis]))
-        else:
+        if order not in (0, 1, 2):
             raise ToppraError(f"Order {order} is not supported.")
+        out = self._batch(ts.reshape(-1), order)[0].cpu().numpy().reshape(ts.shape + (self._path.as_batch().dof,))
+        if getattr(self._path, "_scalar_dof", False):
+            out = out[..., 0]
         return out[0] if scalar else out
 
 
