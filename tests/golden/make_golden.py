@@ -99,6 +99,14 @@ def main():
     ca_ts = np.linspace(0, ca.duration, 64)
     out.update(ca_duration=np.float64(ca.duration), ca_ts=ca_ts, ca_q=ca(ca_ts), ca_qd=ca(ca_ts, 1), ca_qdd=ca(ca_ts, 2),
                ca_tgrid=ca._ts, ca_us=ca._us)
+    # TOPPRAsd (desired duration) and reachable sets on the same problem
+    sd_inst = algo.TOPPRAsd([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
+                            ta.SplineInterpolator(ss, way), gridpoints=grid, solver_wrapper="seidel")
+    for tag, dur in (("sd5", 5.0), ("sd_fast", 1.0), ("sd_slow", 1e9)):
+        sd_inst.set_desired_duration(dur)
+        sdd_d, sd_d, _, _ = sd_inst.compute_parameterization(0, 0, return_data=True)
+        out[tag + "_sd"], out[tag + "_sdd"] = sd_d, sdd_d
+    out["L_0_05"] = inst.compute_reachable_sets(0.0, 0.5)
     # the example's own automatic grid
     auto = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
                        ta.SplineInterpolator(ss, way), solver_wrapper="seidel")

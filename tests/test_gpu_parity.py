@@ -371,3 +371,20 @@ def test_const_accel_parametrizer_on_device(ta, golden):
     q_end = bp(np.stack([np.array([0.0, d]) for d in dur]), 0).cpu().numpy()
     np.testing.assert_allclose(q_end[:, 0], gb["way"][:, 0], atol=1e-12)
     np.testing.assert_allclose(q_end[:, 1], gb["way"][:, -1], atol=1e-9)
+
+
+def test_toppra_sd_and_reachable_sets(ta, golden):
+    """TOPPRAsd (fastest/slowest passes on the GPU + the reference's bisection) and
+    compute_reachable_sets (per-stage LPs through solve_stagewise_optim), bit-exact vs the reference."""
+    g = golden("cfg1_seed9")
+    path = ta.SplineInterpolator(g["ss"], g["way"])
+    inst = ta.algorithm.TOPPRAsd(_cons(ta, g), path, gridpoints=g["grid"], solver_wrapper="seidel")
+    for tag, dur in (("sd5", 5.0), ("sd_fast", 1.0), ("sd_slow", 1e9)):
+        inst.set_desired_duration(dur)
+        sdd, sd, v, K = inst.compute_parameterization(0, 0, return_data=True)
+        assert _eq(sd, g[tag + "_sd"]) and _eq(sdd, g[tag + "_sdd"]) and _eq(K, g["K"]), tag
+    inst.set_desired_duration(5.0)
+    traj = inst.compute_trajectory(0, 0)
+    assert abs(traj.duration - 5.0) < 1e-3
+    L = ta.algorithm.TOPPRA(_cons(ta, g), path, gridpoints=g["grid"]).compute_reachable_sets(0.0, 0.5)
+    assert _eq(L, g["L_0_05"])

@@ -317,6 +317,8 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
   double *Kp = Kout + (size_t)path * G * 2;
   const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
+  const bool sd_mode = (flags & 4) != 0;        // TOPPRAsd forward-pass rules (no retry, x_next - 1e-5 clip)
+  const bool sd_slow = (flags & 8) != 0;        // TOPPRAsd slowest pass: minimise the next velocity
   double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
   double *up = backward_only ? nullptr : uout + (size_t)path * (G > 1 ? G - 1 : 0);
 
@@ -430,26 +432,32 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       bool ok;
       double uopt = 0.0;
       while (true) {
-        // _forward_step: g = (-2 delta, -1), x_min = x_max = x -> 1-D branch, v0 = 2 delta (pyx:628-636)
+        // _forward_step: g = (-2 delta, -1), x_min = x_max = x -> 1-D branch, v0 = 2 delta (pyx:628-636);
+        // TOPPRAsd's slowest pass uses g = (2 delta, 1) (desired_duration_algorithm.py:218-223)
         ++n_lp1d;
-        ok = lp1d_fixed_x_warp<RPL>(-(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
-        if (ok || tries >= MAX_TRIES) break;
+        ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
+        if (ok || sd_mode || tries >= MAX_TRIES) break;  // TOPPRAsd has no retry rule
         x = fmax(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
         ++tries;
         ++n_retry;
       }
       if (!ok) {
         // reachability_algorithm.py:337-342: xs[i+1:] = nan -> sd NaN -> ErrUnknown; us stay 0
+        // (TOPPRAsd: us[i:] and xs[i+1:] become NaN, desired_duration_algorithm.py:106-111)
         st = TB_STATUS_ERR_UNKNOWN;
         fstage = i;
         if (lane == 0) sdp[i] = x;
         for (int j = i + 1 + lane; j < G; j += 32) sdp[j] = nan_d;
-        for (int j = i + lane; j < N; j += 32) up[j] = 0.0;
+        for (int j = i + lane; j < N; j += 32) up[j] = sd_mode ? nan_d : 0.0;
         break;
       }
       double x_next = x + 2 * delta * uopt;                       // reachability_algorithm.py:352
-      x_next = fmax(x_next - ALG_TINY, 0.9999 * x_next);          // :353
-      x_next = fmin(k1, fmax(k0, x_next));                        // :354
+      if (sd_mode) {
+        x_next = fmin(k1, fmax(k0, x_next - ALG_SMALL));          // desired_duration_algorithm.py:117
+      } else {
+        x_next = fmax(x_next - ALG_TINY, 0.9999 * x_next);        // :353
+        x_next = fmin(k1, fmax(k0, x_next));                      // :354
+      }
       if (lane == 0) {
         up[i] = uopt;
         if (tries) sdp[i] = x;  // x was shrunk by the retry rule
@@ -459,7 +467,8 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     }
     while (n_waited < n_issued) (void)acquire();
     __syncwarp();
-    for (int j = lane; j < G; j += 32) sdp[j] = sqrt(sdp[j]);  // reachability_algorithm.py:365
+    if (!sd_mode)  // TOPPRAsd combines the squared velocities: its passes return x = sd^2
+      for (int j = lane; j < G; j += 32) sdp[j] = sqrt(sdp[j]);  // reachability_algorithm.py:365
   }
   if (lane == 0) {
     status[path] = st;

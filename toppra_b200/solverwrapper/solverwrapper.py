@@ -144,10 +144,15 @@ class B200SolverWrapper(SolverWrapper):
     def _scalar(self, v):
         return engine.as_device(np.array([float(v)]), self.ctx.device)
 
-    def parameterize(self, sd_start, sd_end, counters=False):
+    def parameterize(self, sd_start, sd_end, counters=False, sd_forward=None):
         from ..batch import scan_any
-        out = scan_any(self.records, self.R, self.ctx.d_grid, self.conic, self._scalar(sd_start), self._scalar(sd_end),
-                       counters=counters)
+        if sd_forward is not None:
+            self._no_conic("TOPPRAsd")
+            out = engine.scan(self.records, self.R, self.ctx.d_grid, self._scalar(sd_start), self._scalar(sd_end),
+                              counters=counters, sd_forward=sd_forward)
+        else:
+            out = scan_any(self.records, self.R, self.ctx.d_grid, self.conic, self._scalar(sd_start),
+                           self._scalar(sd_end), counters=counters)
         res = dict(K=out["K"][0].cpu().numpy(), sd=out["sd"][0].cpu().numpy(), u=out["u"][0].cpu().numpy(),
                    status=int(out["status"][0].item()), fail_stage=int(out["fail_stage"][0].item()))
         if counters:
