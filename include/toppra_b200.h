@@ -111,6 +111,12 @@ int tb_coeff_velacc(const double *ppoly, const double *breaks, int breaks_shared
                     int lim_shared, int interp, double *records, int W, int R_total, int row0, int write_xbound,
                     void *stream);
 
+/* JointVelocityConstraintVarying (toppra/constraint/linear_joint_velocity.py:56-87): velocity limits per gridpoint,
+ * vlim_grid [G][dof][2] (vlim_shared=1) or [B][G][dof][2]; write_xbound 1/2/3 as in tb_coeff_velacc. */
+int tb_xbound_varying(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                      const double *grid, int grid_shared, int G, const double *vlim_grid, int vlim_shared,
+                      double *records, int W, int R_total, int write_xbound, void *stream);
+
 /* Row assembly for a generic CanonicalLinear constraint given its collocation parameters:
  *   a, b, c: [B][G][m];  F: [k][m] (F_mode=0, identical) or [B][G][k][m] (F_mode=1);
  *   g: [k] / [B][G][k];  F_mode=2: F = [I; -I] (k = 2m) with g: [k] shared (torque-limit form);

@@ -107,6 +107,13 @@ def main():
         sdd_d, sd_d, _, _ = sd_inst.compute_parameterization(0, 0, return_data=True)
         out[tag + "_sd"], out[tag + "_sdd"] = sd_d, sdd_d
     out["L_0_05"] = inst.compute_reachable_sets(0.0, 0.5)
+    # varying velocity limits (linear_joint_velocity.py:56-87): vlim(s) = vlim * (0.05 + 0.5 s) -> active bound
+    vfun = lambda s: vlim * (0.05 + 0.5 * s)  # noqa: E731
+    pc_var = constraint.JointVelocityConstraintVarying(vfun)
+    out["var_xbound"] = pc_var.compute_constraint_params(ta.SplineInterpolator(ss, way), grid)[-1]
+    var_inst = algo.TOPPRA([pc_var, constraint.JointAccelerationConstraint(alim)], ta.SplineInterpolator(ss, way),
+                           gridpoints=grid, solver_wrapper="seidel")
+    _, out["var_sd"], _, out["var_K"] = var_inst.compute_parameterization(0, 0, return_data=True)
     # the example's own automatic grid
     auto = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
                        ta.SplineInterpolator(ss, way), solver_wrapper="seidel")

@@ -388,3 +388,17 @@ def test_toppra_sd_and_reachable_sets(ta, golden):
     assert abs(traj.duration - 5.0) < 1e-3
     L = ta.algorithm.TOPPRA(_cons(ta, g), path, gridpoints=g["grid"]).compute_reachable_sets(0.0, 0.5)
     assert _eq(L, g["L_0_05"])
+
+
+def test_velocity_constraint_varying(ta, golden):
+    """JointVelocityConstraintVarying (limits as a function of s), bit-exact vs the reference."""
+    g = golden("cfg1_seed9")
+    path = ta.SplineInterpolator(g["ss"], g["way"])
+    vlim = g["vlim"]
+    pc_var = ta.constraint.JointVelocityConstraintVarying(lambda s: vlim * (0.05 + 0.5 * s))
+    assert pc_var.get_dof() == 7
+    assert _eq(pc_var.compute_constraint_params(path, g["grid"])[-1], g["var_xbound"])
+    inst = ta.algorithm.TOPPRA([pc_var, ta.constraint.JointAccelerationConstraint(g["alim"])], path,
+                               gridpoints=g["grid"], solver_wrapper="seidel")
+    _, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+    assert _eq(sd, g["var_sd"]) and _eq(K, g["var_K"])

@@ -22,6 +22,8 @@ _PROTOS = {
     "tb_ppoly_eval": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_coeff_velacc": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _c_dp, _int, _int, _c_dp,
                          _int, _int, _int, _int, ctypes.c_void_p], _int),
+    "tb_xbound_varying": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _int, _c_dp, _int, _int, _int,
+                           ctypes.c_void_p], _int),
     "tb_rows_canlinear": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp,
                            _int, _int, _int, ctypes.c_void_p], _int),
     "tb_init_bounds": ([_c_dp, _int, _int, _int, _int, ctypes.c_void_p], _int),

@@ -2,10 +2,10 @@
 from .constraint import ConstraintType, DiscretizationType, Constraint
 from .linear_constraint import LinearConstraint, canlinear_colloc_to_interpolate, RecordContext
 from .linear_joint_acceleration import JointAccelerationConstraint
-from .linear_joint_velocity import JointVelocityConstraint
+from .linear_joint_velocity import JointVelocityConstraint, JointVelocityConstraintVarying
 from .linear_second_order import SecondOrderConstraint
 from .conic_constraint import ConicConstraint, RobustLinearConstraint
 
 __all__ = ["ConstraintType", "DiscretizationType", "Constraint", "LinearConstraint",
-           "canlinear_colloc_to_interpolate", "JointAccelerationConstraint", "JointVelocityConstraint",
+           "canlinear_colloc_to_interpolate", "JointAccelerationConstraint", "JointVelocityConstraint", "JointVelocityConstraintVarying",
            "SecondOrderConstraint", "RecordContext", "ConicConstraint", "RobustLinearConstraint"]

@@ -80,3 +80,41 @@ class JointVelocityConstraint(LinearConstraint):
                 self.get_dof(), ctx.bpath.dof))
         engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, ctx.limits(self.device_limits(ctx.device)), None,
                             False, records, R_total, 0, 3)
+
+
+class JointVelocityConstraintVarying(LinearConstraint):
+    """Joint velocity limits that vary along the path (reference linear_joint_velocity.py:56-87).
+
+    vlim_func: (float) -> np.ndarray (dof, 2): lower and upper velocity bounds at path position s.  The function is
+    user code, evaluated on the host once per gridpoint; the bound itself is computed on the GPU."""
+
+    def __init__(self, vlim_func):
+        super(JointVelocityConstraintVarying, self).__init__()
+        self.dof = vlim_func(0).shape[0]
+        self._format_string = "    Varying Velocity limit: \n"
+        self.vlim_func = vlim_func
+
+    def _limits_grid(self, ctx):
+        if ctx.grid_host is None:
+            raise NotImplementedError("JointVelocityConstraintVarying needs host gridpoints shared by all paths")
+        vlim_grid = np.array([self.vlim_func(s) for s in ctx.grid_host], dtype=np.float64)
+        return engine.as_device(vlim_grid, ctx.device)
+
+    def compute_constraint_params(self, path, gridpoints):
+        if path.dof != self.get_dof():
+            raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
+                self.get_dof(), path.dof))
+        ctx = single_path_context(path, gridpoints)
+        records, _ = engine.alloc_records(1, ctx.G, 0, ctx.device)
+        engine.xbound_varying(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, self._limits_grid(ctx), records, 0, 2)
+        xbound = records[0, :, 0:2].cpu().numpy().copy()
+        return None, None, None, None, None, None, xbound
+
+    def num_rows(self, ctx):
+        return 0
+
+    def append_records(self, ctx, records, R_total, row0):
+        if ctx.bpath.dof != self.get_dof():
+            raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
+                self.get_dof(), ctx.bpath.dof))
+        engine.xbound_varying(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, self._limits_grid(ctx), records, R_total, 3)

@@ -269,6 +269,46 @@ __global__ void rows_canlinear_kernel(const double *__restrict__ a, const double
   }
 }
 
+// JointVelocityConstraintVarying (linear_joint_velocity.py:56-87, _CythonUtils.pyx:61-101): velocity limits that
+// vary along the path, vlim_grid [G][dof][2] (shared) or [B][G][dof][2].  One thread per (path, gridpoint).
+__global__ void xbound_varying_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks,
+                                      const int breaks_shared, const long B, const int nseg, const int dof,
+                                      const double *__restrict__ grid, const int grid_shared, const int G,
+                                      const double *__restrict__ vlim_grid, const int vlim_shared,
+                                      double *__restrict__ records, const int W, const int R_total, const int mode) {
+  const long total = B * G;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int gi = (int)(idx % G);
+    const long p = idx / G;
+    const double *x = breaks + (breaks_shared ? 0 : p * (nseg + 1));
+    const double *c = ppoly + p * 4 * nseg * dof;
+    const double s = grid[(grid_shared ? 0 : p * G) + gi];
+    const double *vl = vlim_grid + ((vlim_shared ? 0 : p * G) + gi) * (long)dof * 2;
+    const int seg = find_interval(x, nseg, s);
+    float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
+    for (int k = 0; k < dof && seg >= 0; ++k) {
+      const double q = ppoly_eval1(c, nseg, dof, seg, k, s - x[seg], 1);
+      if (q > 0) {
+        const double hi = vl[k * 2 + 1] / q, lo = vl[k * 2 + 0] / q;
+        sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
+        sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);
+      } else if (q < 0) {
+        const double hi = vl[k * 2 + 0] / q, lo = vl[k * 2 + 1] / q;
+        sdmax = __double2float_rn(hi <= (double)sdmax ? hi : (double)sdmax);
+        sdmin = __double2float_rn(lo >= (double)sdmin ? lo : (double)sdmin);
+      }
+    }
+    const float up = __fmul_rn(sdmax, sdmax);
+    const double lo_d = ((double)sdmin >= 0.0) ? (double)sdmin : 0.0;
+    double xlo = lo_d * lo_d, xhi = (double)up;
+    double *rec = records + idx * W;
+    if (mode != 2) { xlo = fmax(VAR_MIN, xlo); xhi = fmin(VAR_MAX, xhi); }
+    if (mode == 3) { xlo = fmax(rec[3 * R_total], xlo); xhi = fmin(rec[3 * R_total + 1], xhi); }
+    rec[3 * R_total] = xlo;
+    rec[3 * R_total + 1] = xhi;
+  }
+}
+
 // Fill the xbound slots (and padding) with the defaults +-1e8 when no constraint supplies them.
 __global__ void init_bounds_kernel(double *__restrict__ records, const long BG, const int W, const int R_total) {
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < BG; idx += (long)gridDim.x * blockDim.x) {
@@ -357,4 +397,23 @@ extern "C" int tb_init_bounds(double *records, int B, int G, int W, int R_total,
   if (blocks > 148L * 32) blocks = 148L * 32;
   init_bounds_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(records, BG, W, R_total);
   return check_launch("tb_init_bounds");
+}
+
+extern "C" int tb_xbound_varying(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                                 const double *grid, int grid_shared, int G, const double *vlim_grid, int vlim_shared,
+                                 double *records, int W, int R_total, int write_xbound, void *stream) {
+  using namespace tb;
+  if (!ppoly || !breaks || !grid || !vlim_grid || !records || B <= 0 || nseg <= 0 || dof <= 0 || G <= 0 ||
+      write_xbound < 1 || write_xbound > 3 || W < 3 * R_total + 2) {
+    set_error("tb_xbound_varying: bad argument");
+    return TB_ERR_ARG;
+  }
+  const long total = (long)B * G;
+  const int threads = 128;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148L * 64) blocks = 148L * 64;
+  xbound_varying_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, vlim_grid, vlim_shared, records, W, R_total,
+      write_xbound);
+  return check_launch("tb_xbound_varying");
 }

@@ -315,3 +315,17 @@ def constaccel_eval(ppoly, breaks, grid, sd, t_grid, us, ts, order):
                                             _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "tb_constaccel_eval")
     return out
+
+
+def xbound_varying(ppoly, breaks, grid, vlim_grid, records, R_total, write_xbound):
+    """Velocity bound with per-gridpoint limits vlim_grid [G,dof,2] or [B,G,dof,2] into the xbound slots."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    G = grid.shape[-1]
+    W = records.shape[-1]
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_xbound_varying(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg, dof,
+                                           _lib.ptr(grid), 1 if grid.dim() == 1 else 0, G, _lib.ptr(vlim_grid),
+                                           1 if vlim_grid.dim() == 3 else 0, _lib.ptr(records), W, int(R_total),
+                                           int(write_xbound), _lib.stream_ptr())
+    _lib.check(rc, "tb_xbound_varying")
