@@ -122,3 +122,20 @@ def test_cfg5_shard_size_chunked(ta):
     assert bool((res.sd[:, 0] == 0).all()) and bool((res.sd[:, -1] == 0).all()) and bool((res.sd[:, 1:-1] > 0).all())
     x = res.sd * res.sd
     assert bool((x <= res.K[:, :, 1] * (1 + 1e-12) + 1e-15).all())
+
+
+@pytest.mark.parametrize("dof,G,B", [(1, 2, 1), (2, 3, 5), (12, 37, 5), (20, 64, 3), (31, 50, 2), (7, 1000, 2)])
+def test_shapes_rows_per_lane_and_tiny_grids(ta, dof, G, B):
+    """1..4 LP rows per lane (R = 4*dof up to 124), one-stage grids, batches that do not fill a CTA: vs the oracle."""
+    from oracle import oracle as orc
+    ss, way, vlim, alim = make_batch(B, 4000 + dof, dof=dof)
+    grid = np.linspace(0, 1, G)
+    path, inst, res = _solve(ta, ss, way, vlim, alim, grid)
+    h = res.to_host()
+    c = path.d_ppoly.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(c[b], orc.cubic_spline_fit(ss, way[b]))
+        o = orc.solve_velacc(c[b], ss, grid, vlim[b], alim[b], True, 0, 0)
+        assert h["status"][b] == o["status"]
+        assert np.array_equal(h["K"][b], o["K"], equal_nan=True) and np.array_equal(h["sd"][b], o["sd"], equal_nan=True)
+        assert np.array_equal(h["sdd"][b], o["u"], equal_nan=True)

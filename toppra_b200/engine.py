@@ -21,7 +21,10 @@ def as_device(x, device, dtype=None):
     dtype = dtype or torch.float64
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device, non_blocking=True).contiguous()
+    arr = np.ascontiguousarray(x)
+    if not arr.flags.writeable:  # e.g. broadcast views: torch wants a writable buffer
+        arr = arr.copy()
+    return torch.as_tensor(arr, dtype=dtype).to(device, non_blocking=True).contiguous()
 
 
 def default_device(device=None):
