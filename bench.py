@@ -348,12 +348,22 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms_dev = timed(step_device, args.steps, max(args.warmup, 3), record_kernels=True)
-    ms_e2e = timed(step_e2e_full, args.steps, max(args.warmup, 3))
-    sampler.stop_flag = True
-    sampler.join(timeout=1.0)
+    def measure():
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        del k_events[:]
+        a = timed(step_device, args.steps, max(args.warmup, 3), record_kernels=True)
+        b = timed(step_e2e_full, args.steps, max(args.warmup, 3))
+        sampler.stop_flag = True
+        sampler.join(timeout=1.0)
+        return a, b, sampler.summary()
+
+    ms_dev, ms_e2e, clocks = measure()
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if bad & set(clocks.get("reasons", [])):  # throttled: take the measurement again, once
+        clocks_first = clocks
+        ms_dev, ms_e2e, clocks = measure()
+        clocks["remeasured_after"] = clocks_first
 
     status = h_out["status"].numpy()
     n_ok = int((status == 0).sum())
@@ -412,7 +422,7 @@ def run_b200(args):
         "kernels_ms": {"K0_spline_fit": k0, "K1_coeff": k1, "K2_scan": k2},
         "roofline": roof, "roofline_k1": roof_k1,
         "lp_solves_per_s": 597.0 / 199 * (G - 1) * B / (k2 * 1e-3),
-        "clocks": sampler.summary(),
+        "clocks": clocks,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
