@@ -164,6 +164,8 @@ int tb_feasible_sets(const double *records, int W, int R, const double *grid, in
 #define TB_SCAN_BACKWARD_ONLY 1
 #define TB_SCAN_SD_FORWARD 4     /* forward-pass rules of TOPPRAsd (desired_duration_algorithm.py:103-121): no retry, x_next - 1e-5; the sd output then holds x = sd^2 */
 #define TB_SCAN_SD_SLOW 8        /* with TB_SCAN_SD_FORWARD: the slowest pass (minimise the next velocity), :218-223 */
+#define TB_SCAN_FORWARD_ONLY 16  /* forward pass alone: K, status (and fail_stage) hold the results of an earlier
+                                   TB_SCAN_BACKWARD_ONLY launch on the same buffers (lets the D2H copy of K overlap) */
 #define TB_SCAN_FEASIBLE_SETS 2 /* tb_scan_robust only: K receives the feasible sets X (compute_feasible_sets) */
 int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,

@@ -139,3 +139,22 @@ def test_shapes_rows_per_lane_and_tiny_grids(ta, dof, G, B):
         assert h["status"][b] == o["status"]
         assert np.array_equal(h["K"][b], o["K"], equal_nan=True) and np.array_equal(h["sd"][b], o["sd"], equal_nan=True)
         assert np.array_equal(h["sdd"][b], o["u"], equal_nan=True)
+
+
+def test_split_backward_forward_and_host_copy(ta):
+    """BatchTOPPRA.solve_to_host: backward-only + forward-only launches (K copied out in between) == single launch."""
+    import torch
+    B, G = 777, 150
+    ss, way, vlim, alim = make_batch_fast(B, seed=21)
+    vlim[:50] *= 0.03  # some velocity-active paths
+    grid = np.linspace(0, 1, G)
+    path = ta.BatchSplineInterpolator(ss, way)
+    cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)]
+    inst = ta.BatchTOPPRA(cons, path, grid)
+    s0 = np.where(np.arange(B) % 7 == 0, 30.0, 0.0)   # every 7th path starts inadmissibly fast -> FailUncontrollable
+    one = inst.compute_parameterization(s0, 0.0).to_host()
+    host = inst.solve_to_host(s0, 0.0)
+    torch.cuda.synchronize()
+    assert (one["status"][::7] == 3).all() and (one["status"][1::7] == 0).all()
+    for key in ("K", "sd", "sdd", "status"):
+        assert np.array_equal(one[key], host[key].numpy(), equal_nan=True), key

@@ -159,6 +159,41 @@ class BatchTOPPRA(object):
             return None  # kernels treat NULL as zeros
         return engine.as_device(np.ascontiguousarray(arr), self.device)
 
+    def solve_to_host(self, sd_start=0.0, sd_end=0.0, pinned=None):
+        """compute_parameterization + copy of (K, sd, sdd, status) to pinned host memory, with the D2H copy of K
+        overlapped with the forward pass: the scan runs as a backward-only and a forward-only launch and K leaves
+        on a second stream in between.  Returns the dict of pinned host tensors (valid after this call)."""
+        torch = engine.torch_mod()
+        if self.conic is not None or self.chunk_size() < self.B:
+            return_host = self.compute_parameterization(sd_start, sd_end).to_host(pinned)
+            return return_host
+        if self.records is None:
+            self.setup()
+        B, G = self.B, self.G
+        if pinned is None:
+            pinned = {"K": torch.empty((B, G, 2), dtype=torch.float64).pin_memory(),
+                      "sd": torch.empty((B, G), dtype=torch.float64).pin_memory(),
+                      "sdd": torch.empty((B, G - 1), dtype=torch.float64).pin_memory(),
+                      "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
+        s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        back = engine.scan(self.records, self.R, self.d_grid, s0, s1, backward_only=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ev)
+            pinned["K"].copy_(back["K"], non_blocking=True)
+        fwd = engine.scan(self.records, self.R, self.d_grid, s0, s1, forward_from=back)
+        pinned["sd"].copy_(fwd["sd"], non_blocking=True)
+        pinned["sdd"].copy_(fwd["u"], non_blocking=True)
+        pinned["status"].copy_(fwd["status"], non_blocking=True)
+        main.wait_stream(self._copy_stream)   # the step is complete (for events / callers) when K has landed too
+        back["K"].record_stream(self._copy_stream)
+        self.last_result = BatchResult(fwd)
+        return pinned
+
     def chunk_size(self):
         """Paths per chunk so that the record buffer stays within max_record_bytes."""
         rows = sum(c.num_rows(self.ctx) for c in self.constraints)

@@ -317,6 +317,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
   double *Kp = Kout + (size_t)path * G * 2;
   const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
+  const bool forward_only = (flags & 16) != 0;  // K and status come from an earlier TB_SCAN_BACKWARD_ONLY launch
   const bool sd_mode = (flags & 4) != 0;        // TOPPRAsd forward-pass rules (no retry, x_next - 1e-5 clip)
   const bool sd_slow = (flags & 8) != 0;        // TOPPRAsd slowest pass: minimise the next velocity
   double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
@@ -357,11 +358,17 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   const double sds = sd_start ? sd_start[path] : 0.0;
   const double sdeh = sd_end_hi ? sd_end_hi[path] : sde;
   double kn0 = sde * sde, kn1 = sdeh * sdeh;  // K[N] = [sdmin^2, sdmax^2], reachability_algorithm.py:185
-  if (lane == 0) { Kp[2 * N] = kn0; Kp[2 * N + 1] = kn1; }
+  if (lane == 0 && !forward_only) { Kp[2 * N] = kn0; Kp[2 * N + 1] = kn1; }
   int st = TB_STATUS_OK, fstage = -1;
   int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0;  // active_c_up / active_c_down, initialised to zeros (pyx:526-527)
-  for (int q = 0; q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
-  for (int i = N - 1; i >= 0; --i) {
+  if (forward_only) {
+    st = status[path];
+    fstage = fail_stage ? fail_stage[path] : -1;
+    kn0 = Kp[0];
+    kn1 = Kp[1];
+  }
+  for (int q = 0; !forward_only && q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
+  for (int i = forward_only ? -1 : N - 1; i >= 0; --i) {
     const double *rec = acquire();
     load_rows<RPL>(rec, R, nC, lane, a, b, c);
     const double xlo = rec[3 * R], xhi = rec[3 * R + 1];

@@ -147,22 +147,26 @@ def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
 
 
 def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False,
-         sd_forward=None):
+         sd_forward=None, forward_from=None):
     """K2.  Returns dict(K [B,G,2], sd [B,G], u [B,G-1], status [B] int32, fail_stage [B] int32[, counters [B,4]])."""
     torch = torch_mod()
     B, G, W = records.shape
     dev = records.device
-    K = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+    if forward_from is not None:  # forward pass alone on the K / status of an earlier backward-only launch
+        K, status, fail_stage = forward_from["K"], forward_from["status"], forward_from["fail_stage"]
+    else:
+        K = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        fail_stage = torch.empty((B,), dtype=torch.int32, device=dev)
     sd = None if backward_only else torch.empty((B, G), dtype=torch.float64, device=dev)
     u = None if backward_only else torch.empty((B, max(G - 1, 0)), dtype=torch.float64, device=dev)
-    status = torch.empty((B,), dtype=torch.int32, device=dev)
-    fail_stage = torch.empty((B,), dtype=torch.int32, device=dev)
     cnt = torch.zeros((B, 4), dtype=torch.int32, device=dev) if counters else None
     u_arg = u if (u is None or u.numel() > 0) else torch.empty((1,), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.load().tb_scan_ex(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
                                     _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi),
-                                    (1 if backward_only else 0) | ({None: 0, "fast": 4, "slow": 12}[sd_forward]),
+                                    (1 if backward_only else 0) | ({None: 0, "fast": 4, "slow": 12}[sd_forward])
+                                    | (16 if forward_from is not None else 0),
                                     _lib.ptr(K), _lib.ptr(sd),
                                     _lib.ptr(u_arg),
                                     _lib.ptr(status), _lib.ptr(fail_stage), _lib.ptr(cnt), _lib.stream_ptr())
