@@ -602,18 +602,24 @@ __global__ void lp1d_batch_kernel(const double *__restrict__ v, const double *__
   }
 }
 
-constexpr int SCAN_WARPS = 4;
+#ifndef TB_SCAN_WARPS
+#define TB_SCAN_WARPS 1
+#endif
+constexpr int SCAN_WARPS = TB_SCAN_WARPS;  // 1: a finished path frees its slot at once (measured best: 1 < 2 < 4)
+#ifndef TB_SCAN_WARPS_PER_SM
+#define TB_SCAN_WARPS_PER_SM 32  // register budget of the dense build: 65536 / (32 * 32) -> 64 registers/thread (measured: 32 > 28 > 24)
+#endif
 
 template <int RPL>
 int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                 const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
                 double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
   const size_t smem = (size_t)SCAN_WARPS * SCAN_NBUF * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t);
-  // Two register budgets for the common nC <= 32 case: 7 CTAs/SM (72 regs, 28 warps/SM: the 4096-path batch of
-  // BASELINE cfg 2 fits one wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
+  // Two register budgets for the common nC <= 32 case: 64 registers (32 one-warp CTAs per SM: the 4096-path batch
+  // of BASELINE cfg 2 is a single wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
   static const char *occ_env = getenv("TB_SCAN_OCC");
   const bool dense = occ_env ? (occ_env[0] == 'd') : true;
-  auto kern = (RPL == 1 && dense) ? scan_kernel<RPL, SCAN_WARPS, (RPL == 1 ? 7 : 1)> : scan_kernel<RPL, SCAN_WARPS, 1>;
+  auto kern = (RPL == 1 && dense) ? scan_kernel<RPL, SCAN_WARPS, (RPL == 1 ? TB_SCAN_WARPS_PER_SM / SCAN_WARPS : 1)> : scan_kernel<RPL, SCAN_WARPS, 1>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
