@@ -17,8 +17,14 @@
 namespace tb {
 namespace {
 
-constexpr int COEFF_THREADS = 256;
-constexpr int COEFF_CH_SMALL = 32, COEFF_CH_LARGE = 64;  // gridpoints per CTA
+#ifndef TB_COEFF_THREADS
+#define TB_COEFF_THREADS 128
+#endif
+#ifndef TB_COEFF_CH
+#define TB_COEFF_CH 32
+#endif
+constexpr int COEFF_THREADS = TB_COEFF_THREADS;
+constexpr int COEFF_CH_SMALL = 32, COEFF_CH_LARGE = TB_COEFF_CH;  // gridpoints per CTA
 
 __device__ __forceinline__ int R_total_or1(int R_total) { return R_total > 0 ? R_total : 1; }
 

@@ -98,7 +98,10 @@ __device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
 }
 
 constexpr int BOXBASE = 1 << 20;
-constexpr int SCAN_NBUF = 4;  // record buffers per warp (3 stages of look-ahead)
+#ifndef TB_SCAN_NBUF
+#define TB_SCAN_NBUF 4
+#endif
+constexpr int SCAN_NBUF = TB_SCAN_NBUF;  // record buffers per warp (NBUF-1 stages of look-ahead)
 
 // One projected constraint of the 1-D sub-problem (pyx:326-347): its limit on t as an upper bound `thi` (denom >
 // TINY) or a lower bound `tlo` (denom < -TINY); +-LP_INF = no limit of that kind (the 1-D LP's own bounds);
@@ -133,18 +136,20 @@ __device__ __forceinline__ void box_row(const int m, const double low0, const do
 // Per violated row k (one "re-solve"): the earlier rows and the four box rows are projected onto line k, one item
 // per lane.  The box rows ride on lanes whose own row does not take part in this re-solve (rows at or after k,
 // padding lanes); only if fewer than four such lanes exist they fall back to an extra item slot.
-template <int RPL>
-__device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, const double (&a)[RPL],
+// PERM = a valid warm-start pair permutes the row order (pyx:252-264); PERM = false is the natural order, for which
+// position == row index and the bookkeeping folds away (the common case in the TOPP-RA passes: the previous
+// optimum usually sits on a box bound, which makes the pair invalid).
+template <int RPL, bool PERM>
+__device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL], const int nC,
                                           const double low0, const double high0, const double low1,
                                           const double high1, int &ac0, int &ac1, double &out_u, double &out_x,
                                           const int lane, int &n_resolve) {
-  if (low0 > high0 || low1 > high1) return false;  // pyx:233-235
   double p0 = (v0 > LP_TINY) ? high0 : low0;       // pyx:236-247
   double p1 = (v1 > LP_TINY) ? high1 : low1;
   int nac0 = (v0 > LP_TINY) ? -2 : -1;
   int nac1 = (v1 > LP_TINY) ? -4 : -3;
-  const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;
+  constexpr bool valid = PERM;
   int pos[RPL];
 #pragma unroll
   for (int s = 0; s < RPL; ++s) {
@@ -245,6 +250,19 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
   out_u = p0;
   out_x = p1;
   return true;
+}
+
+template <int RPL>
+__device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, const double (&a)[RPL],
+                                          const double (&b)[RPL], const double (&c)[RPL], const int nC,
+                                          const double low0, const double high0, const double low1,
+                                          const double high1, int &ac0, int &ac1, double &out_u, double &out_x,
+                                          const int lane, int &n_resolve) {
+  if (low0 > high0 || low1 > high1) return false;  // pyx:233-235
+  const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;  // warp-uniform
+  if (valid)
+    return lp2d_impl<RPL, true>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane, n_resolve);
+  return lp2d_impl<RPL, false>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane, n_resolve);
 }
 
 // cy_solve_lp1d (pyx:93-144) as used by the x_min == x_max branch of solve_stagewise_optim (pyx:631-650):
