@@ -107,7 +107,7 @@ class BatchTOPPRA(object):
     gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
     """
 
-    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=16 << 30):
+    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30):
         if not isinstance(path, BatchSplineInterpolator):
             raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
         torch = engine.torch_mod()
