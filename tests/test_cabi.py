@@ -60,3 +60,25 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "_never_", (dirpath, f)
+
+
+def _build_c_example(tmp):
+    import subprocess
+    exe = os.path.join(tmp, "solve_host")
+    lib_dir = os.path.join(ROOT, "toppra_b200")
+    subprocess.check_call(["gcc", os.path.join(ROOT, "examples", "solve_host.c"), "-I", os.path.join(ROOT, "include"),
+                           "-L", lib_dir, "-ltoppra_b200", "-Wl,-rpath," + lib_dir, "-lm", "-o", exe])
+    return exe
+
+
+def test_plain_c_program_links_against_the_cabi(tmp_path):
+    """A torch-free C program compiles and links against include/toppra_b200.h + libtoppra_b200.so."""
+    assert os.path.exists(_build_c_example(str(tmp_path)))
+
+
+@pytest.mark.gpu
+def test_plain_c_program_runs(tmp_path):
+    import subprocess
+    out = subprocess.run([_build_c_example(str(tmp_path))], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("status 0") == 8
