@@ -84,7 +84,7 @@ static double u_interval(stage_t *st, double x, double *uhi) {
   return hi - lo;
 }
 
-static int extreme_x(stage_t *st, int dir, double xl, double xh, double *xout) {
+static int extreme_x(stage_t *st, int dir, double xl, double xh, double *xout, double hint) {
   if (xl > xh) return 0;
   double uh;
   double xgoal = (dir > 0) ? xh : xl, xother = (dir > 0) ? xl : xh;
@@ -92,6 +92,20 @@ static int extreme_x(stage_t *st, int dir, double xl, double xh, double *xout) {
   if (wg >= 0.0) { *xout = xgoal; return 1; }
   double wo = u_interval(st, xother, &uh);
   double xf = xother, wf = wo;
+  double xb0 = xgoal, wb0 = wg;
+  if (wo >= 0.0 && hint > xl && hint < xh) {
+    double h1 = hint, h2 = (dir > 0) ? fmin(xh, hint * 1.25 + 1e-9) : fmax(xl, hint * 0.8 - 1e-9);
+    double w1 = u_interval(st, h1, &uh);
+    if (w1 >= 0.0) {
+      xf = h1; wf = w1;
+      if (h2 != xgoal) {
+        double w2 = u_interval(st, h2, &uh);
+        if (w2 >= 0.0) { xf = h2; wf = w2; } else { xb0 = h2; wb0 = w2; }
+      }
+    } else {
+      xb0 = h1; wb0 = w1;
+    }
+  }
   if (!(wo >= 0.0)) {
     const double invphi = 0.6180339887498949;
     double lo = xl, hi = xh;
@@ -108,7 +122,7 @@ static int extreme_x(stage_t *st, int dir, double xl, double xh, double *xout) {
     }
     if (!found) return 0;
   }
-  double xb = xgoal, wb = wg;
+  double xb = xb0, wb = wb0;
   for (int it = 0; it < 200; ++it) {
     double width = fabs(xb - xf);
     if (!(width > 2.3e-16 * (fabs(xb) + fabs(xf)) + 1e-300)) break;
@@ -155,8 +169,8 @@ int orc_solve_rows_robust(const double *rows, const double *xbound, const double
     a[0] = -2 * delta; b[0] = -1.0; c[0] = K[2 * (i + 1)];
     a[1] = 2 * delta; b[1] = 1.0; c[1] = -K[2 * (i + 1) + 1];
     double x_upper = NAN, x_lower = NAN;
-    int ok_hi = extreme_x(&st, +1, xl, xh, &x_upper);
-    int ok_lo = ok_hi && extreme_x(&st, -1, xl, xh, &x_lower);
+    int ok_hi = extreme_x(&st, +1, xl, xh, &x_upper, K[2 * (i + 1) + 1]);
+    int ok_lo = ok_hi && extreme_x(&st, -1, xl, xh, &x_lower, K[2 * (i + 1)]);
     if (!ok_hi) x_upper = NAN;
     if (!ok_lo) x_lower = NAN;
     if (x_lower < 0) x_lower = 0;

@@ -104,7 +104,8 @@ template <int RPL>
 __device__ __forceinline__ bool extreme_x(const int dir, const double xl, const double xh, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL],
                                           const unsigned (&cmask)[RPL], const int lane, const double ru,
-                                          const double rx, const double rc, double &xout, int &n_eval) {
+                                          const double rx, const double rc, double &xout, int &n_eval,
+                                          const double hint /* NaN = none */) {
   if (xl > xh) return false;
   double uh;
   const double xgoal = (dir > 0) ? xh : xl, xother = (dir > 0) ? xl : xh;
@@ -114,6 +115,23 @@ __device__ __forceinline__ bool extreme_x(const int dir, const double xl, const 
   double wo = u_interval<RPL>(xother, a, b, c, cmask, lane, ru, rx, rc, uh);
   ++n_eval;
   double xf = xother, wf = wo;
+  double xb0 = xgoal, wb0 = wg;
+  if (wo >= 0.0 && hint > xl && hint < xh) {
+    // the answer of the neighbouring stage is usually close: two probes around it shrink the bracket at once
+    const double h1 = hint, h2 = (dir > 0) ? fmin(xh, hint * 1.25 + 1e-9) : fmax(xl, hint * 0.8 - 1e-9);
+    const double w1 = u_interval<RPL>(h1, a, b, c, cmask, lane, ru, rx, rc, uh);
+    ++n_eval;
+    if (w1 >= 0.0) {
+      xf = h1; wf = w1;
+      if (h2 != xgoal) {
+        const double w2 = u_interval<RPL>(h2, a, b, c, cmask, lane, ru, rx, rc, uh);
+        ++n_eval;
+        if (w2 >= 0.0) { xf = h2; wf = w2; } else { xb0 = h2; wb0 = w2; }
+      }
+    } else {
+      xb0 = h1; wb0 = w1;
+    }
+  }
   if (!(wo >= 0.0)) {
     // both ends infeasible: golden-section search for the maximum of the concave width
     const double invphi = 0.6180339887498949;
@@ -133,8 +151,8 @@ __device__ __forceinline__ bool extreme_x(const int dir, const double xl, const 
     }
     if (!found) return false;
   }
-  // bracket: xf feasible (wf >= 0), xgoal infeasible (wg < 0, possibly -inf)
-  double xb = xgoal, wb = wg;
+  // bracket: xf feasible (wf >= 0), xb infeasible (w < 0, possibly -inf)
+  double xb = xb0, wb = wb0;
   for (int it = 0; it < 200; ++it) {
     const double width = fabs(xb - xf);
     if (!(width > 2.3e-16 * (fabs(xb) + fabs(xf)) + 1e-300)) break;
@@ -173,7 +191,7 @@ __device__ __forceinline__ void rload_rows(const double *__restrict__ rec, const
 }
 
 template <int RPL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (RPL == 1) ? 28 / WARPS : 1)
 scan_robust_kernel(const double *__restrict__ records, const int W, const int R, const int conic0, const int conicn,
                    const double ru, const double rx, const double rc, const double *__restrict__ grid,
                    const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
@@ -208,8 +226,8 @@ scan_robust_kernel(const double *__restrict__ records, const int W, const int R,
         if (lane == 1) { a[0] = 2 * delta; b[0] = 1.0; c[0] = -CVXPY_MAXX; }
       }
       double x0 = nan_d, x1 = nan_d;
-      if (!extreme_x<RPL>(-1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x0, n_eval)) x0 = nan_d;
-      if (!extreme_x<RPL>(+1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x1, n_eval)) x1 = nan_d;
+      if (!extreme_x<RPL>(-1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x0, n_eval, nan_d)) x0 = nan_d;
+      if (!extreme_x<RPL>(+1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x1, n_eval, nan_d)) x1 = nan_d;
       if (x0 < 0) x0 = 0;
       if (lane == 0) { Kp[2 * i] = x0; Kp[2 * i + 1] = x1; }
     }
@@ -224,6 +242,8 @@ scan_robust_kernel(const double *__restrict__ records, const int W, const int R,
   for (int i = N - 1; i >= 0; --i) {
     const double *rec = rec_path + (size_t)i * W;
     rload_rows<RPL>(rec, R, nC, lane, conic0, conicn, a, b, c, cmask);
+    if (i > 0 && lane * 16 < W)  // pull the next stage's record towards L1 while this stage is solved
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(rec - W + lane * 16));
     // x box: NaN x_min/x_max -> -/+ECOS_INFTY; xbound: x <= min(ECOS_MAXX, hi), x >= lo  (ecos_solverwrapper.py:112-172)
     const double xl = fmax(-ECOS_INFTY, rec[3 * R]);
     const double xh = fmin(ECOS_INFTY, fmin(ECOS_MAXX, rec[3 * R + 1]));
@@ -231,8 +251,8 @@ scan_robust_kernel(const double *__restrict__ records, const int W, const int R,
     if (lane == 0) { a[0] = -2 * delta; b[0] = -1.0; c[0] = kn0; }
     if (lane == 1) { a[0] = 2 * delta; b[0] = 1.0; c[0] = -kn1; }
     double x_upper = nan_d, x_lower = nan_d;
-    const bool ok_hi = extreme_x<RPL>(+1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x_upper, n_eval);
-    const bool ok_lo = ok_hi && extreme_x<RPL>(-1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x_lower, n_eval);
+    const bool ok_hi = extreme_x<RPL>(+1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x_upper, n_eval, kn1);
+    const bool ok_lo = ok_hi && extreme_x<RPL>(-1, xl, xh, a, b, c, cmask, lane, ru, rx, rc, x_lower, n_eval, kn0);
     if (!ok_hi) x_upper = nan_d;
     if (!ok_lo) x_lower = nan_d;
     if (x_lower < 0) x_lower = 0;
@@ -264,6 +284,7 @@ scan_robust_kernel(const double *__restrict__ records, const int W, const int R,
     for (int i = 0; i < N; ++i) {
       const double *rec = rec_path + (size_t)i * W;
       rload_rows<RPL>(rec, R, nC, lane, conic0, conicn, a, b, c, cmask);
+      if (i + 2 < N && lane * 16 < W) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 2 * W + lane * 16));
       const double delta = gp[i + 1] - gp[i];
       const double k0 = Kp[2 * (i + 1)], k1 = Kp[2 * (i + 1) + 1];
       if (lane == 0) { a[0] = -2 * delta; b[0] = -1.0; c[0] = k0; }
@@ -315,7 +336,7 @@ scan_robust_kernel(const double *__restrict__ records, const int W, const int R,
   }
 }
 
-constexpr int ROBUST_WARPS = 4;
+constexpr int ROBUST_WARPS = 1;  // like K2: a finished path frees its slot at once
 
 template <int RPL>
 int launch_robust(const double *records, int W, int R, int conic0, int conicn, const double *ell, const double *grid,
