@@ -135,6 +135,65 @@ def main():
     g = np.sort(np.r_[0.0, 1.0, rng.rand(148)])
     batch_case("nonuniform_grid", range(1000, 1008), 150, grid=g)
 
+    # ---- forward-pass retry rule (reachability_algorithm.py:315-343; SURVEY §7 "cold but must exist") ----------
+    # (a) start velocity admissible only through the 1e-5 slack: first forward LP infeasible, succeeds after a retry
+    retry = dict(way=[], vlim=[], alim=[], sd_start=[], K=[], sd=[], sdd=[], status=[])
+    ss5, grid200 = np.linspace(0, 1, 5), np.linspace(0, 1, 200)
+    for seed in range(1000, 1006):
+        way, vlim_, alim_ = make_path(seed)
+        out0, _ = solve_ref(ss5, way, vlim_, alim_, grid200)
+        s0 = float(np.sqrt(out0["K"][0, 1] + (3e-8 if seed % 2 else 5e-6)))
+        out1, _ = solve_ref(ss5, way, vlim_, alim_, grid200, sd_start=s0)
+        retry["way"].append(way); retry["vlim"].append(vlim_); retry["alim"].append(alim_); retry["sd_start"].append(s0)
+        for k in ("K", "sd", "sdd", "status"):
+            retry[k].append(out1[k])
+    np.savez_compressed(os.path.join(HERE, "retry_after_slack_start.npz"), ss=ss5, grid=grid200,
+                        **{k: np.asarray(v) for k, v in retry.items()})
+    print("retry (slack start): statuses", retry["status"])
+
+    # (b) random row-level problems whose forward pass exhausts the retry budget (found by random search with the
+    #     oracle, seeds below), run through the REFERENCE via a pass-through CanonicalLinear constraint (F = I, g = 0)
+    class RowConstraint(constraint.LinearConstraint):
+        def __init__(self, rows, xb):
+            super(RowConstraint, self).__init__()
+            self.rows, self.xb, self.identical, self.dof = rows, xb, False, 1
+
+        def compute_constraint_params(self, path, gridpoints):
+            G_, _, R_ = self.rows.shape
+            F = np.tile(np.eye(R_)[None], (G_, 1, 1))
+            return self.rows[:, 0], self.rows[:, 1], self.rows[:, 2], F, np.zeros((G_, R_)), None, self.xb
+
+    rng = np.random.RandomState(0)
+    rc = {}
+    n_found = 0
+    for trial in range(200000):
+        G_ = rng.randint(3, 8); R_ = rng.randint(2, 6)
+        grid_ = np.sort(np.r_[0, 1, rng.rand(G_ - 2)])
+        if np.any(np.diff(grid_) < 1e-3):
+            continue
+        rows_ = np.zeros((G_, 3, R_))
+        rows_[:, 0, :] = rng.randn(G_, R_) * rng.choice([1, 0.1, 3])
+        rows_[:, 1, :] = rng.randn(G_, R_)
+        rows_[:, 2, :] = -rng.rand(G_, R_) * rng.choice([1, 0.2])
+        xb_ = np.stack((np.zeros(G_), rng.rand(G_) * 2 + 0.05), axis=1)
+        sd0_ = rng.rand() * 0.3
+        if trial not in (4202, 27645, 52804, 67731, 100515, 160523, 11, 12, 13, 14):
+            continue
+        dummy = ta.SplineInterpolator([0.0, 1.0], [[0.0], [1.0]])
+        inst_ = algo.TOPPRA([RowConstraint(rows_, xb_)], dummy, gridpoints=grid_, solver_wrapper="seidel")
+        sdd_, sd_, _, K_ = inst_.compute_parameterization(sd0_, 0.0, return_data=True)
+        codes = list(algo.ParameterizationReturnCode)
+        tag = "c%d_" % n_found
+        rc[tag + "grid"], rc[tag + "rows"], rc[tag + "xb"], rc[tag + "sd_start"] = grid_, rows_, xb_, np.float64(sd0_)
+        rc[tag + "K"] = K_
+        rc[tag + "sd"] = np.full(G_, np.nan) if sd_ is None else sd_
+        rc[tag + "sdd"] = np.full(G_ - 1, np.nan) if sdd_ is None else sdd_
+        rc[tag + "status"] = np.int64(codes.index(inst_.problem_data.return_code))
+        n_found += 1
+    rc["n"] = np.int64(n_found)
+    np.savez_compressed(os.path.join(HERE, "retry_row_problems.npz"), **rc)
+    print("retry (row problems):", n_found, "cases, statuses", [int(rc["c%d_status" % i]) for i in range(n_found)])
+
     # ---- P6: 2-DOF collocation golden of cpp/tests/test_algorithm.cpp:25-169 (generator script :25-57) ----
     path = ta.SplineInterpolator([0, 1, 2, 3], [[0, 0], [1, 3], [2, 4], [0, 0]])
     pc_vel = constraint.JointVelocityConstraint([1.0, 1.0])

@@ -402,3 +402,32 @@ def test_velocity_constraint_varying(ta, golden):
                                gridpoints=g["grid"], solver_wrapper="seidel")
     _, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
     assert _eq(sd, g["var_sd"]) and _eq(K, g["var_K"])
+
+
+def test_forward_retry_rule(ta, golden):
+    """The cold retry branch of the forward pass (reachability_algorithm.py:315-343) against reference outputs."""
+    import torch
+    g = golden("retry_after_slack_start")
+    path = ta.BatchSplineInterpolator(g["ss"], g["way"])
+    inst = ta.BatchTOPPRA([ta.constraint.JointVelocityConstraint(g["vlim"]),
+                           ta.constraint.JointAccelerationConstraint(g["alim"])], path, g["grid"])
+    res = inst.compute_parameterization(g["sd_start"], 0.0, counters=True)
+    h = res.to_host()
+    assert _eq(h["status"], g["status"]) and set(g["status"].tolist()) == {0, 1}
+    assert _eq(h["K"], g["K"]) and _eq(h["sd"], g["sd"]) and _eq(h["sdd"], g["sdd"])
+    assert (res.counters[:, 3].cpu().numpy() > 0).all()           # every path went through the retry rule
+    r = golden("retry_row_problems")
+    for i in range(int(r["n"])):
+        t = "c%d_" % i
+        rows, xb, grid = r[t + "rows"], r[t + "xb"], r[t + "grid"]
+        G, _, R = rows.shape
+        W = ta.engine.record_doubles(R)
+        rec = np.zeros((1, G, W))
+        rec[0, :, :3 * R] = rows.reshape(G, 3 * R)
+        rec[0, :, 3 * R:3 * R + 2] = xb
+        dev = torch.device("cuda")
+        out = ta.engine.scan(ta.engine.as_device(rec, dev), R, ta.engine.as_device(grid, dev),
+                             ta.engine.as_device(np.array([float(r[t + "sd_start"])]), dev), None)
+        assert int(out["status"][0]) == int(r[t + "status"]), i
+        assert _eq(out["K"][0].cpu().numpy(), r[t + "K"]) and _eq(out["sd"][0].cpu().numpy(), r[t + "sd"]), i
+        assert _eq(out["u"][0].cpu().numpy(), r[t + "sdd"]), i

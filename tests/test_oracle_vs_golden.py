@@ -226,3 +226,26 @@ def test_torque_second_order(golden):
         o = orc.solve_rows(rows, base["xbound"], g["grid"], 0, 0)
         assert o["status"] == g["status"][b]
         assert _eq(o["K"], g["K"][b]) and _eq(o["sd"], g["sd"][b]) and _eq(o["u"], g["sdd"][b])
+
+
+def test_forward_retry_rule(golden):
+    """reachability_algorithm.py:315-343: x is lowered by max(x - 1e-8, 0.999 x) up to 10 times when the forward LP is
+    infeasible.  (a) start velocities that are admissible only through the 1e-5 slack: an excess of 3e-8 is absorbed
+    by retries (Ok), 5e-6 exhausts them (ErrUnknown); (b) row-level problems found by random search."""
+    g = golden("retry_after_slack_start")
+    n_ok = 0
+    for b in range(g["way"].shape[0]):
+        c = orc.cubic_spline_fit(g["ss"], g["way"][b])
+        lin = orc.solve_velacc(c, g["ss"], g["grid"], g["vlim"][b], g["alim"][b], True, 0, 0, want_rows=True)
+        w = orc.Wrapper(g["grid"], lin["rows"], lin["xbound"])
+        o = w.compute_parameterization(float(g["sd_start"][b]), 0.0)
+        assert o["status"] == g["status"][b] and o["retries"] > 0
+        assert _eq(o["K"], g["K"][b]) and _eq(o["sd"], g["sd"][b]) and _eq(o["u"], g["sdd"][b])
+        n_ok += o["status"] == 0
+    assert 0 < n_ok < g["way"].shape[0]
+    r = golden("retry_row_problems")
+    for i in range(int(r["n"])):
+        t = "c%d_" % i
+        o = orc.solve_rows(r[t + "rows"], r[t + "xb"], r[t + "grid"], float(r[t + "sd_start"]), 0.0)
+        assert o["status"] == int(r[t + "status"]), i
+        assert _eq(o["K"], r[t + "K"]) and _eq(o["sd"], r[t + "sd"]) and _eq(o["u"], r[t + "sdd"]), i
