@@ -74,6 +74,13 @@ def main():
             return inst, res
 
         ms, (inst, res) = timed(step, steps=3 if B * G > 5e7 else 5)
+        split = {}
+        if inst.chunk_size() >= B:   # single chunk: time K0 / record build (K1 + user inv_dyn) / scan separately
+            split["fit_ms"], path0 = timed(lambda: ta.BatchSplineInterpolator(d_ss, d_way), steps=3)
+            inst0 = ta.BatchTOPPRA(cons, path0, d_grid)
+            split["records_ms"], _ = timed(inst0.setup, steps=3)
+            split["scan_ms"], _ = timed(lambda: inst0.compute_parameterization(0.0, 0.0), steps=3)
+            del inst0, path0
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -81,7 +88,8 @@ def main():
         if rank == 0:
             print(json.dumps({"config": name, "n_gpus": world, "paths_per_gpu": B, "gridpoints": G, "dof": dof, "rows": inst.R,
                               "chunk_paths": inst.chunk_size(), "ms_per_step": float(t.item()),
-                              "paths_per_s": B * world / float(t.item()) * 1e3, "status_hist_rank0": hist}), flush=True)
+                              "paths_per_s": B * world / float(t.item()) * 1e3, "status_hist_rank0": hist, "split": split}),
+                  flush=True)
         del inst, res, d_way
         torch.cuda.empty_cache()
     if world > 1:

@@ -45,12 +45,12 @@ def inv_dyn_numpy(q, qd, qdd):
 
 
 def inv_dyn_torch(q, qd, qdd):
-    """Batched form on tensors [M, dof] (same formula)."""
+    """Batched form on tensors [M, dof] (same formula).  M(q) qdd is evaluated without materialising the [M, dof, dof]
+    matrices: sum_j cos(q_i - q_j) qdd_j = cos q_i * sum_j cos q_j qdd_j + sin q_i * sum_j sin q_j qdd_j."""
     import torch
-    dof = q.shape[-1]
-    Mm = 2.0 * torch.eye(dof, dtype=q.dtype, device=q.device) + 0.3 * torch.cos(q[:, :, None] - q[:, None, :])
-    return (torch.bmm(Mm, qdd[:, :, None])[:, :, 0] + 0.1 * torch.sin(q) * (qd * qd).sum(-1, keepdim=True)
-            + 4.9 * torch.sin(q))
+    cq, sq = torch.cos(q), torch.sin(q)
+    mq = 2.0 * qdd + 0.3 * (cq * (cq * qdd).sum(-1, keepdim=True) + sq * (sq * qdd).sum(-1, keepdim=True))
+    return mq + 0.1 * sq * (qd * qd).sum(-1, keepdim=True) + 4.9 * sq
 
 
 def make_torque_problem(seed, dof=6, nway=5):
