@@ -10,7 +10,6 @@ import numpy as np
 
 from .reachability_algorithm import ReachabilityAlgorithm
 from .. import algorithm as algo
-from ...constants import SMALL
 
 logger = logging.getLogger(__name__)
 
