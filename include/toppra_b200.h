@@ -166,6 +166,10 @@ int tb_feasible_sets(const double *records, int W, int R, const double *grid, in
 #define TB_SCAN_SD_SLOW 8        /* with TB_SCAN_SD_FORWARD: the slowest pass (minimise the next velocity), :218-223 */
 #define TB_SCAN_FORWARD_ONLY 16  /* forward pass alone: K, status (and fail_stage) hold the results of an earlier
                                    TB_SCAN_BACKWARD_ONLY launch on the same buffers (lets the D2H copy of K overlap) */
+#define TB_SCAN_FAST_LOWER 32   /* OPT-IN, not bit-identical: K[i][0] = xbound_lo whenever some u is feasible there (the exact LP
+                                   optimum) instead of replaying the reference's ~4 Seidel re-solves, whose projection
+                                   arithmetic returns xbound_lo +- ~1e-16; falls back to the Seidel LP otherwise.
+                                   Deviation from the reference: <= ~1e-15 on K and sd (tests: 1e-12). */
 #define TB_SCAN_FEASIBLE_SETS 2 /* tb_scan_robust only: K receives the feasible sets X (compute_feasible_sets) */
 int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,

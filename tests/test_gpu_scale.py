@@ -158,3 +158,22 @@ def test_split_backward_forward_and_host_copy(ta):
     assert (one["status"][::7] == 3).all() and (one["status"][1::7] == 0).all()
     for key in ("K", "sd", "sdd", "status"):
         assert np.array_equal(one[key], host[key].numpy(), equal_nan=True), key
+
+
+def test_fast_lower_bound_mode(ta):
+    """exact=False (TB_SCAN_FAST_LOWER): same LP optima, not the reference's rounding noise: deviations <= 1e-12
+    (measured ~1e-16), statuses equal; exact=True stays bit-identical (all the other tests)."""
+    B, G = 2048, 200
+    ss, way, vlim, alim = make_batch_fast(B, seed=99)
+    vlim[:256] *= 0.03
+    grid = np.linspace(0, 1, G)
+    path = ta.BatchSplineInterpolator(ss, way)
+    cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)]
+    exact = ta.BatchTOPPRA(cons, path, grid).compute_parameterization(0.0, 0.0, counters=True)
+    fast = ta.BatchTOPPRA(cons, path, grid, exact=False).compute_parameterization(0.0, 0.0, counters=True)
+    he, hf = exact.to_host(), fast.to_host()
+    assert np.array_equal(he["status"], hf["status"]) and not he["status"].any()
+    assert np.abs(he["K"] - hf["K"]).max() <= 1e-12 and np.abs(he["sd"] - hf["sd"]).max() <= 1e-12
+    assert np.abs(he["sdd"] - hf["sdd"]).max() <= 1e-9 * max(1.0, np.abs(he["sdd"]).max())
+    ce, cf = exact.counters.cpu().numpy(), fast.counters.cpu().numpy()
+    assert cf[:, 2].sum() < 0.7 * ce[:, 2].sum()      # far fewer projected re-solves

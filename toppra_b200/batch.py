@@ -22,10 +22,11 @@ def conic_info(ctx, constraints):
 
 
 def scan_any(records, R, grid, conic, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False,
-             counters=False):
+             counters=False, fast_lower=False):
     """K2 for purely linear problems, K2r when a robust constraint is present."""
     if conic is None:
-        return engine.scan(records, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters)
+        return engine.scan(records, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters,
+                           fast_lower=fast_lower)
     if sd_end_hi is not None:
         raise NotImplementedError("robust problems: compute_controllable_sets needs sdmin == sdmax")
     return engine.scan_robust(records, R, conic[0], conic[1], conic[2], grid, sd_start, sd_end, backward_only, counters)
@@ -107,7 +108,7 @@ class BatchTOPPRA(object):
     gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
     """
 
-    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30):
+    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30, exact=True):
         if not isinstance(path, BatchSplineInterpolator):
             raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
         torch = engine.torch_mod()
@@ -130,6 +131,10 @@ class BatchTOPPRA(object):
         # Stage records cost 8 * (3R + 2) * G bytes per path (138 KB at 7-DOF / 200 gridpoints): batches whose
         # records exceed `max_record_bytes` are solved in chunks through one reused record buffer.
         self.max_record_bytes = int(max_record_bytes)
+        # exact=True (default): bit-identical to the reference's seidelWrapper.  exact=False: the min-x LP of the
+        # backward pass takes the shortcut TB_SCAN_FAST_LOWER (include/toppra_b200.h): same LP optimum, deviations
+        # from the reference's rounding noise <= ~1e-15, about 1.7x faster.
+        self.exact = bool(exact)
         self._grid_host = grid_host
         self.conic = conic_info(self.ctx, self.constraints)
 
@@ -179,7 +184,7 @@ class BatchTOPPRA(object):
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-        back = engine.scan(self.records, self.R, self.d_grid, s0, s1, backward_only=True)
+        back = engine.scan(self.records, self.R, self.d_grid, s0, s1, backward_only=True, fast_lower=not self.exact)
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(self._copy_stream):
@@ -209,7 +214,8 @@ class BatchTOPPRA(object):
         if nchunk >= self.B:
             if self.records is None:
                 self.setup()
-            return BatchResult(scan_any(self.records, self.R, self.d_grid, self.conic, s0, s1, counters=counters))
+            return BatchResult(scan_any(self.records, self.R, self.d_grid, self.conic, s0, s1, counters=counters,
+                                        fast_lower=not self.exact))
         B, G, dev = self.B, self.G, self.device
         out = dict(K=torch.empty((B, G, 2), dtype=torch.float64, device=dev),
                    sd=torch.empty((B, G), dtype=torch.float64, device=dev),
@@ -229,7 +235,7 @@ class BatchTOPPRA(object):
             else:
                 rec, _ = build_records(ctx, self.constraints, out=buf)
             part = scan_any(rec, self.R, grid, self.conic, None if s0 is None else s0[lo:hi],
-                            None if s1 is None else s1[lo:hi], counters=counters)
+                            None if s1 is None else s1[lo:hi], counters=counters, fast_lower=not self.exact)
             for key in out:
                 out[key][lo:hi] = part[key]
         return BatchResult(out)

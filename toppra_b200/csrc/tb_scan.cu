@@ -316,7 +316,7 @@ __device__ __forceinline__ void set_xnext_rows(const int lane, const double delt
   if (lane == 1) { a[0] = 2 * delta; b[0] = 1.0; c[0] = -xn_max; }
 }
 
-template <int RPL, int WARPS, int MINB>
+template <int RPL, int WARPS, int MINB, bool FAST>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
             const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
@@ -336,6 +336,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   double *Kp = Kout + (size_t)path * G * 2;
   const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
   const bool forward_only = (flags & 16) != 0;  // K and status come from an earlier TB_SCAN_BACKWARD_ONLY launch
+  constexpr bool fast_lower = FAST;             // opt-in shortcut for the min-x LP (TB_SCAN_FAST_LOWER, not bit-identical)
   const bool sd_mode = (flags & 4) != 0;        // TOPPRAsd forward-pass rules (no retry, x_next - 1e-5 clip)
   const bool sd_slow = (flags & 8) != 0;        // TOPPRAsd slowest pass: minimise the next velocity
   double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
@@ -402,10 +403,21 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
                                       n_resolve);
     const double x_upper = ok_hi ? xx : __longlong_as_double(0x7ff8000000000000LL);
     // x_lower: g = (-1e-9, 1) -> v = (1e-9, -1), slot active_c_up, reachability_algorithm.py:234-236
-    ++n_lp2d;
-    const bool ok_lo = lp2d_warp<RPL>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
-                                      n_resolve);
-    double x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
+    bool ok_lo;
+    double x_lower;
+    double ufeas;
+    if (fast_lower && xlo <= xhi && lp1d_fixed_x_warp<RPL>(1.0, xlo, a, b, c, VAR_MIN, VAR_MAX, ufeas)) {
+      // TB_SCAN_FAST_LOWER: some u is feasible at x = xlo, so min x IS xlo.  The reference reaches the same vertex
+      // through ~4 projected re-solves and returns xlo plus rounding noise of its projection arithmetic
+      // (|noise| <= ~1e-16, 5 % of the stages): this shortcut is exact for the LP, not bit-identical to that noise.
+      ok_lo = true;
+      x_lower = xlo;
+      ++n_lp1d;
+    } else {
+      ++n_lp2d;
+      ok_lo = lp2d_warp<RPL>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane, n_resolve);
+      x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
+    }
     if (x_lower < 0) x_lower = 0;  // reachability_algorithm.py:190-191
     if (lane == 0) { Kp[2 * i] = x_lower; Kp[2 * i + 1] = x_upper; }
     if (!(ok_hi && ok_lo)) {
@@ -637,7 +649,10 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
   // of BASELINE cfg 2 is a single wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
   static const char *occ_env = getenv("TB_SCAN_OCC");
   const bool dense = occ_env ? (occ_env[0] == 'd') : true;
-  auto kern = (RPL == 1 && dense) ? scan_kernel<RPL, SCAN_WARPS, (RPL == 1 ? TB_SCAN_WARPS_PER_SM / SCAN_WARPS : 1)> : scan_kernel<RPL, SCAN_WARPS, 1>;
+  constexpr int MINB = (RPL == 1 ? TB_SCAN_WARPS_PER_SM / SCAN_WARPS : 1);
+  const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
+  auto kern = (RPL == 1 && dense) ? (fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true> : scan_kernel<RPL, SCAN_WARPS, MINB, false>)
+                                  : (fast ? scan_kernel<RPL, SCAN_WARPS, 1, true> : scan_kernel<RPL, SCAN_WARPS, 1, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

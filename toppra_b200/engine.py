@@ -147,7 +147,7 @@ def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
 
 
 def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False,
-         sd_forward=None, forward_from=None):
+         sd_forward=None, forward_from=None, fast_lower=False):
     """K2.  Returns dict(K [B,G,2], sd [B,G], u [B,G-1], status [B] int32, fail_stage [B] int32[, counters [B,4]])."""
     torch = torch_mod()
     B, G, W = records.shape
@@ -166,7 +166,7 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
         rc = _lib.load().tb_scan_ex(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
                                     _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi),
                                     (1 if backward_only else 0) | ({None: 0, "fast": 4, "slow": 12}[sd_forward])
-                                    | (16 if forward_from is not None else 0),
+                                    | (16 if forward_from is not None else 0) | (32 if fast_lower else 0),
                                     _lib.ptr(K), _lib.ptr(sd),
                                     _lib.ptr(u_arg),
                                     _lib.ptr(status), _lib.ptr(fail_stage), _lib.ptr(cnt), _lib.stream_ptr())
