@@ -139,7 +139,7 @@ __device__ __forceinline__ void box_row(const int m, const double low0, const do
 // PERM = a valid warm-start pair permutes the row order (pyx:252-264); PERM = false is the natural order, for which
 // position == row index and the bookkeeping folds away (the common case in the TOPP-RA passes: the previous
 // optimum usually sits on a box bound, which makes the pair invalid).
-template <int RPL, bool PERM>
+template <int RPL, bool PERM, bool SKIP>
 __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL], const int nC,
                                           const double low0, const double high0, const double low1,
@@ -158,6 +158,7 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
   }
   const unsigned lt_mask = (1u << lane) - 1u;
   int kpos = -1;
+  bool walk_ok = SKIP && (v0 > LP_TINY) && (v1 < 0);  // see the skip-ahead below
   while (true) {
     // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
     int mypos = INT_MAX;
@@ -167,12 +168,64 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
       const bool cand = !(val < LP_TINY) && (pos[s] > kpos) && (pos[s] != INT_MAX);
       mypos = cand ? min(mypos, pos[s]) : mypos;
     }
-    const int knew = __reduce_min_sync(FULL, mypos);
+    int knew = __reduce_min_sync(FULL, mypos);
     if (knew == INT_MAX) break;
+    if constexpr (RPL == 1 && !PERM && SKIP) {
+      // Skip-ahead for the min-x LP of the backward pass (objective (1e-9, -1)); bit-identical, see DESIGN.md §4 K2.
+      // While every visit so far was on an upper bound of u (a > 0) and ended with x pinned at its lower box bound
+      // (1-D winner = box row "low1 <= x", nac1 == -3; also the start vertex), the following visits only walk u
+      // down through the rows that tighten it at that x, and each visit recomputes the point from scratch
+      // (z + t d over ALL earlier rows): the final state depends only on the LAST visited row.  The walk is replayed
+      // with plain arithmetic (u_j = -(b_j x + c_j)/a_j, ~25 instructions per visited row instead of a full
+      // projected re-solve).  If every visit/skip decision is clear of the TINY threshold by a margin far above the
+      // rounding error of the exact points, every visited row picks the lower end of its line (same v1d test as the
+      // exact path) and the rows that bound u from below hold at the final u, the reference is certain to visit
+      // the last row of the walk, and ONE exact re-solve on that row reproduces its state bit for bit (validated
+      // against the sequential solver on 1e6 LPs and by tests/test_gpu_scale.py).  Any doubt -> normal path.
+      if (walk_ok && nac1 == -3) {
+        const double x = p1;
+        double ucur = p0;
+        const double bxc = b[0] * x + c[0];
+        const bool upr = a[0] > LP_TINY, lor = a[0] < -LP_TINY, real = pos[0] != INT_MAX;
+        const double uown = -bxc / ((upr || lor) ? a[0] : 1.0);
+        const double v1d_own = (-b[0]) * v0 + a[0] * v1;  // the exact path's v1d if this row were visited
+        const unsigned m_up = __ballot_sync(FULL, upr && ((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
+        const double amag = fabs(b[0] * x) + fabs(c[0]);
+        int cur = kpos, last = -1;
+        bool ok = true;
+        while (true) {
+          const double au = a[0] * ucur;
+          const double val = au + b[0] * x + c[0];
+          const bool after = real && pos[0] > cur;
+          const bool marg = after && (fabs(val - LP_TINY) <= 1e-11 + 1e-12 * (fabs(au) + amag));
+          const bool viol = after && !(val < LP_TINY);
+          const unsigned mv = __ballot_sync(FULL, viol || marg);
+          if (mv == 0) break;
+          const int j = __ffs(mv) - 1;
+          const unsigned mm = __ballot_sync(FULL, marg);
+          if (((mm >> j) & 1u) || !((m_up >> j) & 1u)) { ok = false; break; }
+          ucur = __shfl_sync(FULL, uown, j);
+          cur = j;
+          last = j;
+        }
+        if (ok && last >= 0) {
+          // rows before the target that bound u from below (or not at all) must hold at the final u with margin
+          const bool before = real && pos[0] < last;
+          const bool bad = (before && ((lor && (uown > ucur - 1e-9 * (1.0 + fabs(ucur)))) ||
+                                       (!upr && !lor && (bxc > -1e-9)))) ||
+                           (ucur < low0 + 1.0) || (ucur > high0 - 1.0);
+          if (!__any_sync(FULL, bad)) knew = last;
+        }
+      }
+    }
     kpos = knew;
     const int krow = pos_row(kpos, valid, ac0, ac1);
     ++n_resolve;
     nac0 = krow;
+    if constexpr (SKIP) {  // the walk argument needs every visited row to be an upper bound of u
+      const unsigned m_upper = __ballot_sync(FULL, a[0] > LP_TINY);
+      if (RPL != 1 || !((m_upper >> (krow & 31)) & 1u)) walk_ok = false;
+    }
     // broadcast row k
     double ak = a[0], bk = b[0], ck = c[0];
 #pragma unroll
@@ -244,6 +297,7 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
     nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
     p0 = z0 + tstar * dt0;  // pyx:362-363
     p1 = z1 + tstar * dt1;
+    if constexpr (SKIP) { if (nac1 != -3) walk_ok = false; }  // x left its lower box bound
   }
   ac0 = nac0;
   ac1 = nac1;
@@ -252,7 +306,7 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
   return true;
 }
 
-template <int RPL>
+template <int RPL, bool SKIP = false>
 __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL], const int nC,
                                           const double low0, const double high0, const double low1,
@@ -261,8 +315,10 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
   if (low0 > high0 || low1 > high1) return false;  // pyx:233-235
   const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;  // warp-uniform
   if (valid)
-    return lp2d_impl<RPL, true>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane, n_resolve);
-  return lp2d_impl<RPL, false>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane, n_resolve);
+    return lp2d_impl<RPL, true, false>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
+                                       n_resolve);
+  return lp2d_impl<RPL, false, SKIP>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
+                                     n_resolve);
 }
 
 // cy_solve_lp1d (pyx:93-144) as used by the x_min == x_max branch of solve_stagewise_optim (pyx:631-650):
@@ -415,7 +471,8 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       ++n_lp1d;
     } else {
       ++n_lp2d;
-      ok_lo = lp2d_warp<RPL>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane, n_resolve);
+      ok_lo = lp2d_warp<RPL, true>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+                                   n_resolve);
       x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
     }
     if (x_lower < 0) x_lower = 0;  // reachability_algorithm.py:190-191
