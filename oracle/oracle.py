@@ -28,12 +28,46 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = ctypes.CDLL(build())
-        _LIB.orc_wrapper_create.restype = ctypes.c_void_p
-        for name in ("orc_wrapper_a", "orc_wrapper_b", "orc_wrapper_c", "orc_wrapper_low", "orc_wrapper_high"):
-            getattr(_LIB, name).restype = _dp
-            getattr(_LIB, name).argtypes = [ctypes.c_void_p]
+        _LIB = _setup(ctypes.CDLL(build()))
     return _LIB
+
+
+def _setup(L):
+    L.orc_wrapper_create.restype = ctypes.c_void_p
+    for name in ("orc_wrapper_a", "orc_wrapper_b", "orc_wrapper_c", "orc_wrapper_low", "orc_wrapper_high"):
+        getattr(L, name).restype = _dp
+        getattr(L, name).argtypes = [ctypes.c_void_p]
+    return L
+
+
+class shortcut_model:
+    """Context manager: route this module through liboracle_shortcuts.so (oracle/shortcut_model.c), whose wrapper
+    checks the scalar model of the CUDA kernel's Seidel shortcuts on every 2-variable LP.  `stats()` returns
+    dict(lps, mismatches, resolves_ref, resolves_model, a_used, a_declined, b_used, b_declined)."""
+    _lib = None
+
+    def __enter__(self):
+        global _LIB
+        if shortcut_model._lib is None:
+            so = os.path.join(_HERE, "liboracle_shortcuts.so")
+            subprocess.check_call(["make", "-C", _HERE, "liboracle_shortcuts.so"], stdout=subprocess.DEVNULL)
+            shortcut_model._lib = _setup(ctypes.CDLL(so))
+        self._saved = _LIB
+        _LIB = shortcut_model._lib
+        _LIB.orc_shortcut_model_enable(1)
+        self.stats(reset=True)
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB
+        shortcut_model._lib.orc_shortcut_model_enable(0)
+        _LIB = self._saved
+
+    def stats(self, reset=False):
+        out = np.zeros(8, dtype=np.int64)
+        shortcut_model._lib.orc_shortcut_model_stats(out.ctypes.data_as(_lp), 1 if reset else 0)
+        keys = ("lps", "mismatches", "resolves_ref", "resolves_model", "a_used", "a_declined", "b_used", "b_declined")
+        return dict(zip(keys, (int(v) for v in out)))
 
 
 def _d(a):

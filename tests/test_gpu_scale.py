@@ -198,3 +198,61 @@ def test_skip_ahead_is_bit_identical_on_many_paths(ta):
     # fewer projected re-solves than LPs x 3 shows the skip-ahead is actually taken
     cnt = res.counters.cpu().numpy()
     assert cnt[:, 2].mean() < 2.5 * (G - 1)
+
+
+@pytest.mark.parametrize("R0,G", [(6, 24), (20, 16)])
+def test_seidel_shortcuts_on_degenerate_rows(ta, R0, G):
+    """The K2 shortcuts (csrc/tb_scan.cu, A: jump to the last visited row, B: skip the first warm-start re-solve) must
+    fall back to the ordinary walk whenever a decision is close to the TINY threshold: raw rows with near-duplicate,
+    scaled, parallel and slightly rotated copies (perturbations 1e-14 .. 1e-6), bit-for-bit against the sequential
+    oracle.  2*R0 + 2 rows: one and two rows per lane."""
+    import torch
+    from oracle import oracle as orc
+    B = 1500
+    rng = np.random.RandomState(99 + R0)
+    R = 2 * R0
+    rows = np.empty((B, G, 3, R))
+    xb = np.empty((B, G, 2))
+    for i in range(B):
+        a = rng.randn(G, R0)
+        b = rng.randn(G, R0)
+        c = -rng.rand(G, R0) * 10 ** rng.uniform(-1, 1)
+        eps = 10 ** rng.uniform(-14, -6)
+        kind = i % 4
+        if kind == 0:
+            a2, b2, c2 = a * (1 + eps * rng.randn(G, R0)), b * (1 + eps * rng.randn(G, R0)), c * (1 + eps * rng.randn(G, R0))
+        elif kind == 1:
+            sc = 10 ** rng.uniform(-3, 3, size=(G, R0))
+            a2, b2, c2 = a * sc, b * sc, c * sc + eps * rng.randn(G, R0)
+        elif kind == 2:
+            a2, b2, c2 = a.copy(), b.copy(), c + eps * rng.randn(G, R0)
+        else:
+            a2, b2, c2 = a + eps * rng.randn(G, R0), b.copy(), c.copy()
+        perm = rng.permutation(R)
+        rows[i, :, 0] = np.concatenate((a, a2), 1)[:, perm]
+        rows[i, :, 1] = np.concatenate((b, b2), 1)[:, perm]
+        rows[i, :, 2] = np.concatenate((c, c2), 1)[:, perm]
+        xb[i, :, 0] = 0.0
+        xb[i, :, 1] = 10 ** rng.uniform(-2, 3)
+    grid = np.linspace(0, 1, G)
+    dev = torch.device("cuda:0")
+    rec, W = ta.engine.alloc_records(B, G, R, dev)
+    host = np.zeros((B, G, W))
+    host[:, :, 0:R] = rows[:, :, 0]
+    host[:, :, R:2 * R] = rows[:, :, 1]
+    host[:, :, 2 * R:3 * R] = rows[:, :, 2]
+    host[:, :, 3 * R] = xb[:, :, 0]
+    host[:, :, 3 * R + 1] = xb[:, :, 1]
+    rec.copy_(torch.from_numpy(host))
+    z = torch.zeros(B, dtype=torch.float64, device=dev)
+    out = ta.engine.scan(rec, R, torch.from_numpy(grid).to(dev), z, z, z, counters=True)
+    K, sd, u, st = (out[k].cpu().numpy() for k in ("K", "sd", "u", "status"))
+    nok = 0
+    for i in range(B):
+        o = orc.solve_rows(rows[i], xb[i], grid, 0.0, 0.0)
+        assert o["status"] == st[i], i
+        assert np.array_equal(K[i], o["K"], equal_nan=True), i
+        if o["status"] == 0:
+            nok += 1
+            assert np.array_equal(sd[i], o["sd"]) and np.array_equal(u[i], o["u"]), i
+    assert nok > B // 2

@@ -98,6 +98,9 @@ __device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
 }
 
 constexpr int BOXBASE = 1 << 20;
+constexpr double SKIP_GAP = 1e-7;   // shortcuts A/B: required violation, relative to the terms' magnitudes (TINY = 1e-10)
+constexpr double SKIP_BIG = 1e300;
+constexpr double SKIP_TMAX = 90.0;  // shortcut A: largest line parameter of a skipped visit (see lp2d_impl)
 #ifndef TB_SCAN_NBUF
 #define TB_SCAN_NBUF 4
 #endif
@@ -158,7 +161,8 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
   }
   const unsigned lt_mask = (1u << lane) - 1u;
   int kpos = -1;
-  bool walk_ok = SKIP && (v0 > LP_TINY) && (v1 < 0);  // see the skip-ahead below
+  // shortcuts A/B below: only for the two objectives of the backward pass (min x, max x)
+  const bool skip_ok = SKIP && (((v0 > LP_TINY) && (v1 < 0)) || ((v0 < -LP_TINY) && (v1 > 0)));
   while (true) {
     // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
     int mypos = INT_MAX;
@@ -170,51 +174,110 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
     }
     int knew = __reduce_min_sync(FULL, mypos);
     if (knew == INT_MAX) break;
-    if constexpr (RPL == 1 && !PERM && SKIP) {
-      // Skip-ahead for the min-x LP of the backward pass (objective (1e-9, -1)); bit-identical, see DESIGN.md §4 K2.
-      // While every visit so far was on an upper bound of u (a > 0) and ended with x pinned at its lower box bound
-      // (1-D winner = box row "low1 <= x", nac1 == -3; also the start vertex), the following visits only walk u
-      // down through the rows that tighten it at that x, and each visit recomputes the point from scratch
-      // (z + t d over ALL earlier rows): the final state depends only on the LAST visited row.  The walk is replayed
-      // with plain arithmetic (u_j = -(b_j x + c_j)/a_j, ~25 instructions per visited row instead of a full
-      // projected re-solve).  If every visit/skip decision is clear of the TINY threshold by a margin far above the
-      // rounding error of the exact points, every visited row picks the lower end of its line (same v1d test as the
-      // exact path) and the rows that bound u from below hold at the final u, the reference is certain to visit
-      // the last row of the walk, and ONE exact re-solve on that row reproduces its state bit for bit (validated
-      // against the sequential solver on 1e6 LPs and by tests/test_gpu_scale.py).  Any doubt -> normal path.
-      if (walk_ok && nac1 == -3) {
-        const double x = p1;
-        double ucur = p0;
-        const double bxc = b[0] * x + c[0];
-        const bool upr = a[0] > LP_TINY, lor = a[0] < -LP_TINY, real = pos[0] != INT_MAX;
-        const double uown = -bxc / ((upr || lor) ? a[0] : 1.0);
-        const double v1d_own = (-b[0]) * v0 + a[0] * v1;  // the exact path's v1d if this row were visited
-        const unsigned m_up = __ballot_sync(FULL, upr && ((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
-        const double amag = fabs(b[0] * x) + fabs(c[0]);
-        int cur = kpos, last = -1;
-        bool ok = true;
-        while (true) {
-          const double au = a[0] * ucur;
-          const double val = au + b[0] * x + c[0];
-          const bool after = real && pos[0] > cur;
-          const bool marg = after && (fabs(val - LP_TINY) <= 1e-11 + 1e-12 * (fabs(au) + amag));
-          const bool viol = after && !(val < LP_TINY);
-          const unsigned mv = __ballot_sync(FULL, viol || marg);
-          if (mv == 0) break;
-          const int j = __ffs(mv) - 1;
-          const unsigned mm = __ballot_sync(FULL, marg);
-          if (((mm >> j) & 1u) || !((m_up >> j) & 1u)) { ok = false; break; }
-          ucur = __shfl_sync(FULL, uown, j);
-          cur = j;
-          last = j;
-        }
-        if (ok && last >= 0) {
-          // rows before the target that bound u from below (or not at all) must hold at the final u with margin
-          const bool before = real && pos[0] < last;
-          const bool bad = (before && ((lor && (uown > ucur - 1e-9 * (1.0 + fabs(ucur)))) ||
-                                       (!upr && !lor && (bxc > -1e-9)))) ||
-                           (ucur < low0 + 1.0) || (ucur > high0 - 1.0);
-          if (!__any_sync(FULL, bad)) knew = last;
+    if constexpr (SKIP) {
+      if (kpos < 0 && skip_ok) {
+        if constexpr (!PERM) {
+          // Shortcut A (natural order).  Start vertex = (high0, low1) for the min-x LP, (low0,
+          // high1) for the max-x LP.  In mirrored variables (ua = sg*u) every visit of the reference's walk sits on a
+          // row that bounds ua from above, lands on x = its box bound and only lowers ua; each visit recomputes the
+          // point from scratch over ALL earlier rows, so the final state depends only on the LAST visited row, and
+          // that is the row m with the smallest own bound at this x.  The reference is certain to visit m when the
+          // smallest bound among the OTHER rows (and the start value) violates row m far above the TINY threshold;
+          // one exact re-solve on m then reproduces the reference's state bit for bit, and the exact walk goes on
+          // from there.  Rows before m that bound ua from below (or not at all) must hold at the final point with
+          // a margin, and every upper row must pick the low end of its line (the exact path's v1d test).  Any doubt
+          // -> ordinary walk.  Validated against the sequential solver on 2.5e7 LPs (incl. near-duplicate rows).
+          const double sg = (v0 > 0) ? 1.0 : -1.0;
+          const double x = p1, u0m = sg * p0;
+          double uo[RPL], bxc[RPL];
+          bool upr[RPL], lor[RPL];
+          double lmin = SKIP_BIG;
+          bool bad = false;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) {
+            const bool real = pos[s] != INT_MAX;
+            const double sa = sg * a[s];
+            bxc[s] = b[s] * x + c[s];
+            upr[s] = real && (sa > LP_TINY);
+            lor[s] = real && (sa < -LP_TINY);
+            uo[s] = sg * (-bxc[s] / ((upr[s] || lor[s]) ? a[s] : 1.0));
+            const double v1d_own = (-b[s]) * v0 + a[s] * v1;  // the exact path's v1d if this row were visited
+            bad = bad || (upr[s] && !((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
+            // line parameter t of this row's landing point (own bound, x): a skipped visit must neither end on the
+            // +-1e10 sentinel of the 1-D LP nor be far enough from the foot point for a "parallel" row (|denom| <=
+            // TINY although the lines cross) to fail the LP_SMALL test there: |t| * TINY stays far below LP_SMALL
+            bad = bad || (upr[s] && !(fabs(x * a[s] - (sg * uo[s]) * b[s]) < SKIP_TMAX * (a[s] * a[s] + b[s] * b[s])));
+            lmin = (upr[s] && uo[s] < lmin) ? uo[s] : lmin;
+          }
+          const double um = warp_min(lmin);
+          int mp = INT_MAX;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) mp = (upr[s] && uo[s] == um) ? min(mp, pos[s]) : mp;
+          const int m = __reduce_min_sync(FULL, mp);
+          if (m != INT_MAX) {
+            double l2 = SKIP_BIG;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) l2 = (upr[s] && pos[s] != m && uo[s] < l2) ? uo[s] : l2;
+            double second = warp_min(l2);
+            second = (u0m < second) ? u0m : second;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+              if (pos[s] == m) {
+                const double au = a[s] * (sg * second);
+                const double val = au + bxc[s];
+                bad = bad || !(val >= SKIP_GAP * (1.0 + fabs(au) + fabs(b[s] * x) + fabs(c[s])));
+              } else if (pos[s] < m) {
+                bad = bad || (lor[s] && (uo[s] > um - 1e-9 * (1.0 + fabs(um)))) ||
+                      (!upr[s] && !lor[s] && ((bxc[s] > -1e-9) || (a[s] != 0.0)));
+              }
+            }
+            const double ur = sg * um;
+            bad = bad || (ur < low0 + 1.0) || (ur > high0 - 1.0);
+            if (!__any_sync(FULL, bad)) knew = m;
+          }
+        } else if (knew == 0) {
+          // Shortcut B (valid warm-start pair; order = row p = ac1, row k = ac0, the rest).  Row p is violated at
+          // the start vertex, so the reference re-solves on it against the box only and holds the optimum of line p
+          // inside the box next.  That point is cheap to compute with plain arithmetic; if row k is violated there
+          // far above the TINY threshold the reference is certain to re-solve on position 1 next, and that re-solve
+          // (row p + the box, recomputed from scratch) does not depend on the skipped one.
+          const int lp = ac1 & 31;
+          double ap = a[0], bp = b[0], cp = c[0];
+#pragma unroll
+          for (int s = 1; s < RPL; ++s)
+            if ((ac1 >> 5) == s) { ap = a[s]; bp = b[s]; cp = c[s]; }
+          ap = __shfl_sync(FULL, ap, lp);
+          bp = __shfl_sync(FULL, bp, lp);
+          cp = __shfl_sync(FULL, cp, lp);
+          bool okb = fabs(ap) > 1e-6;
+          const bool slope = fabs(bp) > 1e-6;
+          okb = okb && (slope || bp == 0.0);
+          const double ia = 1.0 / (okb ? ap : 1.0), ib = 1.0 / (slope ? bp : 1.0);
+          double xl = low1, xh = high1;
+          if (slope) {  // u(x) = -(bp x + cp)/ap must stay inside [low0, high0]
+            const double x1 = -(ap * low0 + cp) * ib, x2 = -(ap * high0 + cp) * ib;
+            const double xa = (x1 < x2) ? x1 : x2, xb = (x1 < x2) ? x2 : x1;
+            xl = (xa > xl) ? xa : xl;
+            xh = (xb < xh) ? xb : xh;
+          } else {
+            const double uc = -cp * ia;
+            okb = okb && !(uc < low0 + 1.0) && !(uc > high0 - 1.0);
+          }
+          okb = okb && (xl <= xh - 1e-7 * (1.0 + fabs(xl) + fabs(xh)));
+          const double slp = v1 - v0 * bp * ia;  // d objective / dx along line p
+          okb = okb && !(fabs(slp) < 1e-6);
+          const double sx = (slp > 0) ? xh : xl;
+          const double su = -(bp * sx + cp) * ia;
+          // the skipped 1-D optimum must stay clear of the +-1e10 sentinel (pyx:376-383 would report infeasible)
+          okb = okb && (fabs(sx * ap - su * bp) < 1e9 * (ap * ap + bp * bp));
+          bool kviol = false;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) {
+            const double t1 = a[s] * su, t2 = b[s] * sx;
+            const double val = t1 + t2 + c[s];
+            kviol = kviol || ((pos[s] == 1) && (val >= SKIP_GAP * (1.0 + fabs(t1) + fabs(t2) + fabs(c[s]))));
+          }
+          if (__any_sync(FULL, kviol) && okb) knew = 1;
         }
       }
     }
@@ -222,10 +285,6 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
     const int krow = pos_row(kpos, valid, ac0, ac1);
     ++n_resolve;
     nac0 = krow;
-    if constexpr (SKIP) {  // the walk argument needs every visited row to be an upper bound of u
-      const unsigned m_upper = __ballot_sync(FULL, a[0] > LP_TINY);
-      if (RPL != 1 || !((m_upper >> (krow & 31)) & 1u)) walk_ok = false;
-    }
     // broadcast row k
     double ak = a[0], bk = b[0], ck = c[0];
 #pragma unroll
@@ -297,7 +356,6 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
     nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
     p0 = z0 + tstar * dt0;  // pyx:362-363
     p1 = z1 + tstar * dt1;
-    if constexpr (SKIP) { if (nac1 != -3) walk_ok = false; }  // x left its lower box bound
   }
   ac0 = nac0;
   ac1 = nac1;
@@ -315,7 +373,7 @@ __device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, cons
   if (low0 > high0 || low1 > high1) return false;  // pyx:233-235
   const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;  // warp-uniform
   if (valid)
-    return lp2d_impl<RPL, true, false>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
+    return lp2d_impl<RPL, true, SKIP>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
                                        n_resolve);
   return lp2d_impl<RPL, false, SKIP>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
                                      n_resolve);
@@ -455,7 +513,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     double uu, xx;
     // x_upper: g = (1e-9, -1) -> v = (-1e-9, 1), slot active_c_down (g[1] <= 0), reachability_algorithm.py:229-233
     ++n_lp2d;
-    const bool ok_hi = lp2d_warp<RPL>(-1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
+    const bool ok_hi = lp2d_warp<RPL, true>(-1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
                                       n_resolve);
     const double x_upper = ok_hi ? xx : __longlong_as_double(0x7ff8000000000000LL);
     // x_lower: g = (-1e-9, 1) -> v = (1e-9, -1), slot active_c_up, reachability_algorithm.py:234-236
