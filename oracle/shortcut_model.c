@@ -99,19 +99,12 @@ static int sm_shortcut_b(const double v[3], const double *a, const double *b, co
   const double ap = a[p], bp = b[p], cp = c[p];
   if (!(fabs(ap) > 1e-6)) return 0;
   const double ia = 1.0 / ap;
-  double xl = low[1], xh = high[1];
-  if (fabs(bp) > 1e-6) {
-    const double ib = 1.0 / bp;
-    const double x1 = -(ap * low[0] + cp) * ib, x2 = -(ap * high[0] + cp) * ib;
-    const double xa = x1 < x2 ? x1 : x2, xb = x1 < x2 ? x2 : x1;
-    if (xa > xl) xl = xa;
-    if (xb < xh) xh = xb;
-  } else if (bp != 0.0) return 0;
-  else { const double uc = -cp * ia; if (uc < low[0] + 1.0 || uc > high[0] - 1.0) return 0; }
-  if (!(xl <= xh - 1e-7 * (1 + fabs(xl) + fabs(xh)))) return 0;
+  if (!(low[1] <= high[1] - 1e-7 * (1 + fabs(low[1]) + fabs(high[1])))) return 0;
   const double slope = v[1] - v[0] * bp * ia;
   if (fabs(slope) < 1e-6) return 0;
-  const double sx = slope > 0 ? xh : xl, su = -(bp * sx + cp) * ia;
+  /* optimum of line p inside the box = the x bound the objective points to, if u stays well inside its bounds there */
+  const double sx = slope > 0 ? high[1] : low[1], su = -(bp * sx + cp) * ia;
+  if (!(su >= low[0] + 1.0 && su <= high[0] - 1.0)) return 0;
   if (!(fabs(sx * ap - su * bp) < 1e9 * (ap * ap + bp * bp))) return 0; /* clear of the +-1e10 sentinel */
   const double t1 = a[k] * su, t2 = b[k] * sx, val = t1 + t2 + c[k];
   return val >= sm_gap * (1.0 + fabs(t1) + fabs(t2) + fabs(c[k]));

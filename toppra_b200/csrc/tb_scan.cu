@@ -164,78 +164,82 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
   // shortcuts A/B below: only for the two objectives of the backward pass (min x, max x)
   const bool skip_ok = SKIP && (((v0 > LP_TINY) && (v1 < 0)) || ((v0 < -LP_TINY) && (v1 > 0)));
   while (true) {
-    // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
-    int mypos = INT_MAX;
-#pragma unroll
-    for (int s = 0; s < RPL; ++s) {
-      const double val = a[s] * p0 + b[s] * p1 + c[s];
-      const bool cand = !(val < LP_TINY) && (pos[s] > kpos) && (pos[s] != INT_MAX);
-      mypos = cand ? min(mypos, pos[s]) : mypos;
-    }
-    int knew = __reduce_min_sync(FULL, mypos);
-    if (knew == INT_MAX) break;
-    if constexpr (SKIP) {
+    int knew = INT_MAX;
+    if constexpr (SKIP && !PERM) {
       if (kpos < 0 && skip_ok) {
-        if constexpr (!PERM) {
-          // Shortcut A (natural order).  Start vertex = (high0, low1) for the min-x LP, (low0,
-          // high1) for the max-x LP.  In mirrored variables (ua = sg*u) every visit of the reference's walk sits on a
-          // row that bounds ua from above, lands on x = its box bound and only lowers ua; each visit recomputes the
-          // point from scratch over ALL earlier rows, so the final state depends only on the LAST visited row, and
-          // that is the row m with the smallest own bound at this x.  The reference is certain to visit m when the
-          // smallest bound among the OTHER rows (and the start value) violates row m far above the TINY threshold;
-          // one exact re-solve on m then reproduces the reference's state bit for bit, and the exact walk goes on
-          // from there.  Rows before m that bound ua from below (or not at all) must hold at the final point with
-          // a margin, and every upper row must pick the low end of its line (the exact path's v1d test).  Any doubt
-          // -> ordinary walk.  Validated against the sequential solver on 2.5e7 LPs (incl. near-duplicate rows).
-          const double sg = (v0 > 0) ? 1.0 : -1.0;
-          const double x = p1, u0m = sg * p0;
-          double uo[RPL], bxc[RPL];
-          bool upr[RPL], lor[RPL];
-          double lmin = SKIP_BIG;
-          bool bad = false;
+        // Shortcut A (natural order).  Start vertex = (high0, low1) for the min-x LP, (low0,
+        // high1) for the max-x LP.  In mirrored variables (ua = sg*u) every visit of the reference's walk sits on a
+        // row that bounds ua from above, lands on x = its box bound and only lowers ua; each visit recomputes the
+        // point from scratch over ALL earlier rows, so the final state depends only on the LAST visited row, and
+        // that is the row m with the smallest own bound at this x.  The reference is certain to visit m when the
+        // smallest bound among the OTHER rows (and the start value) violates row m far above the TINY threshold;
+        // one exact re-solve on m then reproduces the reference's state bit for bit, and the exact walk goes on
+        // from there.  Rows before m that bound ua from below (or not at all) must hold at the final point with
+        // a margin, and every upper row must pick the low end of its line (the exact path's v1d test).  Any doubt
+        // -> ordinary walk.  Validated against the sequential solver on 2.5e7 LPs (incl. near-duplicate rows).
+        const double sg = (v0 > 0) ? 1.0 : -1.0;
+        const double x = p1, u0m = sg * p0;
+        double uo[RPL], bxc[RPL];
+        bool upr[RPL], lor[RPL];
+        double lmin = SKIP_BIG;
+        bool bad = false;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+          const bool real = pos[s] != INT_MAX;
+          const double sa = sg * a[s];
+          bxc[s] = b[s] * x + c[s];
+          upr[s] = real && (sa > LP_TINY);
+          lor[s] = real && (sa < -LP_TINY);
+          uo[s] = sg * (-bxc[s] / ((upr[s] || lor[s]) ? a[s] : 1.0));
+          const double v1d_own = (-b[s]) * v0 + a[s] * v1;  // the exact path's v1d if this row were visited
+          bad = bad || (upr[s] && !((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
+          // line parameter t of this row's landing point (own bound, x): a skipped visit must neither end on the
+          // +-1e10 sentinel of the 1-D LP nor be far enough from the foot point for a "parallel" row (|denom| <=
+          // TINY although the lines cross) to fail the LP_SMALL test there: |t| * TINY stays far below LP_SMALL
+          bad = bad || (upr[s] && !(fabs(x * a[s] - (sg * uo[s]) * b[s]) < SKIP_TMAX * (a[s] * a[s] + b[s] * b[s])));
+          lmin = (upr[s] && uo[s] < lmin) ? uo[s] : lmin;
+        }
+        const double um = warp_min(lmin);
+        int mp = INT_MAX;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) mp = (upr[s] && uo[s] == um) ? min(mp, pos[s]) : mp;
+        const int m = __reduce_min_sync(FULL, mp);
+        if (m != INT_MAX) {
+          double l2 = SKIP_BIG;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) l2 = (upr[s] && pos[s] != m && uo[s] < l2) ? uo[s] : l2;
+          double second = warp_min(l2);
+          second = (u0m < second) ? u0m : second;
 #pragma unroll
           for (int s = 0; s < RPL; ++s) {
-            const bool real = pos[s] != INT_MAX;
-            const double sa = sg * a[s];
-            bxc[s] = b[s] * x + c[s];
-            upr[s] = real && (sa > LP_TINY);
-            lor[s] = real && (sa < -LP_TINY);
-            uo[s] = sg * (-bxc[s] / ((upr[s] || lor[s]) ? a[s] : 1.0));
-            const double v1d_own = (-b[s]) * v0 + a[s] * v1;  // the exact path's v1d if this row were visited
-            bad = bad || (upr[s] && !((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
-            // line parameter t of this row's landing point (own bound, x): a skipped visit must neither end on the
-            // +-1e10 sentinel of the 1-D LP nor be far enough from the foot point for a "parallel" row (|denom| <=
-            // TINY although the lines cross) to fail the LP_SMALL test there: |t| * TINY stays far below LP_SMALL
-            bad = bad || (upr[s] && !(fabs(x * a[s] - (sg * uo[s]) * b[s]) < SKIP_TMAX * (a[s] * a[s] + b[s] * b[s])));
-            lmin = (upr[s] && uo[s] < lmin) ? uo[s] : lmin;
-          }
-          const double um = warp_min(lmin);
-          int mp = INT_MAX;
-#pragma unroll
-          for (int s = 0; s < RPL; ++s) mp = (upr[s] && uo[s] == um) ? min(mp, pos[s]) : mp;
-          const int m = __reduce_min_sync(FULL, mp);
-          if (m != INT_MAX) {
-            double l2 = SKIP_BIG;
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) l2 = (upr[s] && pos[s] != m && uo[s] < l2) ? uo[s] : l2;
-            double second = warp_min(l2);
-            second = (u0m < second) ? u0m : second;
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) {
-              if (pos[s] == m) {
-                const double au = a[s] * (sg * second);
-                const double val = au + bxc[s];
-                bad = bad || !(val >= SKIP_GAP * (1.0 + fabs(au) + fabs(b[s] * x) + fabs(c[s])));
-              } else if (pos[s] < m) {
-                bad = bad || (lor[s] && (uo[s] > um - 1e-9 * (1.0 + fabs(um)))) ||
-                      (!upr[s] && !lor[s] && ((bxc[s] > -1e-9) || (a[s] != 0.0)));
-              }
+            if (pos[s] == m) {
+              const double au = a[s] * (sg * second);
+              const double val = au + bxc[s];
+              bad = bad || !(val >= SKIP_GAP * (1.0 + fabs(au) + fabs(b[s] * x) + fabs(c[s])));
+            } else if (pos[s] < m) {
+              bad = bad || (lor[s] && (uo[s] > um - 1e-9 * (1.0 + fabs(um)))) ||
+                    (!upr[s] && !lor[s] && ((bxc[s] > -1e-9) || (a[s] != 0.0)));
             }
-            const double ur = sg * um;
-            bad = bad || (ur < low0 + 1.0) || (ur > high0 - 1.0);
-            if (!__any_sync(FULL, bad)) knew = m;
           }
-        } else if (knew == 0) {
+          const double ur = sg * um;
+          bad = bad || (ur < low0 + 1.0) || (ur > high0 - 1.0);
+          if (!__any_sync(FULL, bad)) knew = m;
+        }
+      }
+    }
+    if (knew == INT_MAX) {
+      // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
+      int mypos = INT_MAX;
+#pragma unroll
+      for (int s = 0; s < RPL; ++s) {
+        const double val = a[s] * p0 + b[s] * p1 + c[s];
+        const bool cand = !(val < LP_TINY) && (pos[s] > kpos) && (pos[s] != INT_MAX);
+        mypos = cand ? min(mypos, pos[s]) : mypos;
+      }
+      knew = __reduce_min_sync(FULL, mypos);
+      if (knew == INT_MAX) break;
+      if constexpr (SKIP && PERM) {
+        if (kpos < 0 && skip_ok && knew == 0) {
           // Shortcut B (valid warm-start pair; order = row p = ac1, row k = ac0, the rest).  Row p is violated at
           // the start vertex, so the reference re-solves on it against the box only and holds the optimum of line p
           // inside the box next.  That point is cheap to compute with plain arithmetic; if row k is violated there
@@ -250,24 +254,15 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
           bp = __shfl_sync(FULL, bp, lp);
           cp = __shfl_sync(FULL, cp, lp);
           bool okb = fabs(ap) > 1e-6;
-          const bool slope = fabs(bp) > 1e-6;
-          okb = okb && (slope || bp == 0.0);
-          const double ia = 1.0 / (okb ? ap : 1.0), ib = 1.0 / (slope ? bp : 1.0);
-          double xl = low1, xh = high1;
-          if (slope) {  // u(x) = -(bp x + cp)/ap must stay inside [low0, high0]
-            const double x1 = -(ap * low0 + cp) * ib, x2 = -(ap * high0 + cp) * ib;
-            const double xa = (x1 < x2) ? x1 : x2, xb = (x1 < x2) ? x2 : x1;
-            xl = (xa > xl) ? xa : xl;
-            xh = (xb < xh) ? xb : xh;
-          } else {
-            const double uc = -cp * ia;
-            okb = okb && !(uc < low0 + 1.0) && !(uc > high0 - 1.0);
-          }
-          okb = okb && (xl <= xh - 1e-7 * (1.0 + fabs(xl) + fabs(xh)));
+          const double ia = 1.0 / (okb ? ap : 1.0);
+          okb = okb && (low1 <= high1 - 1e-7 * (1.0 + fabs(low1) + fabs(high1)));
           const double slp = v1 - v0 * bp * ia;  // d objective / dx along line p
           okb = okb && !(fabs(slp) < 1e-6);
-          const double sx = (slp > 0) ? xh : xl;
+          // optimum of line p inside the box: the x bound the objective points to, provided u stays well inside its
+          // own bounds there (otherwise the u bounds clip the line first: left to the exact path)
+          const double sx = (slp > 0) ? high1 : low1;
           const double su = -(bp * sx + cp) * ia;
+          okb = okb && (su >= low0 + 1.0) && (su <= high0 - 1.0);
           // the skipped 1-D optimum must stay clear of the +-1e10 sentinel (pyx:376-383 would report infeasible)
           okb = okb && (fabs(sx * ap - su * bp) < 1e9 * (ap * ap + bp * bp));
           bool kviol = false;
@@ -411,13 +406,12 @@ __device__ __forceinline__ void load_rows(const double *rec, const int R, const 
 #pragma unroll
   for (int s = 0; s < RPL; ++s) {
     const int r = lane + 32 * s;
-    if (r >= 2 && r < nC) {
-      a[s] = rec[r - 2];
-      b[s] = rec[R + r - 2];
-      c[s] = rec[2 * R + r - 2];
-    } else {
-      a[s] = 0.0; b[s] = 0.0; c[s] = -1.0;
-    }
+    const bool in = (r >= 2) && (r < nC);
+    const int j = in ? r - 2 : 0;  // always a valid slot of the record: load, then select
+    const double va = rec[j], vb = rec[R + j], vc = rec[2 * R + j];
+    a[s] = in ? va : 0.0;
+    b[s] = in ? vb : 0.0;
+    c[s] = in ? vc : -1.0;
   }
 }
 
@@ -425,9 +419,12 @@ template <int RPL>
 __device__ __forceinline__ void set_xnext_rows(const int lane, const double delta, const double xn_min,
                                                const double xn_max, double (&a)[RPL], double (&b)[RPL],
                                                double (&c)[RPL]) {
-  // pyx:604-620: row0 = (-2 delta, -1, x_next_min), row1 = (2 delta, 1, -x_next_max)
-  if (lane == 0) { a[0] = -2 * delta; b[0] = -1.0; c[0] = xn_min; }
-  if (lane == 1) { a[0] = 2 * delta; b[0] = 1.0; c[0] = -xn_max; }
+  // pyx:604-620: row0 = (-2 delta, -1, x_next_min), row1 = (2 delta, 1, -x_next_max); selects, no branches
+  const bool xr = lane < 2, first = lane == 0;
+  const double sgn = first ? -1.0 : 1.0;
+  a[0] = xr ? sgn * (2 * delta) : a[0];  // -(2 delta) == -2 * delta bit for bit
+  b[0] = xr ? sgn : b[0];
+  c[0] = xr ? (first ? xn_min : -xn_max) : c[0];
 }
 
 template <int RPL, int WARPS, int MINB, bool FAST>
@@ -445,9 +442,19 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double)) + warp * SCAN_NBUF;
   const int N = G - 1, nC = R + 2;
   const unsigned rec_bytes = (unsigned)(W * sizeof(double));
-  const double *rec_path = records + (size_t)path * G * W;
-  const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
-  double *Kp = Kout + (size_t)path * G * 2;
+  // Per-path base pointers live in shared memory: under the 64-register cap the compiler otherwise rebuilds them
+  // from blockIdx and the kernel parameters (a chain of 64-bit multiplies) at every use inside the stage loops.
+  const void *volatile *sptr = reinterpret_cast<const void *volatile *>(
+      smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double) + (size_t)WARPS * SCAN_NBUF * sizeof(uint64_t)) + warp * 4;
+  if (lane == 0) {
+    sptr[0] = records + (size_t)path * G * W;
+    sptr[1] = grid + (grid_shared ? 0 : (size_t)path * G);
+    sptr[2] = Kout + (size_t)path * G * 2;
+  }
+  __syncwarp();
+  auto rec_path = [&]() { return static_cast<const double *>(sptr[0]); };
+  auto gp = [&]() { return static_cast<const double *>(sptr[1]); };
+  auto Kp = [&]() { return static_cast<double *>(const_cast<void *>(sptr[2])); };
   const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
   const bool forward_only = (flags & 16) != 0;  // K and status come from an earlier TB_SCAN_BACKWARD_ONLY launch
   constexpr bool fast_lower = FAST;             // opt-in shortcut for the min-x LP (TB_SCAN_FAST_LOWER, not bit-identical)
@@ -471,7 +478,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     if (lane == 0) {
       const unsigned q = n_issued % SCAN_NBUF;
       mbar_expect_tx(&bars[q], rec_bytes);
-      bulk_g2s(bufs + (size_t)q * W, rec_path + (size_t)stage * W, rec_bytes, &bars[q]);
+      bulk_g2s(bufs + (size_t)q * W, rec_path() + (size_t)stage * W, rec_bytes, &bars[q]);
     }
     ++n_issued;
   };
@@ -483,7 +490,8 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   };
   constexpr int AHEAD = SCAN_NBUF - 1;
 
-  int n_lp2d = 0, n_lp1d = 0, n_resolve = 0, n_retry = 0;
+  // instrumentation: projected re-solves, retries, fast-mode stages; the LP counts are derived from the stage counts
+  int n_resolve = 0, n_retry = 0, n_fast = 0;
   double a[RPL], b[RPL], c[RPL];
 
   // ---------------- backward pass: controllable sets, reachability_algorithm.py:166-238 ----------------
@@ -491,14 +499,13 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   const double sds = sd_start ? sd_start[path] : 0.0;
   const double sdeh = sd_end_hi ? sd_end_hi[path] : sde;
   double kn0 = sde * sde, kn1 = sdeh * sdeh;  // K[N] = [sdmin^2, sdmax^2], reachability_algorithm.py:185
-  if (lane == 0 && !forward_only) { Kp[2 * N] = kn0; Kp[2 * N + 1] = kn1; }
+  if (lane == 0 && !forward_only) { double *kq = Kp(); kq[2 * N] = kn0; kq[2 * N + 1] = kn1; }
   int st = TB_STATUS_OK, fstage = -1;
   int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0;  // active_c_up / active_c_down, initialised to zeros (pyx:526-527)
   if (forward_only) {
     st = status[path];
     fstage = fail_stage ? fail_stage[path] : -1;
-    kn0 = Kp[0];
-    kn1 = Kp[1];
+    { const double *kq = Kp(); kn0 = kq[0]; kn1 = kq[1]; }
   }
   for (int q = 0; !forward_only && q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
   for (int i = forward_only ? -1 : N - 1; i >= 0; --i) {
@@ -507,12 +514,12 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     const double xlo = rec[3 * R], xhi = rec[3 * R + 1];
     __syncwarp();
     if (i - AHEAD >= 0) issue(i - AHEAD);
-    const double delta = gp[i + 1] - gp[i];
+    const double *gq = gp();
+    const double delta = gq[i + 1] - gq[i];
     set_xnext_rows<RPL>(lane, delta, kn0, kn1, a, b, c);
     // low/high: pyx:587-601 with x_min = x_max = NaN
     double uu, xx;
     // x_upper: g = (1e-9, -1) -> v = (-1e-9, 1), slot active_c_down (g[1] <= 0), reachability_algorithm.py:229-233
-    ++n_lp2d;
     const bool ok_hi = lp2d_warp<RPL, true>(-1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
                                       n_resolve);
     const double x_upper = ok_hi ? xx : __longlong_as_double(0x7ff8000000000000LL);
@@ -526,24 +533,29 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       // (|noise| <= ~1e-16, 5 % of the stages): this shortcut is exact for the LP, not bit-identical to that noise.
       ok_lo = true;
       x_lower = xlo;
-      ++n_lp1d;
+      ++n_fast;
     } else {
-      ++n_lp2d;
-      ok_lo = lp2d_warp<RPL, true>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+        ok_lo = lp2d_warp<RPL, true>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
                                    n_resolve);
       x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
     }
     if (x_lower < 0) x_lower = 0;  // reachability_algorithm.py:190-191
-    if (lane == 0) { Kp[2 * i] = x_lower; Kp[2 * i + 1] = x_upper; }
+    if (lane == 0) { double *kq = Kp(); kq[2 * i] = x_lower; kq[2 * i + 1] = x_upper; }
     if (!(ok_hi && ok_lo)) {
       // reachability_algorithm.py:192-197: stop; the remaining K entries stay 0 (np.zeros)
       st = TB_STATUS_FAIL_UNCONTROLLABLE;
       fstage = i;
-      for (int j = lane; j < 2 * i; j += 32) Kp[j] = 0.0;
+      { double *kq = Kp(); for (int j = lane; j < 2 * i; j += 32) kq[j] = 0.0; }
       break;
     }
     kn0 = x_lower;
     kn1 = x_upper;
+  }
+  if (counters && lane == 0 && !forward_only) {
+    // backward stages entered: N, or N - fstage when stage fstage failed; 2 LPs each (fast mode: n_fast of them 1-variable)
+    const int nb = (st == TB_STATUS_OK) ? N : N - fstage;
+    counters[path * 4 + 0] = 2 * nb - n_fast;
+    counters[path * 4 + 1] = n_fast;
   }
   // drain a prefetch that was issued but not consumed (failure path), so the buffers can be reused
   while (n_waited < n_issued) (void)acquire();
@@ -577,8 +589,10 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       load_rows<RPL>(rec, R, nC, lane, a, b, c);
       __syncwarp();
       if (i + AHEAD < N) issue(i + AHEAD);
-      const double delta = gp[i + 1] - gp[i];
-      const double k0 = Kp[2 * (i + 1)], k1 = Kp[2 * (i + 1) + 1];
+      const double *gq = gp();
+      const double delta = gq[i + 1] - gq[i];
+      const double *kq = Kp();
+      const double k0 = kq[2 * (i + 1)], k1 = kq[2 * (i + 1) + 1];
       set_xnext_rows<RPL>(lane, delta, k0, k1, a, b, c);
       int tries = 0;
       bool ok;
@@ -586,8 +600,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       while (true) {
         // _forward_step: g = (-2 delta, -1), x_min = x_max = x -> 1-D branch, v0 = 2 delta (pyx:628-636);
         // TOPPRAsd's slowest pass uses g = (2 delta, 1) (desired_duration_algorithm.py:218-223)
-        ++n_lp1d;
-        ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
+          ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
         if (ok || sd_mode || tries >= MAX_TRIES) break;  // TOPPRAsd has no retry rule
         x = fmax(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
         ++tries;
@@ -626,8 +639,11 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     status[path] = st;
     if (fail_stage) fail_stage[path] = fstage;
     if (counters) {
-      counters[path * 4 + 0] = n_lp2d;
-      counters[path * 4 + 1] = n_lp1d;
+      // forward: one 1-variable LP per stage entered (N, or fstage + 1 when stage fstage failed) + one per retry;
+      // none when the path failed before the forward pass
+      const int n_fwd_stages = (st == TB_STATUS_OK) ? N : ((st == TB_STATUS_ERR_UNKNOWN) ? fstage + 1 : -1);
+      if (forward_only) { counters[path * 4 + 0] = 0; counters[path * 4 + 1] = 0; }
+      if (n_fwd_stages >= 0) counters[path * 4 + 1] += n_fwd_stages + n_retry;
       counters[path * 4 + 2] = n_resolve;
       counters[path * 4 + 3] = n_retry;
     }
@@ -759,7 +775,8 @@ template <int RPL>
 int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                 const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
                 double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
-  const size_t smem = (size_t)SCAN_WARPS * SCAN_NBUF * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t);
+  const size_t smem = (size_t)SCAN_WARPS * SCAN_NBUF * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t) +
+                      SCAN_WARPS * 4 * sizeof(void *);
   // Two register budgets for the common nC <= 32 case: 64 registers (32 one-warp CTAs per SM: the 4096-path batch
   // of BASELINE cfg 2 is a single wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
   static const char *occ_env = getenv("TB_SCAN_OCC");
