@@ -30,18 +30,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// Arrive/copy/wait take 32-bit shared-window addresses (computed once per kernel): no generic->shared conversion and
+// no 64-bit pointer arithmetic in the stage loops.
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, unsigned bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait_s(const uint32_t addr, unsigned parity) {
   uint32_t ok;
-  const uint32_t addr = smem_u32(bar);
   do {
     asm volatile(
         "{\n"
@@ -96,6 +96,10 @@ __device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
   if (r >= hi) ++r;
   return r;
 }
+
+// Python's builtin max(a, b) / min(a, b) on floats (reachability_algorithm.py:324-354): a unless b compares beyond it
+__device__ __forceinline__ double py_max(const double a, const double b) { return (b > a) ? b : a; }
+__device__ __forceinline__ double py_min(const double a, const double b) { return (b < a) ? b : a; }
 
 constexpr int BOXBASE = 1 << 20;
 constexpr double SKIP_GAP = 1e-7;   // shortcuts A/B: required violation, relative to the terms' magnitudes (TINY = 1e-10)
@@ -190,7 +194,11 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
           bxc[s] = b[s] * x + c[s];
           upr[s] = real && (sa > LP_TINY);
           lor[s] = real && (sa < -LP_TINY);
-          uo[s] = sg * (-bxc[s] / ((upr[s] || lor[s]) ? a[s] : 1.0));
+          // a zero numerator (row 0 at x = 0 with K_lo = 0: every stage) would send the IEEE division through its
+          // slow-path subroutine; this value only feeds the margin tests, so 0 is substituted directly
+          const bool zn = (bxc[s] == 0.0);
+          const double qd = -(zn ? 1.0 : bxc[s]) / ((upr[s] || lor[s]) ? a[s] : 1.0);
+          uo[s] = zn ? 0.0 : sg * qd;
           const double v1d_own = (-b[s]) * v0 + a[s] * v1;  // the exact path's v1d if this row were visited
           bad = bad || (upr[s] && !((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
           // line parameter t of this row's landing point (own bound, x): a skipped visit must neither end on the
@@ -385,7 +393,12 @@ __device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double 
   for (int s = 0; s < RPL; ++s) {
     const double bxc = b[s] * x + c[s];
     const bool up = a[s] > LP_TINY, dn = a[s] < -LP_TINY;
-    const double t = -bxc / ((up || dn) ? a[s] : 1.0);  // unused lanes divide by 1: stay on the division fast path
+    // unused lanes divide by 1 and a zero numerator (row 0 at x = 0 with K_lo = 0) is not divided at all: both would
+    // leave the IEEE division's fast path.  (-bxc) * a is the quotient's correctly signed zero.
+    const double den = (up || dn) ? a[s] : 1.0;
+    const bool zn = (bxc == 0.0);
+    const double q = -(zn ? 1.0 : bxc) / den;
+    const double t = zn ? (-bxc) * den : q;
     my_hi = (up && t < my_hi) ? t : my_hi;
     my_lo = (dn && t > my_lo) ? t : my_lo;
   }
@@ -435,7 +448,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
             double *__restrict__ Kout, double *__restrict__ sdout, double *__restrict__ uout,
             int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (WARPS == 1) ? 0 : (int)(threadIdx.x >> 5), lane = (WARPS == 1) ? (int)threadIdx.x : (int)(threadIdx.x & 31);
   const long path = (long)blockIdx.x * WARPS + warp;
   if (path >= B) return;
   double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * SCAN_NBUF * W;
@@ -474,17 +487,18 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   // Ring of SCAN_NBUF record buffers: up to SCAN_NBUF-1 bulk copies in flight per warp.  The forward pass solves a
   // stage in well under the HBM round trip, so one stage of look-ahead is not enough there.
   unsigned n_issued = 0, n_waited = 0;
+  const uint32_t bufs_s = smem_u32(bufs), bars_s = smem_u32(bars);
   auto issue = [&](int stage) {
     if (lane == 0) {
       const unsigned q = n_issued % SCAN_NBUF;
-      mbar_expect_tx(&bars[q], rec_bytes);
-      bulk_g2s(bufs + (size_t)q * W, rec_path() + (size_t)stage * W, rec_bytes, &bars[q]);
+      mbar_expect_tx_s(bars_s + q * 8u, rec_bytes);
+      bulk_g2s_s(bufs_s + q * rec_bytes, rec_path() + (size_t)stage * W, rec_bytes, bars_s + q * 8u);
     }
     ++n_issued;
   };
   auto acquire = [&]() -> const double * {
     const unsigned q = n_waited % SCAN_NBUF;
-    mbar_wait(&bars[q], (n_waited / SCAN_NBUF) & 1);
+    mbar_wait_s(bars_s + q * 8u, (n_waited / SCAN_NBUF) & 1);
     ++n_waited;
     return bufs + (size_t)q * W;
   };
@@ -602,7 +616,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
         // TOPPRAsd's slowest pass uses g = (2 delta, 1) (desired_duration_algorithm.py:218-223)
           ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
         if (ok || sd_mode || tries >= MAX_TRIES) break;  // TOPPRAsd has no retry rule
-        x = fmax(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
+        x = py_max(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
         ++tries;
         ++n_retry;
       }
@@ -618,10 +632,10 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       }
       double x_next = x + 2 * delta * uopt;                       // reachability_algorithm.py:352
       if (sd_mode) {
-        x_next = fmin(k1, fmax(k0, x_next - ALG_SMALL));          // desired_duration_algorithm.py:117
+        x_next = py_min(k1, py_max(k0, x_next - ALG_SMALL));          // desired_duration_algorithm.py:117
       } else {
-        x_next = fmax(x_next - ALG_TINY, 0.9999 * x_next);        // :353
-        x_next = fmin(k1, fmax(k0, x_next));                      // :354
+        x_next = py_max(x_next - ALG_TINY, 0.9999 * x_next);        // :353
+        x_next = py_min(k1, py_max(k0, x_next));                      // :354
       }
       if (lane == 0) {
         up[i] = uopt;
