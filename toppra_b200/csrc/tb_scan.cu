@@ -97,6 +97,13 @@ __device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
   return r;
 }
 
+// Identity the optimiser cannot see through: keeps a sanitised division operand from being folded back into the
+// original one when the quotient is later replaced by a select (the compiler would divide the raw value again).
+__device__ __forceinline__ double opaque(double v) {
+  asm volatile("" : "+d"(v));
+  return v;
+}
+
 // Python's builtin max(a, b) / min(a, b) on floats (reachability_algorithm.py:324-354): a unless b compares beyond it
 __device__ __forceinline__ double py_max(const double a, const double b) { return (b > a) ? b : a; }
 __device__ __forceinline__ double py_min(const double a, const double b) { return (b < a) ? b : a; }
@@ -197,7 +204,7 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
           // a zero numerator (row 0 at x = 0 with K_lo = 0: every stage) would send the IEEE division through its
           // slow-path subroutine; this value only feeds the margin tests, so 0 is substituted directly
           const bool zn = (bxc[s] == 0.0);
-          const double qd = -(zn ? 1.0 : bxc[s]) / ((upr[s] || lor[s]) ? a[s] : 1.0);
+          const double qd = -opaque(zn ? 1.0 : bxc[s]) / ((upr[s] || lor[s]) ? a[s] : 1.0);
           uo[s] = zn ? 0.0 : sg * qd;
           const double v1d_own = (-b[s]) * v0 + a[s] * v1;  // the exact path's v1d if this row were visited
           bad = bad || (upr[s] && !((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
@@ -397,7 +404,7 @@ __device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double 
     // leave the IEEE division's fast path.  (-bxc) * a is the quotient's correctly signed zero.
     const double den = (up || dn) ? a[s] : 1.0;
     const bool zn = (bxc == 0.0);
-    const double q = -(zn ? 1.0 : bxc) / den;
+    const double q = -opaque(zn ? 1.0 : bxc) / den;
     const double t = zn ? (-bxc) * den : q;
     my_hi = (up && t < my_hi) ? t : my_hi;
     my_lo = (dn && t > my_lo) ? t : my_lo;
