@@ -320,5 +320,38 @@ def main():
     print("torque: statuses", data["status"])
 
 
+def joint_torque_case():
+    """JointTorqueConstraint (toppra/constraint/joint_torque.py:7-116): vel + torque with dry friction,
+    both discretisation schemes, synthetic closed-form inverse dynamics of tests/problems.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from problems import make_torque_problem, inv_dyn_numpy
+    codes = list(algo.ParameterizationReturnCode)
+    data = {}
+    ssw, grid = np.linspace(0, 1, 5), np.linspace(0, 1, 60)
+    for scheme in (0, 1):
+        outs = []
+        for seed in range(2100, 2103):
+            way, vlim, alim, taulim = make_torque_problem(seed)
+            fric = 0.5 + 0.25 * np.arange(6)
+            path = ta.SplineInterpolator(ssw, way)
+            pc_vel = constraint.JointVelocityConstraint(vlim)
+            pc_tau = constraint.JointTorqueConstraint(inv_dyn_numpy, taulim, fric, discretization_scheme=scheme)
+            inst = algo.TOPPRA([pc_vel, pc_tau], path, gridpoints=grid, solver_wrapper="seidel")
+            sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+            a, b, c, F, g, _, _ = pc_tau.compute_constraint_params(path, grid)
+            xb = pc_vel.compute_constraint_params(path, grid)[-1]
+            outs.append(dict(way=way, vlim=vlim, taulim=taulim, fric=fric, K=K, sd=sd, sdd=sdd, a=a, b=b, c=c, F=F, g=g,
+                             xbound=xb, status=codes.index(inst.problem_data.return_code)))
+        for k, v in stack(outs).items():
+            data["s%d_%s" % (scheme, k)] = v
+    data.update(ss=ssw, grid=grid)
+    np.savez_compressed(os.path.join(HERE, "joint_torque_dof6.npz"), **data)
+    print("joint torque: statuses", data["s0_status"], data["s1_status"])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "joint_torque":
+        joint_torque_case()
+    else:
+        main()
+        joint_torque_case()

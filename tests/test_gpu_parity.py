@@ -278,6 +278,31 @@ def test_torque_second_order(ta, golden):
     np.testing.assert_allclose(h["sd"], g["sd"], rtol=1e-9, atol=1e-12)
 
 
+def test_joint_torque_constraint(ta, golden):
+    """JointTorqueConstraint (reference joint_torque.py:7-116): vel + torque with dry friction, Collocation
+    (the reference's default for this class) and Interpolation, bit-exact incl. the host 7-tuple."""
+    from problems import inv_dyn_numpy
+    g = golden("joint_torque_dof6")
+    for scheme in (0, 1):
+        t = "s%d_" % scheme
+        for b in range(g[t + "way"].shape[0]):
+            path = ta.SplineInterpolator(g["ss"], g[t + "way"][b])
+            pc_tau = ta.constraint.JointTorqueConstraint(inv_dyn_numpy, g[t + "taulim"][b], g[t + "fric"][b],
+                                                         discretization_scheme=scheme)
+            assert pc_tau.identical and pc_tau.get_dof() == 6
+            cons = [ta.constraint.JointVelocityConstraint(g[t + "vlim"][b]), pc_tau]
+            inst = ta.algorithm.TOPPRA(cons, path, gridpoints=g["grid"], solver_wrapper="seidel")
+            assert inst.solver_wrapper.nC == 2 + (12 if scheme == 0 else 24)
+            sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+            assert _eq(K, g[t + "K"][b]) and _eq(sd, g[t + "sd"][b]) and _eq(sdd, g[t + "sdd"][b]), (scheme, b)
+            a, bb, c, F, gg, ub, xb = pc_tau.compute_constraint_params(path, g["grid"])
+            assert ub is None and xb is None and _eq(F, g[t + "F"][b]) and _eq(gg, g[t + "g"][b])
+            assert _eq(a, g[t + "a"][b]) and _eq(bb, g[t + "b"][b]) and _eq(c, g[t + "c"][b]), (scheme, b)
+    with pytest.raises(ValueError):
+        ta.constraint.JointTorqueConstraint(inv_dyn_numpy, np.ones((5, 2)), np.zeros(5)).compute_constraint_params(
+            path, g["grid"])
+
+
 def test_errors(ta, golden):
     g = golden("cfg1_seed9")
     path = ta.SplineInterpolator(g["ss"], g["way"])

@@ -228,6 +228,21 @@ def test_torque_second_order(golden):
         assert _eq(o["K"], g["K"][b]) and _eq(o["sd"], g["sd"][b]) and _eq(o["u"], g["sdd"][b])
 
 
+def test_joint_torque_constraint(golden):
+    """JointTorqueConstraint (joint_torque.py:77-116, dry friction, identical F) for both discretisation schemes: the
+    reference's (a, b, c, F, g) through the generic row interface reproduce its K / sd / sdd."""
+    g = golden("joint_torque_dof6")
+    for scheme in (0, 1):
+        t = "s%d_" % scheme
+        for b in range(g[t + "way"].shape[0]):
+            a, bb, cc, F, gv = (g[t + k][b] for k in ("a", "b", "c", "F", "g"))
+            assert F.shape == ((12, 6) if scheme == 0 else (24, 12)) and a.shape[1] == F.shape[1]
+            rows = np.stack((a.dot(F.T), bb.dot(F.T), cc.dot(F.T) - gv), axis=1)
+            o = orc.solve_rows(rows, g[t + "xbound"][b], g["grid"], 0, 0)
+            assert o["status"] == g[t + "status"][b] == 0
+            assert _eq(o["K"], g[t + "K"][b]) and _eq(o["sd"], g[t + "sd"][b]) and _eq(o["u"], g[t + "sdd"][b])
+
+
 def test_forward_retry_rule(golden):
     """reachability_algorithm.py:315-343: x is lowered by max(x - 1e-8, 0.999 x) up to 10 times when the forward LP is
     infeasible.  (a) start velocities that are admissible only through the 1e-5 slack: an excess of 3e-8 is absorbed
