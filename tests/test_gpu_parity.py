@@ -303,6 +303,48 @@ def test_joint_torque_constraint(ta, golden):
             path, g["grid"])
 
 
+def test_cartesian_velocity_norm(ta, orc, golden):
+    """CartesianVelocityNorm (C++-only in the reference: cpp/src/toppra/constraint/cartesian_velocity_norm.cpp:23-54,
+    SURVEY §8 f4): one row (0, v^T S v, -limit) per gridpoint.  Constant and varying limit; checked against the oracle
+    fed with the same rows (bit-exact) and through the constraint's meaning: v^T S v * sd^2 <= limit everywhere."""
+    g = golden("cfg1_seed9")
+    path = ta.SplineInterpolator(g["ss"], g["way"])
+    grid = g["grid"]
+    rng = np.random.RandomState(3)
+    J0 = rng.randn(6, 7)
+    S = np.diag([1.0, 1.0, 1.0, 0.1, 0.1, 0.1])
+
+    def frame_velocity(q, qd):
+        return (J0 + 0.2 * np.sin(q)[None, :]).dot(qd)
+
+    def varying(s):
+        return S * (1.0 + 0.5 * s), 0.6 + 0.4 * np.cos(3.0 * s) ** 2
+
+    qs, qds = path(grid), path(grid, 1)
+    for cart in (ta.constraint.CartesianVelocityNorm(frame_velocity, S, 0.8, dof=7),
+                 ta.constraint.CartesianVelocityNorm(frame_velocity, velocity_limit=varying)):
+        a, b, c, F, gg, ub, xb = cart.compute_constraint_params(path, grid)
+        lim = np.array([0.8 if cart.identical else varying(s)[1] for s in grid])
+        Ss = [S if cart.identical else varying(s)[0] for s in grid]
+        want_b = np.array([frame_velocity(q, qd).dot(Si.dot(frame_velocity(q, qd))) for q, qd, Si in zip(qs, qds, Ss)])
+        assert not a.any() and not c.any() and ub is None and xb is None and _eq(b[:, 0], want_b)
+        assert (F.shape, gg.shape) == (((1, 1), (1,)) if cart.identical else ((len(grid), 1, 1), (len(grid), 1)))
+        cons = [ta.constraint.JointVelocityConstraint(g["vlim"]), cart]
+        inst = ta.algorithm.TOPPRA(cons, path, gridpoints=grid, solver_wrapper="seidel")
+        assert inst.solver_wrapper.nC == 3
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        rows = np.stack((np.zeros_like(b), b, -lim[:, None]), axis=1)
+        o = orc.solve_rows(rows, np.stack((g["xbound"][:, 0], np.minimum(g["xbound"][:, 1], 1e8)), axis=1), grid, 0, 0)
+        assert o["status"] == 0 and inst.problem_data.return_code == ta.algorithm.ParameterizationReturnCode.Ok
+        assert _eq(K, o["K"]) and _eq(sd, o["sd"]) and _eq(sdd, o["u"])
+        used = want_b * sd ** 2 / lim
+        assert used.max() <= 1 + 1e-9 and used.max() > 0.999   # never exceeded, active somewhere
+    with pytest.raises(ValueError):
+        ta.constraint.CartesianVelocityNorm(frame_velocity, np.eye(5), 1.0)
+    with pytest.raises(ValueError):
+        ta.constraint.CartesianVelocityNorm(frame_velocity, S, -1.0)
+
+
 def test_errors(ta, golden):
     g = golden("cfg1_seed9")
     path = ta.SplineInterpolator(g["ss"], g["way"])
