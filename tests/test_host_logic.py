@@ -11,8 +11,9 @@ def test_public_names_match_reference_surface():
     for name in ("SplineInterpolator", "ParametrizeSpline", "ParametrizeConstAccel", "constraint", "algorithm",
                  "solverwrapper", "BatchTOPPRA", "BatchSplineInterpolator"):
         assert hasattr(ta, name)
-    for name in ("JointVelocityConstraint", "JointAccelerationConstraint", "SecondOrderConstraint", "LinearConstraint",
-                 "ConstraintType", "DiscretizationType", "canlinear_colloc_to_interpolate"):
+    for name in ("JointVelocityConstraint", "JointVelocityConstraintVarying", "JointAccelerationConstraint",
+                 "SecondOrderConstraint", "JointTorqueConstraint", "RobustLinearConstraint", "LinearConstraint", "Constraint",
+                 "ConstraintType", "DiscretizationType", "canlinear_colloc_to_interpolate"):  # reference constraint/__init__.py
         assert hasattr(constraint, name)
     for name in ("TOPPRA", "ParameterizationData", "ParameterizationReturnCode", "ParameterizationAlgorithm"):
         assert hasattr(ta.algorithm, name)
@@ -78,3 +79,73 @@ def test_parse_bc_errors():
             engine.parse_bc("periodic", 1, 2, "cpu")
         with pytest.raises(ValueError):
             engine.parse_bc("bogus", 1, 2, "cpu")
+
+
+class _FakePath(object):
+    """Stand-in for a path object: polynomial q(s) evaluated in numpy (the constraints' host side only calls it)."""
+    dof = 3
+
+    def __call__(self, s, order=0):
+        s = np.asarray(s, dtype=float)
+        base = np.stack((np.sin(s), s ** 2, 1.0 - s), axis=-1)
+        d1 = np.stack((np.cos(s), 2 * s, -np.ones_like(s)), axis=-1)
+        d2 = np.stack((-np.sin(s), 2 * np.ones_like(s), np.zeros_like(s)), axis=-1)
+        return (base, d1, d2)[order]
+
+
+def test_joint_torque_constraint_host_tuple(golden):
+    """JointTorqueConstraint (reference joint_torque.py:77-116): the host 7-tuple follows the reference's formulas for any
+    path object; the golden case compares numbers produced by the reference class itself (tests/test_gpu_parity.py does
+    it with the device path evaluation, bit for bit)."""
+    inv_dyn = lambda q, qd, qdd: 2.0 * qdd + 0.3 * qd * qd + np.sin(q)  # noqa: E731
+    tl = np.array([[-3.0, 4.0], [-5.0, 6.0], [-7.0, 8.0]])
+    fric = np.array([0.1, 0.2, 0.3])
+    grid = np.linspace(0, 1, 9)
+    path = _FakePath()
+    c0 = constraint.JointTorqueConstraint(inv_dyn, tl, fric)
+    assert c0.identical and c0.get_dof() == 3 and c0.discretization_type == constraint.DiscretizationType.Collocation
+    a, b, c, F, g, ub, xb = c0.compute_constraint_params(path, grid)
+    q, qd, qdd = path(grid), path(grid, 1), path(grid, 2)
+    np.testing.assert_array_equal(c, np.sin(q) + fric * np.sign(qd))
+    np.testing.assert_allclose(a, 2.0 * qd, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(b, 2.0 * qdd + 0.3 * qd * qd, rtol=0, atol=1e-15)
+    assert ub is None and xb is None
+    np.testing.assert_array_equal(F, np.vstack((np.eye(3), -np.eye(3))))
+    np.testing.assert_array_equal(g, np.r_[tl[:, 1], -tl[:, 0]])
+    c1 = constraint.JointTorqueConstraint(inv_dyn, tl, fric, discretization_scheme=1)
+    a1, b1, cc1, F1, g1, _, _ = c1.compute_constraint_params(path, grid)
+    ra, rb, rc, rF, rg, _, _ = constraint.canlinear_colloc_to_interpolate(a, b, c, F, g, None, None, grid, identical=True)
+    for x, y in ((a1, ra), (b1, rb), (cc1, rc), (F1, rF), (g1, rg)):
+        np.testing.assert_array_equal(x, y)
+    assert F1.shape == (12, 6) and a1.shape == (9, 6)
+    with pytest.raises(ValueError):
+        constraint.JointTorqueConstraint(inv_dyn, np.ones((4, 2)), np.zeros(4)).compute_constraint_params(path, grid)
+    assert "Torque limit" in repr(c0)
+
+
+def test_cartesian_velocity_norm_host_tuple():
+    """CartesianVelocityNorm (cpp/src/toppra/constraint/cartesian_velocity_norm.cpp:23-54): a = c = 0, b = v^T S v,
+    F = [1], g = [limit]; constant limit -> identical F, varying limit -> per-gridpoint F and g; argument checks of
+    CartesianVelocityNorm::check (.cpp:16-21)."""
+    path = _FakePath()
+    grid = np.linspace(0, 1, 7)
+    J = np.arange(18.0).reshape(6, 3) / 10.0
+    vel = lambda q, qd: J.dot(qd) * (1.0 + q[0])  # noqa: E731
+    S = np.diag([1.0, 2.0, 3.0, 0.5, 0.5, 0.5])
+    c0 = constraint.CartesianVelocityNorm(vel, S, 2.5, dof=3)
+    a, b, c, F, g, ub, xb = c0.compute_constraint_params(path, grid)
+    want = np.array([vel(q, qd).dot(S.dot(vel(q, qd))) for q, qd in zip(path(grid), path(grid, 1))])
+    np.testing.assert_array_equal(b[:, 0], want)
+    assert c0.identical and not a.any() and not c.any() and F.shape == (1, 1) and g.tolist() == [2.5] and ub is None and xb is None
+    c1 = constraint.CartesianVelocityNorm(vel, velocity_limit=lambda s: (S * (1 + s), 1.0 + s))
+    a, b, c, F, g, _, _ = c1.compute_constraint_params(path, grid)
+    assert not c1.identical and F.shape == (7, 1, 1) and g.shape == (7, 1)
+    np.testing.assert_array_equal(g[:, 0], 1.0 + grid)
+    np.testing.assert_allclose(b[:, 0], want * (1 + grid), rtol=1e-15)
+    for bad in (dict(S=np.eye(5), limit=1.0), dict(S=S, limit=-1.0), dict()):
+        with pytest.raises(ValueError):
+            constraint.CartesianVelocityNorm(vel, **bad)
+    with pytest.raises(ValueError):
+        constraint.CartesianVelocityNorm(vel, S, 1.0, dof=4).compute_constraint_params(path, grid)
+    with pytest.raises(ValueError):
+        constraint.CartesianVelocityNorm(lambda q, qd: qd, S, 1.0).compute_constraint_params(path, grid)
