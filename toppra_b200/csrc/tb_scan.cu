@@ -151,8 +151,10 @@ __device__ __forceinline__ void box_row(const int m, const double low0, const do
 // per lane.  The box rows ride on lanes whose own row does not take part in this re-solve (rows at or after k,
 // padding lanes); only if fewer than four such lanes exist they fall back to an extra item slot.
 // PERM = a valid warm-start pair permutes the row order (pyx:252-264); PERM = false is the natural order, for which
-// position == row index and the bookkeeping folds away (the common case in the TOPP-RA passes: the previous
-// optimum usually sits on a box bound, which makes the pair invalid).
+// position == row index and the bookkeeping folds away (in the TOPP-RA backward pass: always for the min-x LP, whose
+// optimum sits on the x box bound and invalidates the pair; the max-x LP usually has a valid pair).
+// SKIP = the caller is the backward pass of the scan: the shortcuts A / B below may name the first row to re-solve on
+// (bit-identical, modelled and checked in oracle/shortcut_model.c); everything else walks the rows in order.
 template <int RPL, bool PERM, bool SKIP>
 __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL], const int nC,
@@ -187,7 +189,7 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
         // one exact re-solve on m then reproduces the reference's state bit for bit, and the exact walk goes on
         // from there.  Rows before m that bound ua from below (or not at all) must hold at the final point with
         // a margin, and every upper row must pick the low end of its line (the exact path's v1d test).  Any doubt
-        // -> ordinary walk.  Validated against the sequential solver on 2.5e7 LPs (incl. near-duplicate rows).
+        // -> ordinary walk.  Scalar model + checker: oracle/shortcut_model.c, tests/test_shortcut_model.py.
         const double sg = (v0 > 0) ? 1.0 : -1.0;
         const double x = p1, u0m = sg * p0;
         double uo[RPL], bxc[RPL];
