@@ -154,7 +154,7 @@ __device__ __forceinline__ void box_row(const int m, const double low0, const do
 // position == row index and the bookkeeping folds away (in the TOPP-RA backward pass: always for the min-x LP, whose
 // optimum sits on the x box bound and invalidates the pair; the max-x LP usually has a valid pair).
 // SKIP = the caller is the backward pass of the scan: the shortcuts A / B below may name the first row to re-solve on
-// (bit-identical, modelled and checked in oracle/shortcut_model.c); everything else walks the rows in order.
+// (bit-identical; a scalar model of the rules is checked by tests/test_shortcut_model.py); all else walks the rows in order.
 template <int RPL, bool PERM, bool SKIP>
 __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, const double (&a)[RPL],
                                           const double (&b)[RPL], const double (&c)[RPL], const int nC,
@@ -189,7 +189,7 @@ __device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, cons
         // one exact re-solve on m then reproduces the reference's state bit for bit, and the exact walk goes on
         // from there.  Rows before m that bound ua from below (or not at all) must hold at the final point with
         // a margin, and every upper row must pick the low end of its line (the exact path's v1d test).  Any doubt
-        // -> ordinary walk.  Scalar model + checker: oracle/shortcut_model.c, tests/test_shortcut_model.py.
+        // -> ordinary walk.  A scalar model of these rules is checked by tests/test_shortcut_model.py.
         const double sg = (v0 > 0) ? 1.0 : -1.0;
         const double x = p1, u0m = sg * p0;
         double uo[RPL], bxc[RPL];
