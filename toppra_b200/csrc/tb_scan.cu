@@ -449,11 +449,13 @@ __device__ __forceinline__ void set_xnext_rows(const int lane, const double delt
   c[0] = xr ? (first ? xn_min : -xn_max) : c[0];
 }
 
-template <int RPL, int WARPS, int MINB, bool FAST>
+// CFLAGS >= 0: the scan-mode bits of `flags` (backward-only, forward-only, TOPPRAsd rules) are this compile-time
+// constant (the argument is ignored), so the unused passes and rules and their bookkeeping fold away; -1: run time.
+template <int RPL, int WARPS, int MINB, bool FAST, int CFLAGS = -1>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
             const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
-            const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags,
+            const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags_arg,
             double *__restrict__ Kout, double *__restrict__ sdout, double *__restrict__ uout,
             int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -477,6 +479,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   auto rec_path = [&]() { return static_cast<const double *>(sptr[0]); };
   auto gp = [&]() { return static_cast<const double *>(sptr[1]); };
   auto Kp = [&]() { return static_cast<double *>(const_cast<void *>(sptr[2])); };
+  const int flags = (CFLAGS >= 0) ? CFLAGS : flags_arg;
   const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
   const bool forward_only = (flags & 16) != 0;  // K and status come from an earlier TB_SCAN_BACKWARD_ONLY launch
   constexpr bool fast_lower = FAST;             // opt-in shortcut for the min-x LP (TB_SCAN_FAST_LOWER, not bit-identical)
@@ -808,6 +811,18 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
   const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
   auto kern = (RPL == 1 && dense) ? (fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true> : scan_kernel<RPL, SCAN_WARPS, MINB, false>)
                                   : (fast ? scan_kernel<RPL, SCAN_WARPS, 1, true> : scan_kernel<RPL, SCAN_WARPS, 1, false>);
+  if (RPL == 1 && dense) {
+    // the three launch kinds of the batched solver get their own instantiation: full scan, backward only, forward only
+    const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
+    if (mode == 0)
+      kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, 0> : scan_kernel<RPL, SCAN_WARPS, MINB, false, 0>;
+    else if (mode == TB_SCAN_BACKWARD_ONLY)
+      kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, TB_SCAN_BACKWARD_ONLY>
+                  : scan_kernel<RPL, SCAN_WARPS, MINB, false, TB_SCAN_BACKWARD_ONLY>;
+    else if (mode == TB_SCAN_FORWARD_ONLY)
+      kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, TB_SCAN_FORWARD_ONLY>
+                  : scan_kernel<RPL, SCAN_WARPS, MINB, false, TB_SCAN_FORWARD_ONLY>;
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
