@@ -1,36 +1,50 @@
-"""Base class and enums of path-parametrization constraints — same surface as the reference
-`toppra/constraint/constraint.py:10-103`."""
-from enum import Enum
-import logging
-
-logger = logging.getLogger(__name__)
+"""Enums and the abstract base of path-parameterisation constraints.  Public surface (names, getters, repr layout)
+follows the reference's `toppra/constraint/constraint.py:10-103`; the code is this package's own."""
+import enum
 
 
-class ConstraintType(Enum):
-    """Type of path parametrization constraint."""
+class ConstraintType(enum.Enum):
+    """How a constraint presents itself to the solver: rows (CanonicalLinear) or second-order cones (CanonicalConic)."""
 
     Unknown = -1
     CanonicalLinear = 0
     CanonicalConic = 1
 
 
-class DiscretizationType(Enum):
-    """Discretization scheme: Collocation (0) or Interpolation (1)."""
+class DiscretizationType(enum.Enum):
+    """Collocation: the constraint holds at the gridpoints; Interpolation: also at the next gridpoint expressed in
+    the current stage's variables (linear_constraint.py:84-192)."""
 
     Collocation = 0
     Interpolation = 1
 
 
-class Constraint(object):
-    """The base constraint class."""
+_BY_VALUE = {t.value: t for t in DiscretizationType}
 
-    def __repr__(self):
-        string = self.__class__.__name__ + "(\n"
-        string += "    Type: {:}".format(self.constraint_type) + "\n"
-        string += "    Discretization Scheme: {:}".format(self.discretization_type) + "\n"
-        string += self._format_string
-        string += ")"
-        return string
+
+class Constraint(object):
+    """Abstract constraint.  Subclasses set `constraint_type`, `discretization_type`, `dof`, `n_extra_vars` and
+    `_format_string` (the body of the repr) and implement `compute_constraint_params`."""
+
+    def compute_constraint_params(self, path, gridpoints, *args, **kwargs):
+        raise NotImplementedError
+
+    def set_discretization_type(self, discretization_type):
+        """Accepts the enum or its integer value (0 = Collocation, 1 = Interpolation)."""
+        if isinstance(discretization_type, DiscretizationType):
+            self.discretization_type = discretization_type
+            return
+        for value, scheme in _BY_VALUE.items():
+            if discretization_type == value:
+                self.discretization_type = scheme
+                return
+        raise NotImplementedError("Discretization type: {:} not implemented!".format(discretization_type))
+
+    def get_discretization_type(self):
+        return self.discretization_type
+
+    def get_constraint_type(self):
+        return self.constraint_type
 
     def get_dof(self):
         return self.dof
@@ -38,24 +52,8 @@ class Constraint(object):
     def get_no_extra_vars(self):
         return self.n_extra_vars
 
-    def get_constraint_type(self):
-        return self.constraint_type
-
-    def get_discretization_type(self):
-        return self.discretization_type
-
-    def set_discretization_type(self, discretization_type):
-        """Discretization type: Collocation or Interpolation (int 0/1 or the enum)."""
-        if discretization_type == 0:
-            self.discretization_type = DiscretizationType.Collocation
-        elif discretization_type == 1:
-            self.discretization_type = DiscretizationType.Interpolation
-        elif (discretization_type == DiscretizationType.Collocation
-              or discretization_type == DiscretizationType.Interpolation):
-            self.discretization_type = discretization_type
-        else:
-            raise NotImplementedError("Discretization type: {:} not implemented!".format(discretization_type))
-
-    def compute_constraint_params(self, path, gridpoints, *args, **kwargs):
-        """Evaluate parameters of the constraint."""
-        raise NotImplementedError
+    def __repr__(self):
+        head = ["{:}(".format(type(self).__name__),
+                "    Type: {:}".format(self.constraint_type),
+                "    Discretization Scheme: {:}".format(self.discretization_type)]
+        return "\n".join(head) + "\n" + self._format_string + ")"

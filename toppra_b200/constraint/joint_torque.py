@@ -34,24 +34,27 @@ class JointTorqueConstraint(LinearConstraint):
         self._delegate = None
 
     def compute_constraint_params(self, path, gridpoints):
-        if path.dof != self.get_dof():
-            raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
-                self.get_dof(), path.dof))
-        gridpoints = np.asarray(gridpoints)
-        v_zero = np.zeros(path.dof)
-        p, ps, pss = path(gridpoints), path(gridpoints, 1), path(gridpoints, 2)
-        dof = path.dof
-        F = np.vstack((np.eye(dof), -np.eye(dof)))
+        """Host 7-tuple (a, b, c, F, g, None, None) with the reference's shapes: collocation (G, dof) / F (2 dof, dof),
+        interpolation (G, 2 dof) / F (4 dof, 2 dof); F and g are the same for every gridpoint (`identical`)."""
+        n = self.get_dof()
+        if path.dof != n:
+            raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(n, path.dof))
+        grid = np.asarray(gridpoints)
+        q, dq, ddq = (path(grid, order) for order in (0, 1, 2))
+        rest = np.zeros(n)
+        tau = self.inv_dyn
+        gravity = np.array([tau(qi, rest, rest) for qi in q])                    # w(q, 0, 0)
+        a = np.array([tau(qi, rest, dqi) for qi, dqi in zip(q, dq)]) - gravity      # A(q) p'
+        b = np.array([tau(qi, dqi, ddqi) for qi, dqi, ddqi in zip(q, dq, ddq)]) - gravity
+        c = gravity
+        for j in range(n):  # dry friction D(qd) = fs * sign(qd), joint by joint like the reference (:106-108)
+            c[:, j] += self.fs_coef[j] * np.sign(dq[:, j])
+        F = np.concatenate((np.identity(n), -np.identity(n)))
         g = np.concatenate((self.tau_lim[:, 1], -self.tau_lim[:, 0]))
-        c = np.array([self.inv_dyn(p_, v_zero, v_zero) for p_ in p])
-        a = np.array([self.inv_dyn(p_, v_zero, ps_) for p_, ps_ in zip(p, ps)]) - c
-        b = np.array([self.inv_dyn(p_, ps_, pss_) for p_, ps_, pss_ in zip(p, ps, pss)]) - c
-        for i in range(dof):  # dry friction, :106-108
-            c[:, i] += self.fs_coef[i] * np.sign(ps[:, i])
+        if self.discretization_type == DiscretizationType.Interpolation:
+            return canlinear_colloc_to_interpolate(a, b, c, F, g, None, None, grid, identical=True)
         if self.discretization_type == DiscretizationType.Collocation:
             return a, b, c, F, g, None, None
-        if self.discretization_type == DiscretizationType.Interpolation:
-            return canlinear_colloc_to_interpolate(a, b, c, F, g, None, None, gridpoints, identical=True)
         raise NotImplementedError("Other form of discretization not supported!")
 
     # ---- device protocol: the rows are those of SecondOrderConstraint.joint_torque_constraint -------------

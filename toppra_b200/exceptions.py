@@ -1,9 +1,13 @@
-"""Exceptions — same names as the reference `toppra/exceptions.py`."""
+"""Error types of toppra_b200; the names are those of the reference's `toppra/exceptions.py`."""
 
 
 class ToppraError(Exception):
-    """A generic error class."""
+    pass
 
 
 class BadInputVelocities(ToppraError):
-    """Raised when given input velocity is invalid."""
+    """sd_start / sd_end cannot be used (negative values, reachability_algorithm.py:272-276)."""
+
+
+class SolverNotFound(ToppraError):
+    """The requested solver wrapper is not provided by this build."""
