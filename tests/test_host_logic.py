@@ -149,3 +149,55 @@ def test_cartesian_velocity_norm_host_tuple():
         constraint.CartesianVelocityNorm(vel, S, 1.0, dof=4).compute_constraint_params(path, grid)
     with pytest.raises(ValueError):
         constraint.CartesianVelocityNorm(lambda q, qd: qd, S, 1.0).compute_constraint_params(path, grid)
+
+
+class _FakeTrajectory(object):
+    def __init__(self, path, gridpoints, sd_vec):
+        self.args = (path, gridpoints, sd_vec)
+        self.path_interval = np.array([0.0, 2.5])
+
+
+def test_parameterization_algorithm_base():
+    """ParameterizationAlgorithm (reference algorithm.py:65-194): gridpoint validation, problem_data, parametrizer choice,
+    compute_trajectory returning None unless the solve reports Ok."""
+    from toppra_b200.algorithm import ParameterizationAlgorithm, ParameterizationData
+
+    class Path(_FakePath):
+        path_interval = np.array([0.0, 1.0])
+
+    class Algo(ParameterizationAlgorithm):
+        code = ParameterizationReturnCode.Ok
+
+        def compute_parameterization(self, sd_start, sd_end, return_data=False):
+            self._problem_data.return_code = self.code
+            self._problem_data.sd_vec = np.full(len(self.gridpoints), sd_start + 1.0)
+
+    grid = [0.0, 0.25, 0.5, 1.0]
+    alg = Algo(["c"], Path(), grid, parametrizer="ParametrizeConstAccel")
+    assert alg.constraints == ["c"] and alg._N == 3 and alg.parametrizer is ta.ParametrizeConstAccel
+    assert isinstance(alg.problem_data, ParameterizationData)
+    assert alg.problem_data.return_code == ParameterizationReturnCode.ErrUnknown
+    assert alg.problem_data.sd_vec is None and alg.problem_data.K is None and alg.problem_data.X is None
+    np.testing.assert_array_equal(alg.gridpoints, grid)
+    np.testing.assert_array_equal(alg.problem_data.gridpoints, grid)
+    assert repr(alg.problem_data).startswith("ParameterizationData(return_code:=<ParameterizationReturnCode.ErrUnknown")
+    assert repr(alg.problem_data).endswith("N=4)")
+    assert Algo([], Path(), grid).parametrizer is ta.ParametrizeSpline
+    assert Algo([], Path(), grid, parametrizer="ParametrizeSpline").parametrizer is ta.ParametrizeSpline
+    with pytest.raises(NotImplementedError):
+        ParameterizationAlgorithm([], Path(), grid).compute_parameterization(0, 0)
+    for bad in ([0.0, 0.5, 0.9], [0.1, 0.5, 1.0]):                 # ends must be the path interval
+        with pytest.raises(ValueError, match="Invalid manually supplied gridpoints"):
+            Algo([], Path(), bad)
+    for bad in ([0.0, 0.5, 0.5, 1.0], [0.0, 0.7, 0.3, 1.0]):       # strictly increasing
+        with pytest.raises(ValueError, match="Bad input gridpoints"):
+            Algo([], Path(), bad)
+    alg.parametrizer = _FakeTrajectory
+    traj = alg.compute_trajectory(0.5, 0.0)
+    assert isinstance(traj, _FakeTrajectory) and traj.args[0] is alg.path
+    np.testing.assert_array_equal(traj.args[1], grid)
+    np.testing.assert_array_equal(traj.args[2], np.full(4, 1.5))
+    alg.code = ParameterizationReturnCode.FailUncontrollable
+    assert alg.compute_trajectory() is None
+    assert STATUS_CODES == tuple(ParameterizationReturnCode) and repr(STATUS_CODES[3]) == str(STATUS_CODES[3])
+    assert repr(STATUS_CODES[0]) == "<ParameterizationReturnCode.Ok: 'Ok: Successful parametrization'>"

@@ -1,9 +1,9 @@
-"""Abstract parametrization algorithm and result types — same surface as the reference
-`toppra/algorithm/algorithm.py:27-194`."""
+"""Result types and the abstract base of the parameterisation algorithms.  Names, fields, enum values, messages and
+error behaviour follow the reference's `toppra/algorithm/algorithm.py:27-194` (they are the drop-in surface); the code
+is this package's own."""
 import enum
 import logging
 import time
-from typing import Optional
 
 import numpy as np
 
@@ -13,23 +13,9 @@ from .. import parametrizer as tparam
 logger = logging.getLogger(__name__)
 
 
-class ParameterizationData(object):
-    """Internal data and output (reference algorithm.py:27-46)."""
-
-    def __init__(self, *arg, **kwargs) -> None:
-        self.return_code: ParameterizationReturnCode = ParameterizationReturnCode.ErrUnknown
-        self.gridpoints: Optional[np.ndarray] = None
-        self.sd_vec: Optional[np.ndarray] = None
-        self.sdd_vec: Optional[np.ndarray] = None
-        self.K: Optional[np.ndarray] = None
-        self.X: Optional[np.ndarray] = None
-
-    def __repr__(self):
-        return "ParameterizationData(return_code:={}, N={:d})".format(self.return_code, self.gridpoints.shape[0])
-
-
 class ParameterizationReturnCode(enum.Enum):
-    """Return codes from a parametrization attempt (reference algorithm.py:49-62)."""
+    """Outcome of a parameterisation attempt; the member ORDER is the kernels' status integer
+    (include/toppra_b200.h TB_STATUS_*), the values are the reference's messages (algorithm.py:49-56)."""
 
     Ok = "Ok: Successful parametrization"
     ErrUnknown = "Error: Unknown issue"
@@ -37,44 +23,55 @@ class ParameterizationReturnCode(enum.Enum):
     FailUncontrollable = "Error: Instance is not controllable"
     ErrForwardPassFail = "Error: Forward pass fail. Numerical errors occured"
 
+    def __str__(self):  # like the reference, str() shows the full <Class.Member: 'message'> form (:58-62)
+        return enum.Enum.__repr__(self)
+
     def __repr__(self):
-        return super(ParameterizationReturnCode, self).__repr__()
-
-    def __str__(self):
-        return super(ParameterizationReturnCode, self).__repr__()
+        return enum.Enum.__repr__(self)
 
 
-#: kernel status integer (include/toppra_b200.h TB_STATUS_*) -> enum member
-STATUS_CODES = (
-    ParameterizationReturnCode.Ok,
-    ParameterizationReturnCode.ErrUnknown,
-    ParameterizationReturnCode.ErrShortPath,
-    ParameterizationReturnCode.FailUncontrollable,
-    ParameterizationReturnCode.ErrForwardPassFail,
-)
+#: kernel status integer -> enum member
+STATUS_CODES = tuple(ParameterizationReturnCode)
+
+
+class ParameterizationData(object):
+    """What a solve leaves behind (algorithm.py:27-46): `return_code`, `gridpoints`, `sd_vec`, `sdd_vec`, the
+    controllable sets `K` and the feasible sets `X`; everything but the code starts as None."""
+
+    _ARRAYS = ("gridpoints", "sd_vec", "sdd_vec", "K", "X")
+
+    def __init__(self, *arg, **kwargs):
+        self.return_code = ParameterizationReturnCode.ErrUnknown
+        for name in self._ARRAYS:
+            setattr(self, name, None)
+
+    def __repr__(self):
+        return "ParameterizationData(return_code:={}, N={:d})".format(self.return_code, self.gridpoints.shape[0])
 
 
 class ParameterizationAlgorithm(object):
-    """Base parametrization algorithm class (reference algorithm.py:65-194)."""
+    """Base of TOPPRA / TOPPRAsd (algorithm.py:65-194): holds constraints, path, gridpoints and the output parametrizer
+    class; subclasses implement `compute_parameterization`."""
 
-    def __init__(self, constraint_list, path, gridpoints=None, parametrizer=None,
-                 gridpt_max_err_threshold: float = 1e-3, gridpt_min_nb_points: int = 100):
+    def __init__(self, constraint_list, path, gridpoints=None, parametrizer=None, gridpt_max_err_threshold=1e-3,
+                 gridpt_min_nb_points=100):
         self.constraints = constraint_list
         self.path = path
-        self._problem_data = ParameterizationData()
-        if gridpoints is None:
-            gridpoints = interpolator.propose_gridpoints(
-                path, max_err_threshold=gridpt_max_err_threshold, min_nb_points=gridpt_min_nb_points)
+        if gridpoints is None:  # data-dependent grid, interpolator.py:49-122
+            gridpoints = interpolator.propose_gridpoints(path, max_err_threshold=gridpt_max_err_threshold,
+                                                         min_nb_points=gridpt_min_nb_points)
             logger.info("No gridpoint specified. Automatically choose a gridpoint with %d points", len(gridpoints))
-        if path.path_interval[0] != gridpoints[0] or path.path_interval[1] != gridpoints[-1]:
+        first, last = path.path_interval[0], path.path_interval[1]
+        if first != gridpoints[0] or last != gridpoints[-1]:
             raise ValueError("Invalid manually supplied gridpoints.")
-        self.gridpoints = np.array(gridpoints)
-        self._problem_data.gridpoints = np.array(gridpoints)
-        self._N = len(gridpoints) - 1
-        for i in range(self._N):
-            if gridpoints[i + 1] <= gridpoints[i]:
-                logger.fatal("Input gridpoints are not monotonically increasing.")
-                raise ValueError("Bad input gridpoints.")
+        grid = np.array(gridpoints)
+        if bool(np.any(grid[1:] <= grid[:-1])):
+            logger.fatal("Input gridpoints are not monotonically increasing.")
+            raise ValueError("Bad input gridpoints.")
+        self.gridpoints = grid
+        self._N = grid.shape[0] - 1
+        self._problem_data = ParameterizationData()
+        self._problem_data.gridpoints = grid.copy()
         if parametrizer is None or parametrizer == "ParametrizeSpline":
             self.parametrizer = tparam.ParametrizeSpline
         elif parametrizer == "ParametrizeConstAccel":
@@ -89,22 +86,24 @@ class ParameterizationAlgorithm(object):
         self._constraints = value
 
     @property
-    def problem_data(self) -> ParameterizationData:
-        """Data obtained when solving the path parametrization."""
+    def problem_data(self):
+        """The `ParameterizationData` of the last solve."""
         return self._problem_data
 
-    def compute_parameterization(self, sd_start: float, sd_end: float, return_data: bool = False):
+    def compute_parameterization(self, sd_start, sd_end, return_data=False):
         raise NotImplementedError
 
-    def compute_trajectory(self, sd_start: float = 0, sd_end: float = 0):
-        """Compute the resulting joint trajectory (None if the path cannot be parameterised)."""
-        t0 = time.time()
+    def compute_trajectory(self, sd_start=0, sd_end=0):
+        """Solve, then hand path + gridpoints + velocities to the parametrizer; None when the solve did not succeed
+        (algorithm.py:163-194)."""
+        began = time.time()
         self.compute_parameterization(sd_start, sd_end)
-        if self.problem_data.return_code != ParameterizationReturnCode.Ok:
-            logger.warning("Fail to parametrize path. Return code: %s", self.problem_data.return_code)
+        data = self.problem_data
+        if data.return_code != ParameterizationReturnCode.Ok:
+            logger.warning("Fail to parametrize path. Return code: %s", data.return_code)
             return None
-        outputtraj = self.parametrizer(self.path, self.problem_data.gridpoints, self.problem_data.sd_vec)
+        trajectory = self.parametrizer(self.path, data.gridpoints, data.sd_vec)
         logger.info("Successfully parametrize path. Duration: %.3f, previously %.3f)",
-                    outputtraj.path_interval[1], self.path.path_interval[1])
-        logger.info("Finish parametrization in %.3f secs", time.time() - t0)
-        return outputtraj
+                    trajectory.path_interval[1], self.path.path_interval[1])
+        logger.info("Finish parametrization in %.3f secs", time.time() - began)
+        return trajectory
