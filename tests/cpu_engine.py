@@ -1,0 +1,285 @@
+"""TEST DOUBLE (tests/ only, never imported by the product): a CPU stand-in of `toppra_b200.engine` built on the oracle.
+
+`install(monkeypatch)` replaces the tensor-level kernel wrappers of toppra_b200/engine.py by functions that do the same
+job on CPU torch tensors through the plain-C restatement (oracle/), and lets `_lib.require_cuda()` pass.  With it the
+whole Python host side — SplineInterpolator, constraints, record assembly, solver wrapper, TOPPRA, BatchTOPPRA chunking,
+parametrizers, error paths — runs under `-m "not gpu"` (tests/test_host_pipeline_cpu.py replays the GPU parity tests
+through it).  It checks HOST LOGIC only: the numbers are the oracle's, the CUDA kernels are checked by the `-m gpu`
+tests.  The product has no CPU path; this module lives outside the package on purpose."""
+import ctypes
+
+import numpy as np
+import torch
+
+from oracle import oracle as orc
+
+VAR_MIN, VAR_MAX = -1e8, 1e8
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _per_path(arr, b):
+    """arr is shared ([n]) or per path ([B, n])."""
+    return arr if arr.ndim == 1 else arr[b]
+
+
+# ---- K0 ---------------------------------------------------------------------------------------------------------------
+def spline_fit(ss, wp, bc=((0, None), (0, None))):
+    ssn, wpn = _np(ss), _np(wp)
+    B, n, dof = wpn.shape
+    (k0, v0), (k1, v1) = bc
+    out = np.empty((B, 4, n - 1, dof))
+    for b in range(B):
+        vb0 = np.zeros(dof) if v0 is None else _np(v0)[b]
+        vb1 = np.zeros(dof) if v1 is None else _np(v1)[b]
+        out[b] = orc.cubic_spline_fit(_per_path(ssn, b), wpn[b], ((k0, vb0), (k1, vb1)))
+    return torch.from_numpy(out)
+
+
+def ppoly_eval(ppoly, breaks, s, order):
+    pp, br, sn = _np(ppoly), _np(breaks), _np(s)
+    B = pp.shape[0]
+    return torch.from_numpy(np.stack([orc.ppoly_eval(pp[b], _per_path(br, b), _per_path(sn, b), order) for b in range(B)]))
+
+
+# ---- records ------------------------------------------------------------------------------------------------------------
+def record_doubles(R):
+    return (3 * int(R) + 2 + 1) & ~1
+
+
+def alloc_records(B, G, R, device):
+    W = record_doubles(R)
+    return torch.full((B, G, W), float("nan"), dtype=torch.float64), W
+
+
+def init_bounds(records, R):
+    records[:, :, 3 * R] = VAR_MIN
+    records[:, :, 3 * R + 1] = VAR_MAX
+    records[:, :, 3 * R + 2:] = 0.0
+
+
+def _write_xbound(rec, R_total, xb, mode):
+    lo, hi = rec[:, :, 3 * R_total], rec[:, :, 3 * R_total + 1]
+    xb = torch.from_numpy(np.ascontiguousarray(xb))
+    if mode == 1:
+        lo.copy_(torch.clamp(xb[..., 0], min=VAR_MIN))
+        hi.copy_(torch.clamp(xb[..., 1], max=VAR_MAX))
+    elif mode == 2:
+        lo.copy_(xb[..., 0])
+        hi.copy_(xb[..., 1])
+    elif mode == 3:
+        lo.copy_(torch.maximum(lo, xb[..., 0]))
+        hi.copy_(torch.minimum(hi, xb[..., 1]))
+
+
+def coeff_velacc(ppoly, breaks, grid, vlim, alim, interp, records, R_total, row0=0, write_xbound=1):
+    pp, br, gr = _np(ppoly), _np(breaks), _np(grid)
+    vl, al = _np(vlim), _np(alim)
+    B, _, nseg, dof = pp.shape
+    G = gr.shape[-1]
+    rec = records
+    xb = np.empty((B, G, 2))
+    L = orc.lib()
+    for b in range(B):
+        g = np.ascontiguousarray(_per_path(gr, b))
+        qs = orc.ppoly_eval(pp[b], _per_path(br, b), g, 1)
+        qss = orc.ppoly_eval(pp[b], _per_path(br, b), g, 2)
+        if vl is None:
+            xb[b, :, 0], xb[b, :, 1] = VAR_MIN, VAR_MAX
+        else:
+            xb[b] = orc.velocity_xbound(qs, vl if vl.ndim == 2 else vl[b])
+        if al is not None:
+            R = (4 if interp else 2) * dof
+            a, bb, c = (np.zeros((G, R)) for _ in range(3))
+            alb = np.ascontiguousarray(al if al.ndim == 2 else al[b])
+            dp = ctypes.POINTER(ctypes.c_double)
+            L.orc_accel_rows(np.ascontiguousarray(qs).ctypes.data_as(dp), np.ascontiguousarray(qss).ctypes.data_as(dp),
+                             alb.ctypes.data_as(dp), g.ctypes.data_as(dp), G, dof, 1 if interp else 0, R, 0,
+                             a.ctypes.data_as(dp), bb.ctypes.data_as(dp), c.ctypes.data_as(dp))
+            rec[b, :, row0:row0 + R] = torch.from_numpy(a)
+            rec[b, :, R_total + row0:R_total + row0 + R] = torch.from_numpy(bb)
+            rec[b, :, 2 * R_total + row0:2 * R_total + row0 + R] = torch.from_numpy(c)
+    if write_xbound:
+        _write_xbound(rec, R_total, xb, write_xbound)
+        rec[:, :, 3 * R_total + 2:] = 0.0
+
+
+def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
+    """Port of rows_canlinear_kernel (csrc/tb_coeff.cu): same term order (sum over q = 0..m-1, left to right)."""
+    an, bn, cn, Fn, gn, gr = _np(a), _np(b), _np(c), _np(F), _np(g), _np(grid)
+    B, G, m = an.shape
+    k = Fn.shape[0] if F_mode == 0 else (Fn.shape[2] if F_mode == 1 else 2 * m)
+    nrows = 2 * k if interp else k
+    N = G - 1
+    out = np.zeros((B, G, 3, nrows))
+    for p in range(B):
+        gp = _per_path(gr, p)
+        for gi in range(G):
+            for r in range(nrows):
+                second = r >= k
+                j = r - k if second else r
+                src = gi + 1 if (second and gi < N) else gi
+                lift = second and gi < N
+                two_delta = 2 * (gp[gi + 1] - gp[gi]) if lift else 0.0
+                av = an[p, src] + two_delta * bn[p, src] if lift else an[p, src]
+                if F_mode >= 2:
+                    col, sgn = (j, 1.0) if j < m else (j - m, -1.0)
+                    ta, tb, tc = sgn * av[col], sgn * bn[p, src, col], sgn * cn[p, src, col]
+                    gv = gn[p, j] if F_mode == 3 else gn[j]
+                else:
+                    Fr = Fn[j] if F_mode == 0 else Fn[p, src, j]
+                    ta = tb = tc = 0.0
+                    for q in range(m):
+                        ta = ta + Fr[q] * av[q]
+                        tb = tb + Fr[q] * bn[p, src, q]
+                        tc = tc + Fr[q] * cn[p, src, q]
+                    gv = gn[j] if F_mode == 0 else gn[p, src, j]
+                out[p, gi, :, r] = (ta, tb, tc - gv)
+    t = torch.from_numpy(out)
+    records[:, :, row0:row0 + nrows] = t[:, :, 0]
+    records[:, :, R_total + row0:R_total + row0 + nrows] = t[:, :, 1]
+    records[:, :, 2 * R_total + row0:2 * R_total + row0 + nrows] = t[:, :, 2]
+    return nrows
+
+
+def xbound_varying(*args, **kwargs):
+    raise NotImplementedError("cpu_engine test double: JointVelocityConstraintVarying is covered by the -m gpu tests only")
+
+
+# ---- K2 -----------------------------------------------------------------------------------------------------------------
+def _rows_of(records, R, b):
+    rec = _np(records[b])
+    rows = np.stack((rec[:, 0:R], rec[:, R:2 * R], rec[:, 2 * R:3 * R]), axis=1)
+    return rows, rec[:, 3 * R:3 * R + 2]
+
+
+def _scalar(t, b, default=0.0):
+    return default if t is None else float(_np(t).reshape(-1)[b])
+
+
+def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False,
+         sd_forward=None, forward_from=None, fast_lower=False):
+    if sd_forward is not None:
+        raise NotImplementedError("cpu_engine test double: TOPPRAsd passes are covered by the -m gpu tests only")
+    B, G, W = records.shape
+    gr = _np(grid)
+    K = np.zeros((B, G, 2))
+    sd = np.full((B, G), np.nan)
+    u = np.full((B, max(G - 1, 0)), np.nan)
+    status = np.zeros(B, dtype=np.int32)
+    fail = np.full(B, -1, dtype=np.int32)
+    cnt = np.zeros((B, 4), dtype=np.int32)
+    for b in range(B):
+        rows, xb = _rows_of(records, R, b)
+        w = orc.Wrapper(_per_path(gr, b), rows, xb)
+        s0, s1 = _scalar(sd_start, b), _scalar(sd_end, b)
+        if backward_only:
+            K[b] = w.compute_controllable_sets(s1, _scalar(sd_end_hi, b, s1))
+            bad = np.isnan(K[b]).any(axis=1)
+            if bad.any():
+                status[b], fail[b] = 3, int(np.nonzero(bad)[0].max())
+            continue
+        o = w.compute_parameterization(s0, s1)
+        K[b], status[b] = o["K"], o["status"]
+        if o["status"] == 3:
+            bad = np.isnan(K[b]).any(axis=1)
+            fail[b] = int(np.nonzero(bad)[0].max()) if bad.any() else 0
+        else:
+            sd[b], u[b] = o["sd"], o["u"]
+            if o["status"] != 0:
+                fail[b] = int(np.nonzero(np.isnan(o["sd"]))[0].min()) - 1
+        c = w.counters() if hasattr(w, "counters") else None
+        if c is not None:
+            cnt[b, :3] = [c.get("lp2d", 0), c.get("lp1d", 0), c.get("resolves", 0)]
+            cnt[b, 3] = o.get("retries", 0)
+    out = dict(K=torch.from_numpy(K), status=torch.from_numpy(status), fail_stage=torch.from_numpy(fail),
+               sd=None if backward_only else torch.from_numpy(sd), u=None if backward_only else torch.from_numpy(u))
+    if counters:
+        out["counters"] = torch.from_numpy(cnt)
+    return out
+
+
+def scan_robust(records, R, conic_row0, conic_rows, ellipsoid, grid, sd_start=None, sd_end=None, backward_only=False,
+                counters=False, feasible_sets=False):
+    if backward_only or feasible_sets:
+        raise NotImplementedError("cpu_engine test double: robust controllable / feasible sets are gpu-only here")
+    B, G, W = records.shape
+    gr = _np(grid)
+    K, sd, u = np.zeros((B, G, 2)), np.full((B, G), np.nan), np.full((B, max(G - 1, 1)), np.nan)
+    status = np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        rows, xb = _rows_of(records, R, b)
+        o = orc.solve_rows_robust(rows, xb, _per_path(gr, b), conic_row0, conic_rows, ellipsoid, _scalar(sd_start, b),
+                                  _scalar(sd_end, b))
+        K[b], status[b] = o["K"], o["status"]
+        if o["status"] == 0:
+            sd[b], u[b, :G - 1] = o["sd"], o["u"]
+    out = dict(K=torch.from_numpy(K), sd=torch.from_numpy(sd), u=torch.from_numpy(u[:, :max(G - 1, 0)]),
+               status=torch.from_numpy(status), fail_stage=torch.full((B,), -1, dtype=torch.int32))
+    if counters:
+        out["counters"] = torch.zeros((B, 4), dtype=torch.int32)
+    return out
+
+
+def feasible_sets(records, R, grid):
+    B, G, W = records.shape
+    gr = _np(grid)
+    X = np.empty((B, G, 2))
+    for b in range(B):
+        rows, xb = _rows_of(records, R, b)
+        X[b] = orc.Wrapper(_per_path(gr, b), rows, xb).compute_feasible_sets()
+    return torch.from_numpy(X)
+
+
+# ---- LP shims -------------------------------------------------------------------------------------------------------------
+def lp2d_batch(v, a, b, c, low, high, active_c=None):
+    v, low, high = (np.asarray(_np(t) if isinstance(t, torch.Tensor) else t, dtype=np.float64) for t in (v, low, high))
+    B = v.shape[0]
+    a, b, c = (np.asarray(_np(t) if isinstance(t, torch.Tensor) else t, dtype=np.float64).reshape(B, -1) for t in (a, b, c))
+    act = np.zeros((B, 2), dtype=np.int64) if active_c is None else np.asarray(active_c, dtype=np.int64).reshape(B, 2)
+    res, val, var, out_act = np.zeros(B, np.int32), np.zeros(B), np.zeros((B, 2)), np.zeros((B, 2), np.int32)
+    for i in range(B):
+        res[i], val[i], var[i], out_act[i] = orc.lp2d(v[i], a[i], b[i], c[i], low[i], high[i], act[i])
+    return res, val, var, out_act
+
+
+def lp1d_batch(v, a, b, low, high):
+    v, low, high = (np.asarray(_np(t) if isinstance(t, torch.Tensor) else t, dtype=np.float64) for t in (v, low, high))
+    B = v.shape[0]
+    a, b = (np.asarray(_np(t) if isinstance(t, torch.Tensor) else t, dtype=np.float64).reshape(B, -1) for t in (a, b))
+    res, val, var, act = np.zeros(B, np.int32), np.zeros(B), np.zeros(B), np.zeros(B, np.int32)
+    for i in range(B):
+        res[i], val[i], var[i], act[i] = orc.lp1d(v[i], a[i], b[i], float(low[i]), float(high[i]))
+    return res, val, var, act
+
+
+def time_grid(*args, **kwargs):
+    raise NotImplementedError("cpu_engine test double: ParametrizeConstAccel is covered by the -m gpu tests only")
+
+
+constaccel_eval = time_grid
+
+
+class _NoStream(object):
+    def synchronize(self):
+        pass
+
+
+PATCHED = ("spline_fit", "ppoly_eval", "record_doubles", "alloc_records", "init_bounds", "coeff_velacc",
+           "rows_canlinear", "xbound_varying", "scan", "scan_robust", "feasible_sets", "lp2d_batch", "lp1d_batch",
+           "time_grid", "constaccel_eval")
+
+
+def install(monkeypatch):
+    """Route toppra_b200 through this module for the duration of one test."""
+    import toppra_b200  # noqa: F401
+    from toppra_b200 import _lib, engine
+    monkeypatch.setattr(_lib, "require_cuda", lambda: torch)
+    monkeypatch.setattr(engine, "default_device", lambda device=None: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
+    for name in PATCHED:
+        assert hasattr(engine, name), name
+        monkeypatch.setattr(engine, name, globals()[name])
+    return toppra_b200

@@ -492,7 +492,7 @@ def test_forward_retry_rule(ta, golden):
         rec = np.zeros((1, G, W))
         rec[0, :, :3 * R] = rows.reshape(G, 3 * R)
         rec[0, :, 3 * R:3 * R + 2] = xb
-        dev = torch.device("cuda")
+        dev = ta.engine.default_device()
         out = ta.engine.scan(ta.engine.as_device(rec, dev), R, ta.engine.as_device(grid, dev),
                              ta.engine.as_device(np.array([float(r[t + "sd_start"])]), dev), None)
         assert int(out["status"][0]) == int(r[t + "status"]), i

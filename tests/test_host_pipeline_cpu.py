@@ -1,0 +1,70 @@
+"""CPU (-m "not gpu"): the Python host side end to end, with the kernels replaced by the oracle-backed test double
+tests/cpu_engine.py.  The GPU parity tests of tests/test_gpu_parity.py are replayed unchanged (same assertions against
+the reference's golden vectors), so a regression in the host logic — constraint classes, record assembly, solver
+wrapper, algorithms, chunking, error behaviour — shows up without a GPU.  What the numbers prove here is only that the
+host code feeds and reads the engine correctly; the CUDA kernels themselves are checked by the -m gpu run."""
+import inspect
+
+import numpy as np
+import pytest
+
+import cpu_engine
+import test_gpu_parity as T
+import test_gpu_scale as S
+from conftest import BATCH_CASES  # noqa: F401
+
+REPLAYED = [
+    "test_lp1d_kats", "test_lp2d_kats", "test_lp2d_random100_one_launch", "test_lp2d_many_rows_vs_oracle",
+    "test_spline_fit_all_boundary_conditions", "test_spline_interpolator_api", "test_constraint_params_contract",
+    "test_batch_cases_bit_exact", "test_single_path_api_bit_exact", "test_cpp_2dof_collocation_golden",
+    "test_stagewise_plugin_interface", "test_robustness_suite", "test_torque_second_order",
+    "test_joint_torque_constraint", "test_cartesian_velocity_norm", "test_errors",
+    "test_custom_linear_constraint_generic_rows", "test_forward_retry_rule",
+]
+
+
+def _expand(fn):
+    """[(id, kwargs)] from the function's own @pytest.mark.parametrize marks."""
+    cases = [("", {})]
+    for mark in getattr(fn, "pytestmark", []):
+        if mark.name != "parametrize":
+            continue
+        names = [n.strip() for n in mark.args[0].split(",")]
+        new = []
+        for ident, kw in cases:
+            for values in mark.args[1]:
+                values = values if len(names) > 1 else (values,)
+                new.append((ident + "-" + "-".join(str(v) for v in values), dict(kw, **dict(zip(names, values)))))
+        cases = new
+    return cases
+
+
+CASES = [(T, name, ident, kw) for name in REPLAYED for ident, kw in _expand(getattr(T, name))]
+CASES += [(S, "test_shapes_rows_per_lane_and_tiny_grids", ident, kw)
+          for ident, kw in _expand(S.test_shapes_rows_per_lane_and_tiny_grids)]
+
+
+@pytest.mark.parametrize("module,name,ident,kw", CASES, ids=[n + i for _, n, i, _ in CASES])
+def test_replay_gpu_parity_test_on_cpu(module, name, ident, kw, monkeypatch, golden):
+    ta = cpu_engine.install(monkeypatch)
+    fn = getattr(module, name)
+    from oracle import oracle
+    avail = dict(ta=ta, golden=golden, orc=oracle, **kw)
+    fn(**{p: avail[p] for p in inspect.signature(fn).parameters})
+
+
+def test_chunked_batch_equals_single_launch_on_cpu(monkeypatch):
+    """BatchTOPPRA chunking (max_record_bytes) and BatchSplineInterpolator.chunk: host logic only."""
+    ta = cpu_engine.install(monkeypatch)
+    from problems import make_batch
+    B, G = 12, 40
+    ss, way, vlim, alim = make_batch(B, 1000)
+    grid = np.linspace(0, 1, G)
+    path = ta.BatchSplineInterpolator(ss, way)
+    cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)]
+    one = ta.BatchTOPPRA(cons, path, grid).compute_parameterization(0.0, 0.0).to_host()
+    W = ta.engine.record_doubles(28)
+    many = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=5 * G * W * 8).compute_parameterization(0.0, 0.0).to_host()
+    for k in ("K", "sd", "sdd", "status"):
+        assert np.array_equal(one[k], many[k]), k
+    assert not one["status"].any()
