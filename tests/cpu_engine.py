@@ -144,8 +144,17 @@ def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
     return nrows
 
 
-def xbound_varying(*args, **kwargs):
-    raise NotImplementedError("cpu_engine test double: JointVelocityConstraintVarying is covered by the -m gpu tests only")
+def xbound_varying(ppoly, breaks, grid, vlim_grid, records, R_total, write_xbound):
+    """_create_velocity_constraint_varying (_CythonUtils.pyx:61-101): the constant-limit formula with vlim_grid[i]."""
+    pp, br, gr, vg = _np(ppoly), _np(breaks), _np(grid), _np(vlim_grid)
+    B, G = pp.shape[0], gr.shape[-1]
+    xb = np.empty((B, G, 2))
+    for b in range(B):
+        qs = orc.ppoly_eval(pp[b], _per_path(br, b), _per_path(gr, b), 1)
+        lim = vg if vg.ndim == 3 else vg[b]
+        for i in range(G):
+            xb[b, i] = orc.velocity_xbound(qs[i:i + 1], lim[i])[0]
+    _write_xbound(records, R_total, xb, write_xbound)
 
 
 # ---- K2 -----------------------------------------------------------------------------------------------------------------
@@ -161,9 +170,9 @@ def _scalar(t, b, default=0.0):
 
 def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False,
          sd_forward=None, forward_from=None, fast_lower=False):
-    if sd_forward is not None:
-        raise NotImplementedError("cpu_engine test double: TOPPRAsd passes are covered by the -m gpu tests only")
     B, G, W = records.shape
+    if sd_forward is not None:
+        return _scan_sd(records, R, grid, sd_start, sd_end, sd_forward == "slow")
     gr = _np(grid)
     K = np.zeros((B, G, 2))
     sd = np.full((B, G), np.nan)
@@ -199,6 +208,40 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     if counters:
         out["counters"] = torch.from_numpy(cnt)
     return out
+
+
+def _scan_sd(records, R, grid, sd_start, sd_end, slow):
+    """TOPPRAsd passes (desired_duration_algorithm.py:42-121, 207-234): controllable sets, then a forward pass with no
+    retry rule and x_next = clip(x + 2 delta u - 1e-5, K[i+1]); fastest: g = (-2 delta, -1), slowest: g = (2 delta, 1).
+    The `sd` output holds x = sd^2 like the kernel's TB_SCAN_SD_FORWARD mode."""
+    B, G, W = records.shape
+    gr = _np(grid)
+    K = np.zeros((B, G, 2))
+    xs, us = np.full((B, G), np.nan), np.full((B, G - 1), np.nan)
+    status, fail = np.zeros(B, dtype=np.int32), np.full(B, -1, dtype=np.int32)
+    for b in range(B):
+        rows, xb = _rows_of(records, R, b)
+        g = _per_path(gr, b)
+        w = orc.Wrapper(g, rows, xb)
+        s0, s1 = _scalar(sd_start, b), _scalar(sd_end, b)
+        K[b] = w.compute_controllable_sets(s1, s1)
+        x0 = s0 * s0
+        if np.isnan(K[b]).any() or x0 + 1e-5 < K[b, 0, 0] or K[b, 0, 1] + 1e-5 < x0:
+            status[b] = 3
+            fail[b] = int(np.nonzero(np.isnan(K[b]).any(axis=1))[0].max()) if np.isnan(K[b]).any() else 0
+            continue
+        xs[b, 0] = x0
+        for i in range(G - 1):
+            delta = g[i + 1] - g[i]
+            obj = [2 * delta, 1.0] if slow else [-2 * delta, -1.0]
+            u = w.solve_stagewise_optim(i, None, obj, xs[b, i], xs[b, i], K[b, i + 1, 0], K[b, i + 1, 1])[0]
+            if np.isnan(u):
+                status[b], fail[b] = 1, i
+                break
+            us[b, i] = u
+            xs[b, i + 1] = min(K[b, i + 1, 1], max(K[b, i + 1, 0], xs[b, i] + 2 * delta * u - 1e-5))
+    return dict(K=torch.from_numpy(K), sd=torch.from_numpy(xs), u=torch.from_numpy(us), status=torch.from_numpy(status),
+                fail_stage=torch.from_numpy(fail))
 
 
 def scan_robust(records, R, conic_row0, conic_rows, ellipsoid, grid, sd_start=None, sd_end=None, backward_only=False,
@@ -255,11 +298,41 @@ def lp1d_batch(v, a, b, low, high):
     return res, val, var, act
 
 
-def time_grid(*args, **kwargs):
-    raise NotImplementedError("cpu_engine test double: ParametrizeConstAccel is covered by the -m gpu tests only")
+# ---- K3: ParametrizeConstAccel (parametrizer.py:52-129) -------------------------------------------------------------------
+def time_grid(sd, grid):
+    sdn, gr = _np(sd), _np(grid)
+    B, G = sdn.shape
+    t, us = np.zeros((B, G)), np.zeros((B, G - 1))
+    for b in range(B):
+        s, v = _per_path(gr, b), sdn[b]
+        x = v ** 2
+        for i in range(G - 1):
+            us[b, i] = 0.5 * (x[i + 1] - x[i]) / (s[i + 1] - s[i])
+            t[b, i + 1] = t[b, i] + 2 * (s[i + 1] - s[i]) / (v[i] + v[i + 1])
+    return torch.from_numpy(t), torch.from_numpy(us)
 
 
-constaccel_eval = time_grid
+def constaccel_eval(ppoly, breaks, grid, sd, t_grid, us, ts, order):
+    pp, br, gr, sdn, tg, un, tn = (_np(t) for t in (ppoly, breaks, grid, sd, t_grid, us, ts))
+    B, dof = pp.shape[0], pp.shape[3]
+    M = tn.shape[-1]
+    out = np.zeros((B, M, dof))
+    for b in range(B):
+        s, t = _per_path(gr, b), _per_path(tn, b)
+        idx = np.searchsorted(tg[b], t, side="right") - 1
+        idx = np.where(idx == un.shape[1], idx - 1, idx)
+        dt = t - tg[b][idx]
+        u = un[b][idx]
+        v = sdn[b][idx] + dt * u
+        pos = s[idx] + dt * sdn[b][idx] + 0.5 * dt ** 2 * u
+        ev = lambda k: orc.ppoly_eval(pp[b], _per_path(br, b), pos, k)  # noqa: E731
+        if order == 0:
+            out[b] = ev(0)
+        elif order == 1:
+            out[b] = ev(1) * v[:, None]
+        else:
+            out[b] = ev(2) * v[:, None] ** 2 + ev(1) * u[:, None]
+    return torch.from_numpy(out)
 
 
 class _NoStream(object):

@@ -19,7 +19,8 @@ REPLAYED = [
     "test_batch_cases_bit_exact", "test_single_path_api_bit_exact", "test_cpp_2dof_collocation_golden",
     "test_stagewise_plugin_interface", "test_robustness_suite", "test_torque_second_order",
     "test_joint_torque_constraint", "test_cartesian_velocity_norm", "test_errors",
-    "test_custom_linear_constraint_generic_rows", "test_forward_retry_rule",
+    "test_custom_linear_constraint_generic_rows", "test_forward_retry_rule", "test_const_accel_parametrizer_on_device",
+    "test_toppra_sd_and_reachable_sets", "test_velocity_constraint_varying", "test_cfg1_example_and_trajectory",
 ]
 
 
