@@ -11,6 +11,7 @@ import pytest
 import cpu_engine
 import test_gpu_parity as T
 import test_gpu_scale as S
+import test_zz_ppoly_in as P
 from conftest import BATCH_CASES  # noqa: F401
 
 REPLAYED = [
@@ -41,6 +42,7 @@ def _expand(fn):
 
 
 CASES = [(T, name, ident, kw) for name in REPLAYED for ident, kw in _expand(getattr(T, name))]
+CASES += [(P, name, "", {}) for name in ("test_ppoly_path_single", "test_scalar_and_low_degree_pieces", "test_batch_from_ppoly")]
 CASES += [(S, "test_shapes_rows_per_lane_and_tiny_grids", ident, kw)
           for ident, kw in _expand(S.test_shapes_rows_per_lane_and_tiny_grids)]
 

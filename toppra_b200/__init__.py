@@ -7,7 +7,8 @@ CPU fallback (importing works anywhere, computing needs the GPU and the built li
 import logging
 
 from . import constants, exceptions
-from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, SplineInterpolator, propose_gridpoints)
+from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, PPolyPath, SplineInterpolator,
+                           propose_gridpoints)
 from .parametrizer import BatchParametrizeConstAccel, ParametrizeConstAccel, ParametrizeSpline
 from . import constraint
 from . import solverwrapper
@@ -18,6 +19,6 @@ __version__ = "0.1.0"
 
 logging.getLogger("toppra_b200").addHandler(logging.NullHandler())
 
-__all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "SplineInterpolator", "propose_gridpoints",
+__all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "PPolyPath", "SplineInterpolator", "propose_gridpoints",
            "ParametrizeConstAccel", "ParametrizeSpline", "BatchParametrizeConstAccel", "constraint", "solverwrapper", "algorithm", "BatchResult",
            "BatchTOPPRA", "solve_batch", "constants", "exceptions"]

@@ -136,6 +136,38 @@ class BatchSplineInterpolator(object):
         bc = engine.parse_bc(bc_type, self.B, self._dof, self.device)
         self.d_ppoly = engine.spline_fit(self.d_ss, self.d_wp, bc)
 
+    @classmethod
+    def from_ppoly(cls, breaks, coeffs, device=None):
+        """Paths given directly as piecewise cubics in scipy's PPoly layout ("PPoly in"): any path type
+        that has such a form (CubicSpline / PPoly objects, cubic Hermite paths, polynomials up to degree 3) goes to the
+        kernels without a fit.
+
+        breaks: (nseg + 1,) shared or (B, nseg + 1), strictly increasing.
+        coeffs: (B, k, nseg, dof) with k <= 4, highest power first, local power basis
+                sum_j c[j] (s - breaks[i]) ** (k - 1 - j) like `scipy.interpolate.PPoly.c`; k < 4 is zero-padded."""
+        torch = engine.torch_mod()
+        self = object.__new__(cls)
+        self.device = engine.default_device(device if device is not None else
+                                            (coeffs.device if isinstance(coeffs, torch.Tensor) else None))
+        c = engine.as_device(coeffs, self.device)
+        if c.dim() != 4 or not 1 <= c.shape[1] <= 4:
+            raise ValueError("coeffs must have shape (B, k, nseg, dof) with k <= 4 (cubic pieces at most)")
+        if c.shape[1] < 4:
+            pad = torch.zeros((c.shape[0], 4 - c.shape[1]) + tuple(c.shape[2:]), dtype=c.dtype, device=c.device)
+            c = torch.cat((pad, c), dim=1).contiguous()
+        self.B, _, nseg, self._dof = c.shape
+        self.n = nseg + 1
+        self.d_ss = engine.as_device(breaks, self.device)
+        if self.d_ss.shape[-1] != self.n or self.d_ss.dim() not in (1, 2) or (self.d_ss.dim() == 2 and
+                                                                           self.d_ss.shape[0] != self.B):
+            raise ValueError("breaks must have shape (nseg + 1,) or (B, nseg + 1)")
+        if bool((self.d_ss[..., 1:] <= self.d_ss[..., :-1]).any()):
+            raise ValueError("breaks must be strictly increasing")
+        self.bc_type = None
+        self.d_ppoly = c
+        self.d_wp = engine.ppoly_eval(self.d_ppoly, self.d_ss, self.d_ss, 0)  # positions at the breaks
+        return self
+
     @property
     def dof(self):
         return self._dof
@@ -247,4 +279,51 @@ class SplineInterpolator(AbstractGeometricPath):
     def as_batch(self):
         if self._batch is None:
             raise ValueError("single-waypoint paths cannot be parameterised")
+        return self._batch
+
+
+class PPolyPath(AbstractGeometricPath):
+    """A single path given as a piecewise cubic in scipy's PPoly layout ("PPoly in"): the way other path
+    types of the reference (scipy CubicSpline / PPoly objects, the cubic-Hermite `SimplePath`, polynomials up to degree
+    3) reach the GPU solver.  `ppoly`: an object with `.c` (k, nseg[, dof]) and `.x` (nseg + 1,), or the pair (c, x)."""
+
+    def __init__(self, ppoly, x=None, device=None):
+        super(PPolyPath, self).__init__()
+        c = np.asarray(ppoly.c if x is None else ppoly, dtype=np.float64)
+        self._x = np.asarray(ppoly.x if x is None else x, dtype=np.float64)
+        self._scalar_dof = c.ndim == 2
+        if self._scalar_dof:
+            c = c[:, :, None]
+        if c.ndim != 3:
+            raise ValueError("PPoly coefficients must have shape (k, nseg) or (k, nseg, dof)")
+        self._batch = BatchSplineInterpolator.from_ppoly(self._x, c[None], device=device)
+
+    def __call__(self, path_positions, order=0):
+        if order not in (0, 1, 2):
+            raise ValueError(f"Invalid order {order}")
+        scalar_in = np.ndim(path_positions) == 0
+        s = np.atleast_1d(np.asarray(path_positions, dtype=np.float64))
+        out = self._batch(s.reshape(-1), order)[0].reshape(s.shape + (self._batch.dof,))
+        if self._scalar_dof:
+            out = out[..., 0]
+        return out[0] if scalar_in else out
+
+    @property
+    def dof(self):
+        return self._batch.dof
+
+    @property
+    def path_interval(self):
+        return np.array([self._x[0], self._x[-1]])
+
+    @property
+    def duration(self):
+        return self._x[-1] - self._x[0]
+
+    @property
+    def waypoints(self):
+        """Breakpoints and the positions there."""
+        return self._x, self(self._x)
+
+    def as_batch(self):
         return self._batch
