@@ -349,9 +349,39 @@ def joint_torque_case():
     print("joint torque: statuses", data["s0_status"], data["s1_status"])
 
 
+def other_paths_case():
+    """SimplePath (toppra/simplepath.py, cubic Hermite via scipy BPoly) and PolynomialPath (interpolator.py:584-686):
+    evaluations at sample positions and the vel+acc parameterisation along them (SURVEY §8 f4 'other path types')."""
+    codes = list(algo.ParameterizationReturnCode)
+    rng = np.random.RandomState(77)
+    data = {}
+    x = np.array([0.0, 0.3, 0.9, 1.4, 2.0, 2.5])
+    y = rng.randn(6, 3)
+    yd = rng.randn(6, 3) * 0.5
+    vlim = np.vstack((-np.ones(3) * 3, np.ones(3) * 3)).T
+    alim = np.vstack((-np.ones(3) * 8, np.ones(3) * 8)).T
+    s = np.linspace(0, 2.5, 41)
+    grid = np.linspace(0, 2.5, 80)
+    for tag, path in (("sp_auto", ta.SimplePath(x, y)), ("sp_yd", ta.SimplePath(x, y, yd)),
+                      ("poly", ta.PolynomialPath([[1, 2, 3], [-2, 3, 4, 5], [0.5, -1.0]], s_start=0.0, s_end=2.5))):
+        for order in (0, 1, 2):
+            data["%s_q%d" % (tag, order)] = np.asarray(path(s, order), dtype=float)
+        inst = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)], path,
+                           gridpoints=grid, solver_wrapper="seidel")
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        data[tag + "_K"], data[tag + "_sd"], data[tag + "_sdd"] = K, sd, sdd
+        data[tag + "_status"] = codes.index(inst.problem_data.return_code)
+    data.update(x=x, y=y, yd=yd, vlim=vlim, alim=alim, s=s, grid=grid)
+    np.savez_compressed(os.path.join(HERE, "other_paths.npz"), **data)
+    print("other paths: statuses", [int(data[t + "_status"]) for t in ("sp_auto", "sp_yd", "poly")])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "joint_torque":
         joint_torque_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "other_paths":
+        other_paths_case()
     else:
         main()
         joint_torque_case()
+        other_paths_case()

@@ -42,7 +42,8 @@ def _expand(fn):
 
 
 CASES = [(T, name, ident, kw) for name in REPLAYED for ident, kw in _expand(getattr(T, name))]
-CASES += [(P, name, "", {}) for name in ("test_ppoly_path_single", "test_scalar_and_low_degree_pieces", "test_batch_from_ppoly")]
+CASES += [(P, name, "", {}) for name in ("test_ppoly_path_single", "test_scalar_and_low_degree_pieces", "test_batch_from_ppoly",
+                                             "test_simple_path_and_polynomial_path")]
 CASES += [(S, "test_shapes_rows_per_lane_and_tiny_grids", ident, kw)
           for ident, kw in _expand(S.test_shapes_rows_per_lane_and_tiny_grids)]
 

@@ -81,3 +81,46 @@ def test_batch_from_ppoly(ta, golden):
             ta.BatchSplineInterpolator.from_ppoly(g["ss"], bad)
     with pytest.raises(ValueError):
         ta.BatchSplineInterpolator.from_ppoly(np.linspace(0, 1, 4), g["c"])
+
+
+def test_simple_path_and_polynomial_path(ta, golden):
+    """SimplePath (reference simplepath.py, cubic Hermite) and PolynomialPath (interpolator.py:584-686, degree <= 3 here)
+    against the reference's own evaluations and parameterisations.  The reference evaluates Bernstein / power-series
+    forms, this package local cubics: tolerance 1e-12 on values (they are O(1..30)), 1e-9 relative on the solution."""
+    g = golden("other_paths")
+    vel, acc = ta.constraint.JointVelocityConstraint(g["vlim"]), ta.constraint.JointAccelerationConstraint(g["alim"])
+    paths = (("sp_auto", ta.SimplePath(g["x"], g["y"])), ("sp_yd", ta.SimplePath(g["x"], g["y"], g["yd"])),
+             ("poly", ta.PolynomialPath([[1, 2, 3], [-2, 3, 4, 5], [0.5, -1.0]], s_start=0.0, s_end=2.5)))
+    for tag, path in paths:
+        assert path.dof == 3 and path.path_interval.tolist() == [0.0, 2.5] and path.duration == 2.5
+        for order in (0, 1, 2):
+            np.testing.assert_allclose(path(g["s"], order), g["%s_q%d" % (tag, order)], rtol=1e-12, atol=1e-12)
+        inst = ta.algorithm.TOPPRA([vel, acc], path, gridpoints=g["grid"], solver_wrapper="seidel")
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        assert inst.problem_data.return_code == ta.algorithm.STATUS_CODES[int(g[tag + "_status"])]
+        np.testing.assert_allclose(K, g[tag + "_K"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(sd, g[tag + "_sd"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(sdd, g[tag + "_sdd"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(paths[0][1].waypoints, g["y"])
+    # the reference's own unit tests (tests/tests/interpolators/test_simple_path.py, test_poly_interpolator.py)
+    f = ta.SimplePath([0, 1, 2], np.array([0, 1, 1]))
+    assert f(1) == 1.0 and f(2) == 1.0 and f(np.linspace(0, 2, 200), 1).shape == (200, 1)
+    np.testing.assert_allclose(f(1, 1), 0.5)
+    np.testing.assert_allclose([f(0, 1), f(2, 1)], 0, atol=1e-15)
+    fd = ta.SimplePath([0, 1, 2], np.array([0, 1, 1]), np.array([0, 2, 0]))
+    np.testing.assert_allclose([fd(0, 1)[0], fd(1, 1)[0], fd(2, 1)[0]], [0, 2.0, 0], atol=1e-15)
+    fm = ta.SimplePath([0, 1, 2], np.array([[0, 0], [1, 2], [1, 2]]))
+    assert fm(0.5).shape == (2,) and fm.dof == 2
+    np.testing.assert_allclose(fm(1), [1, 2])
+    pi = ta.PolynomialPath([1, 2, 3], s_start=0, s_end=2)
+    assert pi.dof == 1
+    np.testing.assert_allclose(pi.eval([0, 0.5, 1]), [1, 2.75, 6])
+    np.testing.assert_allclose(pi.evald([0, 0.5, 1]), [2, 5, 8])
+    np.testing.assert_allclose(pi.evaldd([0, 0.5, 1]), [6, 6, 6])
+    np.testing.assert_allclose(pi.path_interval, [0, 2])
+    p2 = ta.PolynomialPath([[1, 2, 3], [-2, 3, 4, 5]])
+    np.testing.assert_allclose(p2.eval([0, 0.5, 1]), [[1, -2], [2.75, 1.125], [6, 10]])
+    np.testing.assert_allclose(p2.evald([0, 0.5, 1]), [[2, 3], [5, 10.75], [8, 26]])
+    np.testing.assert_allclose(p2.evaldd([0, 0.5, 1]), [[6, 8], [6, 23], [6, 38]])
+    with pytest.raises(NotImplementedError):
+        ta.PolynomialPath([1, 0, 0, 0, 1])

@@ -7,8 +7,9 @@ CPU fallback (importing works anywhere, computing needs the GPU and the built li
 import logging
 
 from . import constants, exceptions
-from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, PPolyPath, SplineInterpolator,
-                           propose_gridpoints)
+from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, PolynomialPath, PPolyPath,
+                           SplineInterpolator, propose_gridpoints)
+from .simplepath import SimplePath
 from .parametrizer import BatchParametrizeConstAccel, ParametrizeConstAccel, ParametrizeSpline
 from . import constraint
 from . import solverwrapper
@@ -19,6 +20,6 @@ __version__ = "0.1.0"
 
 logging.getLogger("toppra_b200").addHandler(logging.NullHandler())
 
-__all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "PPolyPath", "SplineInterpolator", "propose_gridpoints",
+__all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "PPolyPath", "PolynomialPath", "SimplePath", "SplineInterpolator", "propose_gridpoints",
            "ParametrizeConstAccel", "ParametrizeSpline", "BatchParametrizeConstAccel", "constraint", "solverwrapper", "algorithm", "BatchResult",
            "BatchTOPPRA", "solve_batch", "constants", "exceptions"]

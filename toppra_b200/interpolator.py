@@ -327,3 +327,35 @@ class PPolyPath(AbstractGeometricPath):
 
     def as_batch(self):
         return self._batch
+
+
+class PolynomialPath(PPolyPath):
+    """Polynomial path coeff[i, 0] + coeff[i, 1] s + coeff[i, 2] s^2 + ... on [s_start, s_end] — public surface of the
+    reference's `PolynomialPath` (interpolator.py:584-686).  The GPU evaluation works on cubic pieces, so the degree is
+    limited to 3 here; the polynomial is re-expanded about `s_start` (one piece), values agree with the reference to
+    rounding."""
+
+    def __init__(self, coeff, s_start=0.0, s_end=1.0, device=None):
+        self.s_start, self.s_end = s_start, s_end
+        scalar = np.isscalar(coeff[0])
+        polys = [np.polynomial.Polynomial(np.asarray(c, dtype=np.float64)) for c in ([coeff] if scalar else coeff)]
+        if max(p.degree() for p in polys) > 3:
+            raise NotImplementedError("toppra_b200: PolynomialPath is limited to degree 3 (cubic pieces on the GPU)")
+        self.coeff = np.array(coeff).reshape(1, -1) if scalar else coeff
+        self.poly = polys
+        cols = []
+        for p in polys:  # Taylor coefficients at s_start, highest power first
+            cols.append([p.deriv(3)(s_start) / 6.0, p.deriv(2)(s_start) / 2.0, p.deriv(1)(s_start), p(s_start)])
+        c = np.array(cols, dtype=np.float64).T[:, None, :]          # (4, 1 piece, dof)
+        super(PolynomialPath, self).__init__(c, np.array([s_start, s_end], dtype=np.float64), device=device)
+        self._flat = scalar
+
+    def __call__(self, path_positions, order=0):
+        out = super(PolynomialPath, self).__call__(path_positions, order)
+        if self._flat:  # 1-D coefficient list: the reference returns flattened arrays (interpolator.py:666-686)
+            return np.atleast_1d(out[..., 0])
+        return out
+
+    @property
+    def duration(self):
+        return self.s_end - self.s_start
