@@ -11,6 +11,7 @@ import pytest
 import cpu_engine
 import test_gpu_parity as T
 import test_gpu_scale as S
+import test_robust as Rb
 import test_zz_ppoly_in as P
 from conftest import BATCH_CASES  # noqa: F401
 
@@ -44,6 +45,8 @@ def _expand(fn):
 CASES = [(T, name, ident, kw) for name in REPLAYED for ident, kw in _expand(getattr(T, name))]
 CASES += [(P, name, "", {}) for name in ("test_ppoly_path_single", "test_scalar_and_low_degree_pieces", "test_batch_from_ppoly",
                                              "test_simple_path_and_polynomial_path")]
+for _name in ("test_gpu_zero_ellipsoid_equals_lp_path", "test_gpu_robust_coefficients"):  # full robust solves only
+    CASES += [(Rb, _name, ident, kw) for ident, kw in _expand(getattr(Rb, _name))]
 CASES += [(S, "test_shapes_rows_per_lane_and_tiny_grids", ident, kw)
           for ident, kw in _expand(S.test_shapes_rows_per_lane_and_tiny_grids)]
 
