@@ -356,3 +356,13 @@ def install(monkeypatch):
         assert hasattr(engine, name), name
         monkeypatch.setattr(engine, name, globals()[name])
     return toppra_b200
+
+
+def install_plain():
+    """The same routing without pytest's monkeypatch: for spawned worker processes (tests/test_distributed_gloo.py),
+    which end with the test anyway."""
+    class _Setter(object):
+        @staticmethod
+        def setattr(obj, name, value):
+            setattr(obj, name, value)
+    return install(_Setter)

@@ -53,3 +53,32 @@ def test_gather_world2_gloo(B):
     ret = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), B, 5, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _solve_worker(rank, world, port, ret):
+    """solve_sharded end to end on the oracle-backed CPU engine double (tests/cpu_engine.py): every rank solves its
+    contiguous shard, gloo gathers; the result must be the reference's golden batch on every rank."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_engine
+    cpu_engine.install_plain()
+    from toppra_b200.distributed import solve_sharded
+    g = np.load(os.path.join(here, "golden", "cfg2_seeds1000.npz"))
+    B = 7  # odd: shards of 4 and 3 paths
+    full = solve_sharded(g["ss"], g["way"][:B], g["grid"], g["vlim"][:B], g["alim"][:B], 0.0, 0.0)
+    ok = all(np.array_equal(full[k].numpy(), g[k if k != "sdd" else "sdd"][:B]) for k in ("K", "sd", "sdd"))
+    ok = ok and np.array_equal(full["status"].numpy(), g["status"][:B]) and full["K"].shape == (B, len(g["grid"]), 2)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_solve_sharded_world2_gloo_on_cpu_double():
+    world = 2
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_solve_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
