@@ -60,6 +60,8 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "_never_", (dirpath, f)
+                # nor the oracle-backed engine double the CPU tests install by monkeypatching (tests/cpu_engine.py)
+                assert "cpu_engine" not in text, (dirpath, f)
 
 
 def _build_c_example(tmp):
