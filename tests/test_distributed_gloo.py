@@ -47,7 +47,7 @@ def _worker(rank, world, port, B, G, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B", [8, 9])
+@pytest.mark.parametrize("B", [8, 9, 1])
 def test_gather_world2_gloo(B):
     world = 2
     ret = mp.get_context("spawn").Manager().dict()
@@ -81,4 +81,30 @@ def test_solve_sharded_world2_gloo_on_cpu_double():
     world = 2
     ret = mp.get_context("spawn").Manager().dict()
     mp.spawn(_solve_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def _solve_worker_tiny(rank, world, port, ret):
+    """More ranks than paths: the rank with an empty shard must not hang the gather."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_engine
+    cpu_engine.install_plain()
+    from toppra_b200.distributed import solve_sharded
+    g = np.load(os.path.join(here, "golden", "cfg2_seeds1000.npz"))
+    full = solve_sharded(g["ss"], g["way"][:1], g["grid"], g["vlim"][:1], g["alim"][:1], 0.0, 0.0, device="cpu")
+    ok = np.array_equal(full["K"].numpy(), g["K"][:1]) and np.array_equal(full["sd"].numpy(), g["sd"][:1])
+    ret[rank] = bool(ok and full["status"].shape == (1,))
+    dist.destroy_process_group()
+
+
+def test_solve_sharded_more_ranks_than_paths():
+    world = 2
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_solve_worker_tiny, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}

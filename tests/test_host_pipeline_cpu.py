@@ -75,3 +75,45 @@ def test_chunked_batch_equals_single_launch_on_cpu(monkeypatch):
     for k in ("K", "sd", "sdd", "status"):
         assert np.array_equal(one[k], many[k]), k
     assert not one["status"].any()
+
+
+def test_batch_input_validation_on_cpu(monkeypatch):
+    """Shapes and value ranges are checked on the host before raw pointers reach the kernels: a short limit
+    array, a break array of another batch, a non-increasing knot vector, gridpoints that do not span the path interval
+    and negative boundary velocities raise instead of reading out of bounds / silently extrapolating."""
+    import torch
+    ta = cpu_engine.install(monkeypatch)
+    from problems import make_batch
+    B, G = 6, 30
+    ss, way, vlim, alim = make_batch(B, 1000)
+    grid = np.linspace(0, 1, G)
+    path = ta.BatchSplineInterpolator(ss, way)
+    acc = ta.constraint.JointAccelerationConstraint(alim)
+    with pytest.raises(ValueError):  # limits of a smaller batch
+        ta.BatchTOPPRA([ta.constraint.JointVelocityConstraint(vlim[:B - 1]), acc], path, grid).compute_parameterization(0, 0)
+    with pytest.raises(ValueError):  # wrong dof
+        ta.BatchTOPPRA([ta.constraint.JointVelocityConstraint(vlim[:, :5]), acc], path, grid).compute_parameterization(0, 0)
+    with pytest.raises(ValueError):  # per-path knots of another batch size
+        ta.BatchSplineInterpolator(np.tile(ss, (B - 1, 1)), way)
+    bad_ss = ss.copy()
+    bad_ss[2] = bad_ss[1]
+    with pytest.raises(ValueError):
+        ta.BatchSplineInterpolator(bad_ss, way)
+    with pytest.raises(ValueError):
+        ta.BatchSplineInterpolator(torch.as_tensor(bad_ss), torch.as_tensor(way))
+    cons = [ta.constraint.JointVelocityConstraint(vlim), acc]
+    with pytest.raises(ValueError, match="Invalid manually supplied gridpoints"):
+        ta.BatchTOPPRA(cons, path, np.linspace(0, 0.9, G))
+    with pytest.raises(ValueError, match="Invalid manually supplied gridpoints"):
+        ta.BatchTOPPRA(cons, path, torch.linspace(0.1, 1, G, dtype=torch.float64))
+    with pytest.raises(ValueError, match="Bad input gridpoints"):
+        g2 = grid.copy()
+        g2[3] = g2[2]
+        ta.BatchTOPPRA(cons, path, torch.as_tensor(g2))
+    inst = ta.BatchTOPPRA(cons, path, grid)
+    with pytest.raises(ta.exceptions.BadInputVelocities):
+        inst.compute_parameterization(torch.full((B,), -0.1, dtype=torch.float64), 0.0)
+    with pytest.raises(ValueError):
+        inst.compute_parameterization(torch.zeros(B - 1, dtype=torch.float64), 0.0)
+    with pytest.raises(ta.exceptions.BadInputVelocities):
+        inst.compute_parameterization(-0.1, 0.0)

@@ -108,7 +108,7 @@ class BatchTOPPRA(object):
     gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
     """
 
-    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30, exact=True):
+    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30, exact=True, validate=True):
         if not isinstance(path, BatchSplineInterpolator):
             raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
         torch = engine.torch_mod()
@@ -125,6 +125,24 @@ class BatchTOPPRA(object):
         self.d_grid = engine.as_device(gridpoints, self.device)
         if self.d_grid.dim() not in (1, 2) or (self.d_grid.dim() == 2 and self.d_grid.shape[0] != path.B):
             raise ValueError("gridpoints must have shape (G,) or (B, G)")
+        if validate:
+            # reference algorithm.py:107-120: gridpoints must be increasing and span exactly the path interval
+            # ("Invalid manually supplied gridpoints."); one small device reduction per setup
+            g, ss = self.d_grid, path.d_ss
+            code = ((g[..., 0] != ss[..., 0]).any() | (g[..., -1] != ss[..., -1]).any()).to(torch.int32)
+            if g.shape[-1] > 1:
+                code = code + 2 * (g[..., 1:] <= g[..., :-1]).any().to(torch.int32)
+            code = int(code)
+            if code & 1:
+                raise ValueError("Invalid manually supplied gridpoints.")
+            if code & 2:
+                raise ValueError("Bad input gridpoints.")
+        for c in constraint_list:  # per-path limit arrays must cover exactly this batch (raw pointers go to the kernels)
+            for name in ("vlim", "alim"):
+                lim = getattr(c, name, None)
+                if isinstance(lim, np.ndarray) and (lim.shape[-2] != path.dof or (lim.ndim == 3 and lim.shape[0] != path.B)):
+                    raise ValueError("%s.%s has shape %s; expected (%d, 2) or (%d, %d, 2)"
+                                     % (type(c).__name__, name, lim.shape, path.dof, path.B, path.dof))
         self.ctx = RecordContext(path, self.d_grid, grid_host, None)
         self.records = None
         self.R = None
@@ -156,7 +174,14 @@ class BatchTOPPRA(object):
             return None
         torch = engine.torch_mod()
         if isinstance(v, torch.Tensor):
-            return engine.as_device(v, self.device)
+            t = engine.as_device(v, self.device)
+            if t.dim() == 0:
+                t = t.expand(self.B).contiguous()
+            if tuple(t.shape) != (self.B,):
+                raise ValueError("boundary velocities must be scalars or have shape (B,)")
+            if bool((t < 0).any()):
+                raise BadInputVelocities("Negative path velocities: path velocities must be positive")
+            return t
         arr = np.broadcast_to(np.asarray(v, dtype=np.float64), (self.B,))
         if np.any(arr < 0):
             raise BadInputVelocities("Negative path velocities: path velocities must be positive")
@@ -164,24 +189,37 @@ class BatchTOPPRA(object):
             return None  # kernels treat NULL as zeros
         return engine.as_device(np.ascontiguousarray(arr), self.device)
 
-    def solve_to_host(self, sd_start=0.0, sd_end=0.0, pinned=None):
-        """compute_parameterization + copy of (K, sd, sdd, status) to pinned host memory, with the D2H copy of K
-        overlapped with the forward pass: the scan runs as a backward-only and a forward-only launch and K leaves
-        on a second stream in between.  Returns the dict of pinned host tensors (valid after this call)."""
+    def _pinned_outputs(self, pinned):
+        """Complete `pinned` (a dict, possibly empty / None) to the full set of pinned result tensors."""
         torch = engine.torch_mod()
+        B, G = self.B, self.G
+        shapes = {"K": ((B, G, 2), torch.float64), "sd": ((B, G), torch.float64), "sdd": ((B, G - 1), torch.float64),
+                  "status": ((B,), torch.int32), "fail_stage": ((B,), torch.int32)}
+        pinned = {} if pinned is None else pinned
+        for key, (shape, dt) in shapes.items():
+            if key not in pinned:
+                pinned[key] = torch.empty(shape, dtype=dt).pin_memory()
+        return pinned
+
+    def solve_to_host(self, sd_start=0.0, sd_end=0.0, pinned=None):
+        """compute_parameterization + copy of (K, sd, sdd, status, fail_stage) to pinned host memory, with the D2H
+        copy of K overlapped with the forward pass: the scan runs as a backward-only and a forward-only launch and K
+        leaves on a second stream in between.  Returns the dict of pinned host TENSORS (same keys and types for every
+        problem kind: chunked and robust problems take the plain path); the host is synchronised before returning,
+        so the buffers are valid on return."""
+        torch = engine.torch_mod()
+        pinned = self._pinned_outputs(pinned)
+        main = torch.cuda.current_stream(self.device)
         if self.conic is not None or self.chunk_size() < self.B:
-            return_host = self.compute_parameterization(sd_start, sd_end).to_host(pinned)
-            return return_host
+            res = self.compute_parameterization(sd_start, sd_end)
+            for key in pinned:
+                pinned[key].copy_(getattr(res, key), non_blocking=True)
+            self.last_result = res
+            main.synchronize()
+            return pinned
         if self.records is None:
             self.setup()
-        B, G = self.B, self.G
-        if pinned is None:
-            pinned = {"K": torch.empty((B, G, 2), dtype=torch.float64).pin_memory(),
-                      "sd": torch.empty((B, G), dtype=torch.float64).pin_memory(),
-                      "sdd": torch.empty((B, G - 1), dtype=torch.float64).pin_memory(),
-                      "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
         s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
-        main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         back = engine.scan(self.records, self.R, self.d_grid, s0, s1, backward_only=True, fast_lower=not self.exact)
@@ -194,9 +232,11 @@ class BatchTOPPRA(object):
         pinned["sd"].copy_(fwd["sd"], non_blocking=True)
         pinned["sdd"].copy_(fwd["u"], non_blocking=True)
         pinned["status"].copy_(fwd["status"], non_blocking=True)
+        pinned["fail_stage"].copy_(fwd["fail_stage"], non_blocking=True)
         main.wait_stream(self._copy_stream)   # the step is complete (for events / callers) when K has landed too
         back["K"].record_stream(self._copy_stream)
         self.last_result = BatchResult(fwd)
+        main.synchronize()                    # host-visible: every copy above has landed
         return pinned
 
     def chunk_size(self):

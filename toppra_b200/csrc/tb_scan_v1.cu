@@ -1,0 +1,749 @@
+// tb_scan_v1.cu — round-1 K2 (one warp per path), kept for A/B timing (TB_SCAN_IMPL=v1): backward controllable sets + forward parameterisation (TOPP-RA), one warp per path.
+//
+// Replaces (reference, hungpham2511/toppra v0.6.2):
+//   ReachabilityAlgorithm.compute_controllable_sets / _one_step   reachability_algorithm.py:166-238
+//   ReachabilityAlgorithm.compute_parameterization                reachability_algorithm.py:240-376
+//   TOPPRA._forward_step                                          time_optimal_algorithm.py:55-92
+//   seidelWrapper.solve_stagewise_optim                           cy_seidel_solverwrapper.pyx:549-697
+//   cy_solve_lp2d / cy_solve_lp1d                                 cy_seidel_solverwrapper.pyx:149-390 / 93-144
+//
+// Design (B200): the stages of one path are strictly sequential (K[i] <- K[i+1], x[i+1] <- x[i]), so the
+// parallelism is (i) across paths: one warp per path, and (ii) across the LP rows of a stage: one row per lane
+// (RPL rows per lane when nC > 32).  Seidel's incremental 2-variable LP keeps its exact row order (including
+// the reference's warm-start permutation) so results are bit-identical to the Cython solver:
+//   * "first violated row in order"      -> per-lane position + redux.sync min
+//   * projection of earlier rows + box   -> one fp64 division per lane
+//   * 1-D LP (min of upper / max of lower limits) -> 5-step shuffle reductions
+// The per-stage record (3R+2 doubles) is streamed HBM -> shared memory with cp.async.bulk (TMA bulk copy,
+// mbarrier complete_tx), double-buffered one stage ahead of the solve.
+// Compiled with -fmad=false: no FMA contraction, same roundings as the x86-64 reference.
+#include <limits.h>
+#include <stdlib.h>
+
+#include "tb_common.cuh"
+
+namespace tb {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// Arrive/copy/wait take 32-bit shared-window addresses (computed once per kernel): no generic->shared conversion and
+// no 64-bit pointer arithmetic in the stage loops.
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, unsigned bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(const uint32_t addr, unsigned parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok) __nanosleep(64);  // the copy is still in flight: do not burn issue slots other warps could use
+  } while (!ok);
+}
+
+// Warp-wide min / max of doubles (no NaNs) with two 32-bit redux.sync each instead of five shuffle rounds.
+// Order-preserving map double -> (khi, klo): flip all bits of negative numbers, the sign bit of the others; then
+// reduce the high words, and the low words among the lanes that tie on the high word.
+__device__ __forceinline__ double warp_min(double v) {
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int m = hi >> 31;  // 0 or -1
+  const unsigned khi = (unsigned)(hi ^ (m | (int)0x80000000)), klo = (unsigned)(lo ^ m);
+  const unsigned mh = __reduce_min_sync(FULL, khi);
+  const unsigned ml = __reduce_min_sync(FULL, khi == mh ? klo : 0xffffffffu);
+  const int m2 = ((int)~mh) >> 31;  // -1 if the winner is negative
+  return __hiloint2double((int)(mh ^ (unsigned)(m2 | (int)0x80000000)), (int)(ml ^ (unsigned)m2));
+}
+__device__ __forceinline__ double warp_max(double v) {
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int m = hi >> 31;
+  const unsigned khi = (unsigned)(hi ^ (m | (int)0x80000000)), klo = (unsigned)(lo ^ m);
+  const unsigned mh = __reduce_max_sync(FULL, khi);
+  const unsigned ml = __reduce_max_sync(FULL, khi == mh ? klo : 0u);
+  const int m2 = ((int)~mh) >> 31;
+  return __hiloint2double((int)(mh ^ (unsigned)(m2 | (int)0x80000000)), (int)(ml ^ (unsigned)m2));
+}
+
+// Position of LP row r in Seidel's processing order, cy_seidel_solverwrapper.pyx:252-264:
+// a valid warm-start pair puts active_c[1] first, active_c[0] second, then the remaining rows ascending.
+__device__ __forceinline__ int row_pos(int r, bool valid, int ac0, int ac1) {
+  if (!valid) return r;
+  if (r == ac1) return 0;
+  if (r == ac0) return 1;
+  return 2 + r - (r > ac0 ? 1 : 0) - (r > ac1 ? 1 : 0);
+}
+__device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
+  if (!valid) return p;
+  if (p == 0) return ac1;
+  if (p == 1) return ac0;
+  const int lo = min(ac0, ac1), hi = max(ac0, ac1);
+  int r = p - 2;
+  if (r >= lo) ++r;
+  if (r >= hi) ++r;
+  return r;
+}
+
+// Identity the optimiser cannot see through: keeps a sanitised division operand from being folded back into the
+// original one when the quotient is later replaced by a select (the compiler would divide the raw value again).
+__device__ __forceinline__ double opaque(double v) {
+  asm volatile("" : "+d"(v));
+  return v;
+}
+
+// Python's builtin max(a, b) / min(a, b) on floats (reachability_algorithm.py:324-354): a unless b compares beyond it
+__device__ __forceinline__ double py_max(const double a, const double b) { return (b > a) ? b : a; }
+__device__ __forceinline__ double py_min(const double a, const double b) { return (b < a) ? b : a; }
+
+constexpr int BOXBASE = 1 << 20;
+constexpr double SKIP_GAP = 1e-7;   // shortcuts A/B: required violation, relative to the terms' magnitudes (TINY = 1e-10)
+constexpr double SKIP_BIG = 1e300;
+constexpr double SKIP_TMAX = 90.0;  // shortcut A: largest line parameter of a skipped visit (see lp2d_impl)
+#ifndef TB_SCAN_NBUF
+#define TB_SCAN_NBUF 4
+#endif
+constexpr int SCAN_NBUF = TB_SCAN_NBUF;  // record buffers per warp (NBUF-1 stages of look-ahead)
+
+// One projected constraint of the 1-D sub-problem (pyx:326-347): its limit on t as an upper bound `thi` (denom >
+// TINY) or a lower bound `tlo` (denom < -TINY); +-LP_INF = no limit of that kind (the 1-D LP's own bounds);
+// bad: parallel & infeasible.  The divisor of unused lanes is replaced by 1 so that the IEEE division never
+// leaves its fast path for a value that is thrown away (x/0 would take the slow-path subroutine).
+__device__ __forceinline__ void project_item(const bool part, const double aj, const double bj, const double cj,
+                                             const double dt0, const double dt1, const double z0, const double z1,
+                                             double &thi, double &tlo, bool &bad) {
+  const double denom = dt0 * aj + dt1 * bj;
+  const double num = cj + z1 * bj + z0 * aj;
+  const bool up = part && (denom > LP_TINY), dn = part && (denom < -LP_TINY);
+  const double t = -num / ((up || dn) ? denom : 1.0);
+  // `cur_x < cur_max` / `cur_x > cur_min` (pyx:115-124): a limit at or beyond the sentinel, or NaN, never wins
+  thi = (up && t < LP_INF) ? t : LP_INF;
+  tlo = (dn && t > -LP_INF) ? t : -LP_INF;
+  bad = bad || (part && !(up || dn) && (num > LP_SMALL));
+}
+
+// (aj, bj, cj) of box row m: 0: low0 <= u, 1: u <= high0, 2: low1 <= x, 3: x <= high1   (pyx:300-318)
+__device__ __forceinline__ void box_row(const int m, const double low0, const double high0, const double low1,
+                                        const double high1, double &aj, double &bj, double &cj) {
+  aj = __hiloint2double((m == 0) ? (int)0xBFF00000 : ((m == 1) ? 0x3FF00000 : 0), 0);
+  bj = __hiloint2double((m == 2) ? (int)0xBFF00000 : ((m == 3) ? 0x3FF00000 : 0), 0);
+  cj = (m < 2) ? ((m == 0) ? low0 : -high0) : ((m == 2) ? low1 : -high1);
+}
+
+// cy_solve_lp2d (pyx:149-390) on one warp.  Lane `lane` holds LP rows r = lane + 32*s, s < RPL
+// (padding rows must be (0, 0, -1)).  maximise v0*u + v1*x  s.t.  a u + b x + c <= 0, low <= (u,x) <= high.
+// ac0/ac1: in = warm-start pair (active_c of the previous solve of this slot), out = new active pair
+// (updated only when feasible, like pyx:673-676,690-691).  Returns false when infeasible.
+//
+// Per violated row k (one "re-solve"): the earlier rows and the four box rows are projected onto line k, one item
+// per lane.  The box rows ride on lanes whose own row does not take part in this re-solve (rows at or after k,
+// padding lanes); only if fewer than four such lanes exist they fall back to an extra item slot.
+// PERM = a valid warm-start pair permutes the row order (pyx:252-264); PERM = false is the natural order, for which
+// position == row index and the bookkeeping folds away (in the TOPP-RA backward pass: always for the min-x LP, whose
+// optimum sits on the x box bound and invalidates the pair; the max-x LP usually has a valid pair).
+// SKIP = the caller is the backward pass of the scan: the shortcuts A / B below may name the first row to re-solve on
+// (bit-identical; a scalar model of the rules is checked by tests/test_shortcut_model.py); all else walks the rows in order.
+template <int RPL, bool PERM, bool SKIP>
+__device__ __forceinline__ bool lp2d_impl(const double v0, const double v1, const double (&a)[RPL],
+                                          const double (&b)[RPL], const double (&c)[RPL], const int nC,
+                                          const double low0, const double high0, const double low1,
+                                          const double high1, int &ac0, int &ac1, double &out_u, double &out_x,
+                                          const int lane, int &n_resolve) {
+  double p0 = (v0 > LP_TINY) ? high0 : low0;       // pyx:236-247
+  double p1 = (v1 > LP_TINY) ? high1 : low1;
+  int nac0 = (v0 > LP_TINY) ? -2 : -1;
+  int nac1 = (v1 > LP_TINY) ? -4 : -3;
+  constexpr bool valid = PERM;
+  int pos[RPL];
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const int r = lane + 32 * s;
+    pos[s] = (r < nC) ? row_pos(r, valid, ac0, ac1) : INT_MAX;
+  }
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int kpos = -1;
+  // shortcuts A/B below: only for the two objectives of the backward pass (min x, max x)
+  const bool skip_ok = SKIP && (((v0 > LP_TINY) && (v1 < 0)) || ((v0 < -LP_TINY) && (v1 > 0)));
+  while (true) {
+    int knew = INT_MAX;
+    if constexpr (SKIP && !PERM) {
+      if (kpos < 0 && skip_ok) {
+        // Shortcut A (natural order).  Start vertex = (high0, low1) for the min-x LP, (low0,
+        // high1) for the max-x LP.  In mirrored variables (ua = sg*u) every visit of the reference's walk sits on a
+        // row that bounds ua from above, lands on x = its box bound and only lowers ua; each visit recomputes the
+        // point from scratch over ALL earlier rows, so the final state depends only on the LAST visited row, and
+        // that is the row m with the smallest own bound at this x.  The reference is certain to visit m when the
+        // smallest bound among the OTHER rows (and the start value) violates row m far above the TINY threshold;
+        // one exact re-solve on m then reproduces the reference's state bit for bit, and the exact walk goes on
+        // from there.  Rows before m that bound ua from below (or not at all) must hold at the final point with
+        // a margin, and every upper row must pick the low end of its line (the exact path's v1d test).  Any doubt
+        // -> ordinary walk.  A scalar model of these rules is checked by tests/test_shortcut_model.py.
+        const double sg = (v0 > 0) ? 1.0 : -1.0;
+        const double x = p1, u0m = sg * p0;
+        double uo[RPL], bxc[RPL];
+        bool upr[RPL], lor[RPL];
+        double lmin = SKIP_BIG;
+        bool bad = false;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+          const bool real = pos[s] != INT_MAX;
+          const double sa = sg * a[s];
+          bxc[s] = b[s] * x + c[s];
+          upr[s] = real && (sa > LP_TINY);
+          lor[s] = real && (sa < -LP_TINY);
+          // a zero numerator (row 0 at x = 0 with K_lo = 0: every stage) would send the IEEE division through its
+          // slow-path subroutine; this value only feeds the margin tests, so 0 is substituted directly
+          const bool zn = (bxc[s] == 0.0);
+          const double qd = -opaque(zn ? 1.0 : bxc[s]) / ((upr[s] || lor[s]) ? a[s] : 1.0);
+          uo[s] = zn ? 0.0 : sg * qd;
+          const double v1d_own = (-b[s]) * v0 + a[s] * v1;  // the exact path's v1d if this row were visited
+          bad = bad || (upr[s] && !((fabs(v1d_own) < LP_TINY) || (v1d_own < 0)));
+          // line parameter t of this row's landing point (own bound, x): a skipped visit must neither end on the
+          // +-1e10 sentinel of the 1-D LP nor be far enough from the foot point for a "parallel" row (|denom| <=
+          // TINY although the lines cross) to fail the LP_SMALL test there: |t| * TINY stays far below LP_SMALL
+          bad = bad || (upr[s] && !(fabs(x * a[s] - (sg * uo[s]) * b[s]) < SKIP_TMAX * (a[s] * a[s] + b[s] * b[s])));
+          lmin = (upr[s] && uo[s] < lmin) ? uo[s] : lmin;
+        }
+        const double um = warp_min(lmin);
+        int mp = INT_MAX;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) mp = (upr[s] && uo[s] == um) ? min(mp, pos[s]) : mp;
+        const int m = __reduce_min_sync(FULL, mp);
+        if (m != INT_MAX) {
+          double l2 = SKIP_BIG;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) l2 = (upr[s] && pos[s] != m && uo[s] < l2) ? uo[s] : l2;
+          double second = warp_min(l2);
+          second = (u0m < second) ? u0m : second;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) {
+            if (pos[s] == m) {
+              const double au = a[s] * (sg * second);
+              const double val = au + bxc[s];
+              bad = bad || !(val >= SKIP_GAP * (1.0 + fabs(au) + fabs(b[s] * x) + fabs(c[s])));
+            } else if (pos[s] < m) {
+              bad = bad || (lor[s] && (uo[s] > um - 1e-9 * (1.0 + fabs(um)))) ||
+                    (!upr[s] && !lor[s] && ((bxc[s] > -1e-9) || (a[s] != 0.0)));
+            }
+          }
+          const double ur = sg * um;
+          bad = bad || (ur < low0 + 1.0) || (ur > high0 - 1.0);
+          if (!__any_sync(FULL, bad)) knew = m;
+        }
+      }
+    }
+    if (knew == INT_MAX) {
+      // first row (in order) violated at the current point, pyx:269-275.  NaN counts as violated (not `< TINY`).
+      int mypos = INT_MAX;
+#pragma unroll
+      for (int s = 0; s < RPL; ++s) {
+        const double val = a[s] * p0 + b[s] * p1 + c[s];
+        const bool cand = !(val < LP_TINY) && (pos[s] > kpos) && (pos[s] != INT_MAX);
+        mypos = cand ? min(mypos, pos[s]) : mypos;
+      }
+      knew = __reduce_min_sync(FULL, mypos);
+      if (knew == INT_MAX) break;
+      if constexpr (SKIP && PERM) {
+        if (kpos < 0 && skip_ok && knew == 0) {
+          // Shortcut B (valid warm-start pair; order = row p = ac1, row k = ac0, the rest).  Row p is violated at
+          // the start vertex, so the reference re-solves on it against the box only and holds the optimum of line p
+          // inside the box next.  That point is cheap to compute with plain arithmetic; if row k is violated there
+          // far above the TINY threshold the reference is certain to re-solve on position 1 next, and that re-solve
+          // (row p + the box, recomputed from scratch) does not depend on the skipped one.
+          const int lp = ac1 & 31;
+          double ap = a[0], bp = b[0], cp = c[0];
+#pragma unroll
+          for (int s = 1; s < RPL; ++s)
+            if ((ac1 >> 5) == s) { ap = a[s]; bp = b[s]; cp = c[s]; }
+          ap = __shfl_sync(FULL, ap, lp);
+          bp = __shfl_sync(FULL, bp, lp);
+          cp = __shfl_sync(FULL, cp, lp);
+          bool okb = fabs(ap) > 1e-6;
+          const double ia = 1.0 / (okb ? ap : 1.0);
+          okb = okb && (low1 <= high1 - 1e-7 * (1.0 + fabs(low1) + fabs(high1)));
+          const double slp = v1 - v0 * bp * ia;  // d objective / dx along line p
+          okb = okb && !(fabs(slp) < 1e-6);
+          // optimum of line p inside the box: the x bound the objective points to, provided u stays well inside its
+          // own bounds there (otherwise the u bounds clip the line first: left to the exact path)
+          const double sx = (slp > 0) ? high1 : low1;
+          const double su = -(bp * sx + cp) * ia;
+          okb = okb && (su >= low0 + 1.0) && (su <= high0 - 1.0);
+          // the skipped 1-D optimum must stay clear of the +-1e10 sentinel (pyx:376-383 would report infeasible)
+          okb = okb && (fabs(sx * ap - su * bp) < 1e9 * (ap * ap + bp * bp));
+          bool kviol = false;
+#pragma unroll
+          for (int s = 0; s < RPL; ++s) {
+            const double t1 = a[s] * su, t2 = b[s] * sx;
+            const double val = t1 + t2 + c[s];
+            kviol = kviol || ((pos[s] == 1) && (val >= SKIP_GAP * (1.0 + fabs(t1) + fabs(t2) + fabs(c[s]))));
+          }
+          if (__any_sync(FULL, kviol) && okb) knew = 1;
+        }
+      }
+    }
+    kpos = knew;
+    const int krow = pos_row(kpos, valid, ac0, ac1);
+    ++n_resolve;
+    nac0 = krow;
+    // broadcast row k
+    double ak = a[0], bk = b[0], ck = c[0];
+#pragma unroll
+    for (int s = 1; s < RPL; ++s)
+      if ((krow >> 5) == s) { ak = a[s]; bk = b[s]; ck = c[s]; }
+    ak = __shfl_sync(FULL, ak, krow & 31);
+    bk = __shfl_sync(FULL, bk, krow & 31);
+    ck = __shfl_sync(FULL, ck, krow & 31);
+    // project the origin onto line k, pyx:290-295: z = (-a c, -b c) / (a^2 + b^2).  One division sequence for
+    // both components: odd lanes divide the second numerator.
+    const double nrm = ak * ak + bk * bk;
+    const double zq = ((lane & 1) ? (-bk * ck) : (-ak * ck)) / nrm;
+    const double z0 = __shfl_sync(FULL, zq, 0);
+    const double z1 = __shfl_sync(FULL, zq, 1);
+    const double dt0 = -bk, dt1 = ak;
+    const double v1d = dt0 * v0 + dt1 * v1;
+    // project the earlier rows and the four box rows onto the line, pyx:298-347
+    double thi[RPL], tlo[RPL];
+    int key[RPL];
+    bool bad = false;
+    const bool idle0 = !(pos[0] < kpos);  // this lane's slot-0 row does not take part (row k, later rows, padding)
+    const unsigned idle = __ballot_sync(FULL, idle0);
+    const bool box_inline = __popc(idle) >= 4;  // warp-uniform
+    {
+      // slot 0: own row, or (on the first four idle lanes) box row m = rank
+      const int m = __popc(idle & lt_mask);
+      const bool isbox = box_inline && idle0 && m < 4;
+      double ba, bb, bc;
+      box_row(m, low0, high0, low1, high1, ba, bb, bc);
+      key[0] = isbox ? BOXBASE + m : pos[0];
+      project_item(isbox || !idle0, isbox ? ba : a[0], isbox ? bb : b[0], isbox ? bc : c[0], dt0, dt1, z0, z1, thi[0],
+                   tlo[0], bad);
+    }
+#pragma unroll
+    for (int s = 1; s < RPL; ++s) {
+      key[s] = pos[s];
+      project_item(pos[s] < kpos, a[s], b[s], c[s], dt0, dt1, z0, z1, thi[s], tlo[s], bad);
+    }
+    // 1-D LP on the line with bounds +-INF, pyx:350 -> cy_solve_lp1d pyx:93-144
+    double my_hi = thi[0], my_lo = tlo[0];
+#pragma unroll
+    for (int s = 1; s < RPL; ++s) {
+      my_hi = (thi[s] < my_hi) ? thi[s] : my_hi;
+      my_lo = (tlo[s] > my_lo) ? tlo[s] : my_lo;
+    }
+    double xhi_t = LP_INF, xlo_t = -LP_INF;  // extra item slot, only when the box rows could not ride inline
+    if (!box_inline) {  // rare: (almost) every row takes part -> box rows on lanes 0..3
+      double ba, bb, bc;
+      box_row(lane, low0, high0, low1, high1, ba, bb, bc);
+      project_item(lane < 4, ba, bb, bc, dt0, dt1, z0, z1, xhi_t, xlo_t, bad);
+      my_hi = (xhi_t < my_hi) ? xhi_t : my_hi;
+      my_lo = (xlo_t > my_lo) ? xlo_t : my_lo;
+    }
+    // The objective's sign decides which end of [cur_min, cur_max] is the optimum (pyx:130-143); only that end is
+    // reduced exactly (max lo = -min(-lo)); "cur_min > cur_max" (pyx:126-128) is a vote against the other side.
+    const bool pick_min = (fabs(v1d) < LP_TINY) || (v1d < 0);
+    const double red = warp_min(pick_min ? -my_lo : my_hi);
+    const double tstar = pick_min ? -red : red;
+    const bool cross = pick_min ? (my_hi < tstar) : (my_lo > tstar);
+    if (__any_sync(FULL, bad || cross)) return false;
+    // optimum on the +-INF sentinel (1-D active index -1/-2) counts as infeasible, pyx:376-383
+    if (tstar == (pick_min ? -LP_INF : LP_INF)) return false;
+    // active item = first (lowest key) item that attains the optimum; tstar is finite here, sentinels never match
+    int mykey = INT_MAX;
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) mykey = ((pick_min ? tlo[s] : thi[s]) == tstar) ? min(mykey, key[s]) : mykey;
+    if (!box_inline) mykey = ((pick_min ? xlo_t : xhi_t) == tstar) ? min(mykey, BOXBASE + lane) : mykey;
+    const int akey = __reduce_min_sync(FULL, mykey);
+    nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
+    p0 = z0 + tstar * dt0;  // pyx:362-363
+    p1 = z1 + tstar * dt1;
+  }
+  ac0 = nac0;
+  ac1 = nac1;
+  out_u = p0;
+  out_x = p1;
+  return true;
+}
+
+template <int RPL, bool SKIP = false>
+__device__ __forceinline__ bool lp2d_warp(const double v0, const double v1, const double (&a)[RPL],
+                                          const double (&b)[RPL], const double (&c)[RPL], const int nC,
+                                          const double low0, const double high0, const double low1,
+                                          const double high1, int &ac0, int &ac1, double &out_u, double &out_x,
+                                          const int lane, int &n_resolve) {
+  if (low0 > high0 || low1 > high1) return false;  // pyx:233-235
+  const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;  // warp-uniform
+  if (valid)
+    return lp2d_impl<RPL, true, SKIP>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
+                                       n_resolve);
+  return lp2d_impl<RPL, false, SKIP>(v0, v1, a, b, c, nC, low0, high0, low1, high1, ac0, ac1, out_u, out_x, lane,
+                                     n_resolve);
+}
+
+// cy_solve_lp1d (pyx:93-144) as used by the x_min == x_max branch of solve_stagewise_optim (pyx:631-650):
+// rows a*u + (b*x + c) <= 0 over ALL nC rows, u in [low0, high0]; objective v0*u.  Returns false if infeasible.
+template <int RPL>
+__device__ __forceinline__ bool lp1d_fixed_x_warp(const double v0, const double x, const double (&a)[RPL],
+                                                  const double (&b)[RPL], const double (&c)[RPL],
+                                                  const double low0, const double high0, double &out_u) {
+  double my_hi = high0, my_lo = low0;
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const double bxc = b[s] * x + c[s];
+    const bool up = a[s] > LP_TINY, dn = a[s] < -LP_TINY;
+    // unused lanes divide by 1 and a zero numerator (row 0 at x = 0 with K_lo = 0) is not divided at all: both would
+    // leave the IEEE division's fast path.  (-bxc) * a is the quotient's correctly signed zero.
+    const double den = (up || dn) ? a[s] : 1.0;
+    const bool zn = (bxc == 0.0);
+    const double q = -opaque(zn ? 1.0 : bxc) / den;
+    const double t = zn ? (-bxc) * den : q;
+    my_hi = (up && t < my_hi) ? t : my_hi;
+    my_lo = (dn && t > my_lo) ? t : my_lo;
+  }
+  // exact reduction of the optimal end only; infeasibility (cur_min > cur_max) as a vote against the other side
+  const bool pick_min = (fabs(v0) < LP_TINY) || (v0 < 0);
+  const double red = warp_min(pick_min ? -my_lo : my_hi);
+  const double ustar = pick_min ? -red : red;
+  if (__any_sync(FULL, pick_min ? (my_hi < ustar) : (my_lo > ustar))) return false;
+  out_u = ustar;
+  return true;
+}
+
+// Load this lane's rows of one stage record (shared memory) into registers.  LP row r: r = 0,1 are the
+// x_next rows (filled by the caller), r >= 2 is static row r-2; padding rows are (0,0,-1).
+template <int RPL>
+__device__ __forceinline__ void load_rows(const double *rec, const int R, const int nC, const int lane,
+                                          double (&a)[RPL], double (&b)[RPL], double (&c)[RPL]) {
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const int r = lane + 32 * s;
+    const bool in = (r >= 2) && (r < nC);
+    const int j = in ? r - 2 : 0;  // always a valid slot of the record: load, then select
+    const double va = rec[j], vb = rec[R + j], vc = rec[2 * R + j];
+    a[s] = in ? va : 0.0;
+    b[s] = in ? vb : 0.0;
+    c[s] = in ? vc : -1.0;
+  }
+}
+
+template <int RPL>
+__device__ __forceinline__ void set_xnext_rows(const int lane, const double delta, const double xn_min,
+                                               const double xn_max, double (&a)[RPL], double (&b)[RPL],
+                                               double (&c)[RPL]) {
+  // pyx:604-620: row0 = (-2 delta, -1, x_next_min), row1 = (2 delta, 1, -x_next_max); selects, no branches
+  const bool xr = lane < 2, first = lane == 0;
+  const double sgn = first ? -1.0 : 1.0;
+  a[0] = xr ? sgn * (2 * delta) : a[0];  // -(2 delta) == -2 * delta bit for bit
+  b[0] = xr ? sgn : b[0];
+  c[0] = xr ? (first ? xn_min : -xn_max) : c[0];
+}
+
+// CFLAGS >= 0: the scan-mode bits of `flags` (backward-only, forward-only, TOPPRAsd rules) are this compile-time
+// constant (the argument is ignored), so the unused passes and rules and their bookkeeping fold away; -1: run time.
+template <int RPL, int WARPS, int MINB, bool FAST, int CFLAGS = -1>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
+            const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
+            const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags_arg,
+            double *__restrict__ Kout, double *__restrict__ sdout, double *__restrict__ uout,
+            int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = (WARPS == 1) ? 0 : (int)(threadIdx.x >> 5), lane = (WARPS == 1) ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  const long path = (long)blockIdx.x * WARPS + warp;
+  if (path >= B) return;
+  double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * SCAN_NBUF * W;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double)) + warp * SCAN_NBUF;
+  const int N = G - 1, nC = R + 2;
+  const unsigned rec_bytes = (unsigned)(W * sizeof(double));
+  // Per-path base pointers live in shared memory: under the 64-register cap the compiler otherwise rebuilds them
+  // from blockIdx and the kernel parameters (a chain of 64-bit multiplies) at every use inside the stage loops.
+  const void *volatile *sptr = reinterpret_cast<const void *volatile *>(
+      smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double) + (size_t)WARPS * SCAN_NBUF * sizeof(uint64_t)) + warp * 4;
+  if (lane == 0) {
+    sptr[0] = records + (size_t)path * G * W;
+    sptr[1] = grid + (grid_shared ? 0 : (size_t)path * G);
+    sptr[2] = Kout + (size_t)path * G * 2;
+  }
+  __syncwarp();
+  auto rec_path = [&]() { return static_cast<const double *>(sptr[0]); };
+  auto gp = [&]() { return static_cast<const double *>(sptr[1]); };
+  auto Kp = [&]() { return static_cast<double *>(const_cast<void *>(sptr[2])); };
+  const int flags = (CFLAGS >= 0) ? CFLAGS : flags_arg;
+  const bool backward_only = (flags & 1) != 0;  // compute_controllable_sets(sdmin, sdmax) alone
+  const bool forward_only = (flags & 16) != 0;  // K and status come from an earlier TB_SCAN_BACKWARD_ONLY launch
+  constexpr bool fast_lower = FAST;             // opt-in shortcut for the min-x LP (TB_SCAN_FAST_LOWER, not bit-identical)
+  const bool sd_mode = (flags & 4) != 0;        // TOPPRAsd forward-pass rules (no retry, x_next - 1e-5 clip)
+  const bool sd_slow = (flags & 8) != 0;        // TOPPRAsd slowest pass: minimise the next velocity
+  double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
+  double *up = backward_only ? nullptr : uout + (size_t)path * (G > 1 ? G - 1 : 0);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < SCAN_NBUF; ++q) mbar_init(&bars[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  // Ring of SCAN_NBUF record buffers: up to SCAN_NBUF-1 bulk copies in flight per warp.  The forward pass solves a
+  // stage in well under the HBM round trip, so one stage of look-ahead is not enough there.
+  unsigned n_issued = 0, n_waited = 0;
+  const uint32_t bufs_s = smem_u32(bufs), bars_s = smem_u32(bars);
+  auto issue = [&](int stage) {
+    if (lane == 0) {
+      const unsigned q = n_issued % SCAN_NBUF;
+      mbar_expect_tx_s(bars_s + q * 8u, rec_bytes);
+      bulk_g2s_s(bufs_s + q * rec_bytes, rec_path() + (size_t)stage * W, rec_bytes, bars_s + q * 8u);
+    }
+    ++n_issued;
+  };
+  auto acquire = [&]() -> const double * {
+    const unsigned q = n_waited % SCAN_NBUF;
+    mbar_wait_s(bars_s + q * 8u, (n_waited / SCAN_NBUF) & 1);
+    ++n_waited;
+    return bufs + (size_t)q * W;
+  };
+  constexpr int AHEAD = SCAN_NBUF - 1;
+
+  // instrumentation: projected re-solves, retries, fast-mode stages; the LP counts are derived from the stage counts
+  int n_resolve = 0, n_retry = 0, n_fast = 0;
+  double a[RPL], b[RPL], c[RPL];
+
+  // ---------------- backward pass: controllable sets, reachability_algorithm.py:166-238 ----------------
+  const double sde = sd_end ? sd_end[path] : 0.0;
+  const double sds = sd_start ? sd_start[path] : 0.0;
+  const double sdeh = sd_end_hi ? sd_end_hi[path] : sde;
+  double kn0 = sde * sde, kn1 = sdeh * sdeh;  // K[N] = [sdmin^2, sdmax^2], reachability_algorithm.py:185
+  if (lane == 0 && !forward_only) { double *kq = Kp(); kq[2 * N] = kn0; kq[2 * N + 1] = kn1; }
+  int st = TB_STATUS_OK, fstage = -1;
+  int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0;  // active_c_up / active_c_down, initialised to zeros (pyx:526-527)
+  if (forward_only) {
+    st = status[path];
+    fstage = fail_stage ? fail_stage[path] : -1;
+    { const double *kq = Kp(); kn0 = kq[0]; kn1 = kq[1]; }
+  }
+  for (int q = 0; !forward_only && q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
+  for (int i = forward_only ? -1 : N - 1; i >= 0; --i) {
+    const double *rec = acquire();
+    load_rows<RPL>(rec, R, nC, lane, a, b, c);
+    const double xlo = rec[3 * R], xhi = rec[3 * R + 1];
+    __syncwarp();
+    if (i - AHEAD >= 0) issue(i - AHEAD);
+    const double *gq = gp();
+    const double delta = gq[i + 1] - gq[i];
+    set_xnext_rows<RPL>(lane, delta, kn0, kn1, a, b, c);
+    // low/high: pyx:587-601 with x_min = x_max = NaN
+    double uu, xx;
+    // x_upper: g = (1e-9, -1) -> v = (-1e-9, 1), slot active_c_down (g[1] <= 0), reachability_algorithm.py:229-233
+    const bool ok_hi = lp2d_warp<RPL, true>(-1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
+                                      n_resolve);
+    const double x_upper = ok_hi ? xx : __longlong_as_double(0x7ff8000000000000LL);
+    // x_lower: g = (-1e-9, 1) -> v = (1e-9, -1), slot active_c_up, reachability_algorithm.py:234-236
+    bool ok_lo;
+    double x_lower;
+    double ufeas;
+    if (fast_lower && xlo <= xhi && lp1d_fixed_x_warp<RPL>(1.0, xlo, a, b, c, VAR_MIN, VAR_MAX, ufeas)) {
+      // TB_SCAN_FAST_LOWER: some u is feasible at x = xlo, so min x IS xlo.  The reference reaches the same vertex
+      // through ~4 projected re-solves and returns xlo plus rounding noise of its projection arithmetic
+      // (|noise| <= ~1e-16, 5 % of the stages): this shortcut is exact for the LP, not bit-identical to that noise.
+      ok_lo = true;
+      x_lower = xlo;
+      ++n_fast;
+    } else {
+        ok_lo = lp2d_warp<RPL, true>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+                                   n_resolve);
+      x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    if (x_lower < 0) x_lower = 0;  // reachability_algorithm.py:190-191
+    if (lane == 0) { double *kq = Kp(); kq[2 * i] = x_lower; kq[2 * i + 1] = x_upper; }
+    if (!(ok_hi && ok_lo)) {
+      // reachability_algorithm.py:192-197: stop; the remaining K entries stay 0 (np.zeros)
+      st = TB_STATUS_FAIL_UNCONTROLLABLE;
+      fstage = i;
+      { double *kq = Kp(); for (int j = lane; j < 2 * i; j += 32) kq[j] = 0.0; }
+      break;
+    }
+    kn0 = x_lower;
+    kn1 = x_upper;
+  }
+  if (counters && lane == 0 && !forward_only) {
+    // backward stages entered: N, or N - fstage when stage fstage failed; 2 LPs each (fast mode: n_fast of them 1-variable)
+    const int nb = (st == TB_STATUS_OK) ? N : N - fstage;
+    counters[path * 4 + 0] = 2 * nb - n_fast;
+    counters[path * 4 + 1] = n_fast;
+  }
+  // drain a prefetch that was issued but not consumed (failure path), so the buffers can be reused
+  while (n_waited < n_issued) (void)acquire();
+  __syncwarp();
+
+  const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  const double x_start = sds * sds;
+  if (backward_only) {
+    if (lane == 0) {
+      status[path] = st;
+      if (fail_stage) fail_stage[path] = fstage;
+    }
+    return;
+  }
+  if (st == TB_STATUS_OK) {
+    // kn0,kn1 == K[0]; admissibility check reachability_algorithm.py:290-301
+    if (x_start + ALG_SMALL < kn0 || kn1 + ALG_SMALL < x_start) { st = TB_STATUS_FAIL_UNCONTROLLABLE; fstage = 0; }
+  }
+  if (st != TB_STATUS_OK) {
+    for (int j = lane; j < G; j += 32) sdp[j] = nan_d;
+    for (int j = lane; j < N; j += 32) up[j] = nan_d;
+  } else {
+    // ---------------- forward pass, reachability_algorithm.py:303-364 ----------------
+    // sd = sqrt(x) is applied in one coalesced sweep after the pass; until then sd[] holds x
+    double x = x_start;
+    if (lane == 0) sdp[0] = x;
+    for (int q = 0; q < AHEAD && q < N; ++q) issue(q);
+    int i = 0;
+    for (; i < N; ++i) {
+      const double *rec = acquire();
+      load_rows<RPL>(rec, R, nC, lane, a, b, c);
+      __syncwarp();
+      if (i + AHEAD < N) issue(i + AHEAD);
+      const double *gq = gp();
+      const double delta = gq[i + 1] - gq[i];
+      const double *kq = Kp();
+      const double k0 = kq[2 * (i + 1)], k1 = kq[2 * (i + 1) + 1];
+      set_xnext_rows<RPL>(lane, delta, k0, k1, a, b, c);
+      int tries = 0;
+      bool ok;
+      double uopt = 0.0;
+      while (true) {
+        // _forward_step: g = (-2 delta, -1), x_min = x_max = x -> 1-D branch, v0 = 2 delta (pyx:628-636);
+        // TOPPRAsd's slowest pass uses g = (2 delta, 1) (desired_duration_algorithm.py:218-223)
+          ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
+        if (ok || sd_mode || tries >= MAX_TRIES) break;  // TOPPRAsd has no retry rule
+        x = py_max(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
+        ++tries;
+        ++n_retry;
+      }
+      if (!ok) {
+        // reachability_algorithm.py:337-342: xs[i+1:] = nan -> sd NaN -> ErrUnknown; us stay 0
+        // (TOPPRAsd: us[i:] and xs[i+1:] become NaN, desired_duration_algorithm.py:106-111)
+        st = TB_STATUS_ERR_UNKNOWN;
+        fstage = i;
+        if (lane == 0) sdp[i] = x;
+        for (int j = i + 1 + lane; j < G; j += 32) sdp[j] = nan_d;
+        for (int j = i + lane; j < N; j += 32) up[j] = sd_mode ? nan_d : 0.0;
+        break;
+      }
+      double x_next = x + 2 * delta * uopt;                       // reachability_algorithm.py:352
+      if (sd_mode) {
+        x_next = py_min(k1, py_max(k0, x_next - ALG_SMALL));          // desired_duration_algorithm.py:117
+      } else {
+        x_next = py_max(x_next - ALG_TINY, 0.9999 * x_next);        // :353
+        x_next = py_min(k1, py_max(k0, x_next));                      // :354
+      }
+      if (lane == 0) {
+        up[i] = uopt;
+        if (tries) sdp[i] = x;  // x was shrunk by the retry rule
+        sdp[i + 1] = x_next;
+      }
+      x = x_next;
+    }
+    while (n_waited < n_issued) (void)acquire();
+    __syncwarp();
+    if (!sd_mode)  // TOPPRAsd combines the squared velocities: its passes return x = sd^2
+      for (int j = lane; j < G; j += 32) sdp[j] = sqrt(sdp[j]);  // reachability_algorithm.py:365
+  }
+  if (lane == 0) {
+    status[path] = st;
+    if (fail_stage) fail_stage[path] = fstage;
+    if (counters) {
+      // forward: one 1-variable LP per stage entered (N, or fstage + 1 when stage fstage failed) + one per retry;
+      // none when the path failed before the forward pass
+      const int n_fwd_stages = (st == TB_STATUS_OK) ? N : ((st == TB_STATUS_ERR_UNKNOWN) ? fstage + 1 : -1);
+      if (forward_only) { counters[path * 4 + 0] = 0; counters[path * 4 + 1] = 0; }
+      if (n_fwd_stages >= 0) counters[path * 4 + 1] += n_fwd_stages + n_retry;
+      counters[path * 4 + 2] = n_resolve;
+      counters[path * 4 + 3] = n_retry;
+    }
+  }
+}
+
+#ifndef TB_SCAN_WARPS
+#define TB_SCAN_WARPS 1
+#endif
+constexpr int SCAN_WARPS = TB_SCAN_WARPS;  // 1: a finished path frees its slot at once (measured best: 1 < 2 < 4)
+#ifndef TB_SCAN_WARPS_PER_SM
+#define TB_SCAN_WARPS_PER_SM 32  // register budget of the dense build: 65536 / (32 * 32) -> 64 registers/thread (measured: 32 > 28 > 24)
+#endif
+
+template <int RPL>
+int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+  const size_t smem = (size_t)SCAN_WARPS * SCAN_NBUF * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t) +
+                      SCAN_WARPS * 4 * sizeof(void *);
+  // Two register budgets for the common nC <= 32 case: 64 registers (32 one-warp CTAs per SM: the 4096-path batch
+  // of BASELINE cfg 2 is a single wave on 148 SMs) or the compiler's free choice.  TB_SCAN_OCC=free|dense overrides.
+  static const char *occ_env = getenv("TB_SCAN_OCC");
+  const bool dense = occ_env ? (occ_env[0] == 'd') : true;
+  constexpr int MINB = (RPL == 1 ? TB_SCAN_WARPS_PER_SM / SCAN_WARPS : 1);
+  const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
+  auto kern = (RPL == 1 && dense) ? (fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true> : scan_kernel<RPL, SCAN_WARPS, MINB, false>)
+                                  : (fast ? scan_kernel<RPL, SCAN_WARPS, 1, true> : scan_kernel<RPL, SCAN_WARPS, 1, false>);
+  if (RPL == 1 && dense) {
+    // the three launch kinds of the batched solver get their own instantiation: full scan, backward only, forward only
+    const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
+    if (mode == 0)
+      kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, 0> : scan_kernel<RPL, SCAN_WARPS, MINB, false, 0>;
+    else if (mode == TB_SCAN_BACKWARD_ONLY)
+      kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, TB_SCAN_BACKWARD_ONLY>
+                  : scan_kernel<RPL, SCAN_WARPS, MINB, false, TB_SCAN_BACKWARD_ONLY>;
+    else if (mode == TB_SCAN_FORWARD_ONLY)
+      kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, TB_SCAN_FORWARD_ONLY>
+                  : scan_kernel<RPL, SCAN_WARPS, MINB, false, TB_SCAN_FORWARD_ONLY>;
+  }
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+  kern<<<blocks, SCAN_WARPS * 32, smem, stream>>>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi,
+                                                  flags, K, sd, u, status, fail_stage, counters);
+  return check_launch("tb_scan");
+}
+
+int check_scan_args(const char *fn, const void *records, int W, int R, const void *grid, int B, int G) {
+  if (!records || !grid || B <= 0 || G <= 0 || R < 0) { set_error("%s: bad argument", fn); return TB_ERR_ARG; }
+  if (R > MAX_ROWS) { set_error("%s: R=%d > %d rows", fn, R, MAX_ROWS); return TB_ERR_UNSUPPORTED; }
+  if (W < 3 * R + 2 || (W & 1)) { set_error("%s: record stride W=%d must be even and >= 3R+2", fn, W); return TB_ERR_ALIGN; }
+  if (((uintptr_t)records & 15) != 0) { set_error("%s: records not 16-byte aligned", fn); return TB_ERR_ALIGN; }
+  return 0;
+}
+
+}  // namespace
+}  // namespace tb
+
+extern "C" int tb_scan_ex_v1(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                          const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                          double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream) {
+  using namespace tb;
+  int rc = check_scan_args("tb_scan", records, W, R, grid, B, G);
+  if (rc) return rc;
+  const bool backward_only = (flags & TB_SCAN_BACKWARD_ONLY) != 0;
+  if (!K || !status || (!backward_only && (!sd || (G > 1 && !u)))) { set_error("tb_scan: null output"); return TB_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nC = R + 2;
+  if (nC <= 32) return launch_scan<1>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  if (nC <= 64) return launch_scan<2>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  if (nC <= 96) return launch_scan<3>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  return launch_scan<4>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+}
+

@@ -26,7 +26,8 @@ def gather_results(local, B_total, group=None):
     out = {}
     for name, t in local.items():
         pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[: t.shape[0]] = t
+        if t.shape[0]:
+            pad[: t.shape[0]] = t
         full = torch.empty((world * nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(full, pad, group=group)
         parts = [full[r * nmax: r * nmax + sizes[r]] for r in range(world)]
@@ -48,8 +49,19 @@ def solve_sharded(ss_waypoints, waypoints, gridpoints, vlim, alim, sd_start=0.0,
         x = np.asarray(x)
         return x[lo:hi] if x.ndim == nd else x
 
-    res = solve_batch(sh(ss_waypoints, 2), waypoints[lo:hi], sh(gridpoints, 2), sh(vlim, 3), sh(alim, 3),
-                      sh(sd_start, 1) if np.ndim(sd_start) else sd_start, sh(sd_end, 1) if np.ndim(sd_end) else sd_end,
-                      device=device)
-    local = dict(K=res.K, sd=res.sd, sdd=res.sdd, status=res.status)
+    if hi > lo:
+        res = solve_batch(sh(ss_waypoints, 2), waypoints[lo:hi], sh(gridpoints, 2), sh(vlim, 3), sh(alim, 3),
+                          sh(sd_start, 1) if np.ndim(sd_start) else sd_start,
+                          sh(sd_end, 1) if np.ndim(sd_end) else sd_end, device=device)
+        local = dict(K=res.K, sd=res.sd, sdd=res.sdd, status=res.status)
+    else:
+        # more ranks than paths: this rank has nothing to solve but still takes part in the gather
+        from . import engine
+        torch = engine.torch_mod()
+        dev = engine.default_device(device)
+        G = np.asarray(gridpoints).shape[-1]
+        local = dict(K=torch.empty((0, G, 2), dtype=torch.float64, device=dev),
+                     sd=torch.empty((0, G), dtype=torch.float64, device=dev),
+                     sdd=torch.empty((0, max(G - 1, 0)), dtype=torch.float64, device=dev),
+                     status=torch.empty((0,), dtype=torch.int32, device=dev))
     return gather_results(local, B, group) if gather else local

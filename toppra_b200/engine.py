@@ -108,6 +108,19 @@ def init_bounds(records, R):
     _lib.check(rc, "tb_init_bounds")
 
 
+def check_grid_shapes(B, breaks, nbreaks, grid, G):
+    """Per-path arrays must have the batch's leading dimension (the kernels index them with the path number)."""
+    if breaks.dim() not in (1, 2) or breaks.shape[-1] != nbreaks or (breaks.dim() == 2 and breaks.shape[0] != B):
+        raise ValueError("breakpoints must have shape (%d,) or (%d, %d); got %s" % (nbreaks, B, nbreaks, tuple(breaks.shape)))
+    if grid.dim() not in (1, 2) or grid.shape[-1] != G or (grid.dim() == 2 and grid.shape[0] != B):
+        raise ValueError("gridpoints must have shape (G,) or (%d, G); got %s" % (B, tuple(grid.shape)))
+
+
+def check_path_vector(t, B, what):
+    if t is not None and tuple(t.shape) != (B,):
+        raise ValueError("%s must have shape (%d,); got %s" % (what, B, tuple(t.shape)))
+
+
 def coeff_velacc(ppoly, breaks, grid, vlim, alim, interp, records, R_total, row0=0, write_xbound=1):
     """K1.  vlim/alim: [dof,2] or [B,dof,2] device tensors (either may be None, not both)."""
     torch = torch_mod()
@@ -115,6 +128,11 @@ def coeff_velacc(ppoly, breaks, grid, vlim, alim, interp, records, R_total, row0
     G = grid.shape[-1]
     W = records.shape[-1]
     lims = [t for t in (vlim, alim) if t is not None]
+    for t in lims:  # raw pointers go to the kernels: a short limit array would be read out of bounds on the device
+        if t.dim() not in (2, 3) or tuple(t.shape[-2:]) != (dof, 2) or (t.dim() == 3 and t.shape[0] != B):
+            raise ValueError("limits must have shape (dof, 2) or (B, dof, 2) with B = %d, dof = %d; got %s"
+                             % (B, dof, tuple(t.shape)))
+    check_grid_shapes(B, breaks, nseg + 1, grid, G)
     shared = all(t.dim() == 2 for t in lims)
     if not shared:
         vlim = None if vlim is None else (vlim if vlim.dim() == 3 else vlim.expand(B, dof, 2).contiguous())
@@ -152,6 +170,10 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     torch = torch_mod()
     B, G, W = records.shape
     dev = records.device
+    if grid.dim() not in (1, 2) or grid.shape[-1] != G or (grid.dim() == 2 and grid.shape[0] != B):
+        raise ValueError("gridpoints must have shape (%d,) or (%d, %d); got %s" % (G, B, G, tuple(grid.shape)))
+    for t, what in ((sd_start, "sd_start"), (sd_end, "sd_end"), (sd_end_hi, "sd_end_hi")):
+        check_path_vector(t, B, what)
     if forward_from is not None:  # forward pass alone on the K / status of an earlier backward-only launch
         K, status, fail_stage = forward_from["K"], forward_from["status"], forward_from["fail_stage"]
     else:
@@ -330,6 +352,9 @@ def xbound_varying(ppoly, breaks, grid, vlim_grid, records, R_total, write_xboun
     B, _, nseg, dof = ppoly.shape
     G = grid.shape[-1]
     W = records.shape[-1]
+    check_grid_shapes(B, breaks, nseg + 1, grid, G)
+    if tuple(vlim_grid.shape[-3:]) != (G, dof, 2) or vlim_grid.dim() not in (3, 4) or (vlim_grid.dim() == 4 and vlim_grid.shape[0] != B):
+        raise ValueError("varying velocity limits must have shape (G, dof, 2) or (B, G, dof, 2); got %s" % (tuple(vlim_grid.shape),))
     with torch.cuda.device(records.device):
         rc = _lib.load().tb_xbound_varying(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg, dof,
                                            _lib.ptr(grid), 1 if grid.dim() == 1 else 0, G, _lib.ptr(vlim_grid),

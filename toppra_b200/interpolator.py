@@ -119,7 +119,7 @@ class BatchSplineInterpolator(object):
 
     `ss_waypoints` / `waypoints` may be numpy arrays (copied H2D here) or CUDA tensors (used in place)."""
 
-    def __init__(self, ss_waypoints, waypoints, bc_type="not-a-knot", device=None):
+    def __init__(self, ss_waypoints, waypoints, bc_type="not-a-knot", device=None, validate=True):
         torch = engine.torch_mod()
         self.device = engine.default_device(device if device is not None else
                                             (waypoints.device if isinstance(waypoints, torch.Tensor) else None))
@@ -128,10 +128,19 @@ class BatchSplineInterpolator(object):
             raise ValueError("waypoints must have shape (B, n, dof)")
         self.B, self.n, self._dof = self.d_wp.shape
         self.d_ss = engine.as_device(ss_waypoints, self.device)
-        if self.d_ss.shape[-1] != self.n or self.d_ss.dim() not in (1, 2):
+        if self.d_ss.shape[-1] != self.n or self.d_ss.dim() not in (1, 2) or (self.d_ss.dim() == 2 and
+                                                                           self.d_ss.shape[0] != self.B):
             raise ValueError("ss_waypoints must have shape (n,) or (B, n)")
         if self.n < 2:
             raise ValueError("at least 2 waypoints are needed")
+        if validate:
+            # scipy CubicSpline raises "`x` must be strictly increasing sequence."; dx = 0 would give inf/NaN here
+            if isinstance(ss_waypoints, torch.Tensor):
+                increasing = not bool((self.d_ss[..., 1:] <= self.d_ss[..., :-1]).any())
+            else:
+                increasing = bool(np.all(np.diff(np.asarray(ss_waypoints, dtype=np.float64), axis=-1) > 0))
+            if not increasing:
+                raise ValueError("`ss_waypoints` must be a strictly increasing sequence.")
         self.bc_type = bc_type
         bc = engine.parse_bc(bc_type, self.B, self._dof, self.device)
         self.d_ppoly = engine.spline_fit(self.d_ss, self.d_wp, bc)
