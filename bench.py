@@ -282,7 +282,8 @@ def run_b200(args):
     h_out = {"K": torch.empty((B, G, 2), dtype=torch.float64).pin_memory(),
              "sd": torch.empty((B, G), dtype=torch.float64).pin_memory(),
              "sdd": torch.empty((B, G - 1), dtype=torch.float64).pin_memory(),
-             "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
+             "status": torch.empty((B,), dtype=torch.int32).pin_memory(),
+             "fail_stage": torch.empty((B,), dtype=torch.int32).pin_memory()}
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
     W = engine.record_doubles(R)
     records = torch.empty((B, G, W), dtype=torch.float64, device=dev)
@@ -293,29 +294,54 @@ def run_b200(args):
 
     scan_mode = {"fast_lower": False}
 
+    xbound = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+
     def step_device(record_kernels=False):
-        """Hot path with inputs resident in HBM: 3 kernel launches (K0, K1, K2)."""
+        """Hot path with inputs resident in HBM: 3 kernel launches: K0 spline fit, K1 velocity bound (xbound only),
+        K2 scan with the acceleration rows built inside the kernel (tb_scan_velacc: K1's record stream fused away)."""
         e = [ev() for _ in range(4)] if record_kernels else None
         if e: e[0].record()
         ppoly = engine.spline_fit(d_ss, d_way)
         if e: e[1].record()
-        engine.coeff_velacc(ppoly, d_ss, d_grid, d_vlim, d_alim, True, records, R, 0, 1)
+        engine.xbound_constant(ppoly, d_ss, d_grid, d_vlim, xbound, 0, 1)
         if e: e[2].record()
-        out = engine.scan(records, R, d_grid, fast_lower=scan_mode["fast_lower"])
+        out = engine.scan_velacc(ppoly, d_ss, d_grid, d_alim, True, xbound, fast_lower=scan_mode["fast_lower"])
         if e:
             e[3].record()
             k_events.append(e)
         return out
 
+    rec_events = []
+
+    def step_records():
+        """The same problem through materialised stage records (K0 -> K1 records -> K2 record scan): what generic
+        constraint lists use; timed for the K1 / K2 rooflines of that path, not part of `value`."""
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        ppoly = engine.spline_fit(d_ss, d_way)
+        e[1].record()
+        engine.coeff_velacc(ppoly, d_ss, d_grid, d_vlim, d_alim, True, records, R, 0, 1)
+        e[2].record()
+        out = engine.scan(records, R, d_grid)
+        e[3].record()
+        rec_events.append(e)
+        return out
+
     # the e2e step builds constraint objects from host limit arrays each step (their H2D copy is part of the step)
+    e2e_mode = {"sync": False}
+
     def step_e2e_full():
-        path = ta.BatchSplineInterpolator(h_ss.to(dev, non_blocking=True), h_way.to(dev, non_blocking=True), device=dev)
+        # the public API with HOST inputs (pinned tensors): the H2D copies happen inside the constructors; inputs are
+        # validated on the host (no device synchronisation)
+        path = ta.BatchSplineInterpolator(h_ss, h_way, device=dev)
         pc_vel = ta.constraint.JointVelocityConstraint(vlim)
         pc_acc = ta.constraint.JointAccelerationConstraint(alim)
         pc_vel._d_cache[str(dev)] = h_vlim.to(dev, non_blocking=True)
         pc_acc._d_cache[str(dev)] = h_alim.to(dev, non_blocking=True)
-        inst = ta.BatchTOPPRA([pc_vel, pc_acc], path, h_grid.to(dev, non_blocking=True))
-        inst.solve_to_host(0.0, 0.0, pinned=h_out)  # K leaves on a copy stream while the forward pass runs
+        inst = ta.BatchTOPPRA([pc_vel, pc_acc], path, h_grid)
+        # K leaves on a copy stream while the forward pass runs; sync=False: pipelined caller, the pinned buffers are
+        # valid at inst.host_ready (all copies are still inside the timed region); sync=True: host waits every step
+        inst.solve_to_host(0.0, 0.0, pinned=h_out, sync=e2e_mode["sync"])
         if world > 1:
             dist.all_gather_into_tensor(gathered, inst.last_result.sd)  # NCCL: gather the result velocities
         return inst
@@ -351,16 +377,19 @@ def run_b200(args):
         sampler.start()
         del k_events[:]
         a = timed(step_device, args.steps, max(args.warmup, 3), record_kernels=True)
+        e2e_mode["sync"] = False
         b = timed(step_e2e_full, args.steps, max(args.warmup, 3))
+        e2e_mode["sync"] = True
+        c = timed(step_e2e_full, args.steps, max(args.warmup, 3))
         sampler.stop_flag = True
         sampler.join(timeout=1.0)
-        return a, b, sampler.summary()
+        return a, b, c, sampler.summary()
 
-    ms_dev, ms_e2e, clocks = measure()
+    ms_dev, ms_e2e, ms_e2e_sync, clocks = measure()
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if bad & set(clocks.get("reasons", [])):  # throttled: take the measurement again, once
         clocks_first = clocks
-        ms_dev, ms_e2e, clocks = measure()
+        ms_dev, ms_e2e, ms_e2e_sync, clocks = measure()
         clocks["remeasured_after"] = clocks_first
 
     # opt-in mode (BatchTOPPRA(exact=False), TB_SCAN_FAST_LOWER): reported beside the headline, never instead of it
@@ -408,7 +437,7 @@ def run_b200(args):
                "algorithmic_bytes_per_launch": bytes_k1, "ms_per_launch": k1}
 
     h2d = int(h_way.numel() + h_vlim.numel() + h_alim.numel() + h_ss.numel() + h_grid.numel()) * 8
-    d2h = int(h_out["K"].numel() + h_out["sd"].numel() + h_out["sdd"].numel()) * 8 + int(h_out["status"].numel()) * 4
+    d2h = int(h_out["K"].numel() + h_out["sd"].numel() + h_out["sdd"].numel()) * 8 + int(h_out["status"].numel()) * 8
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -419,8 +448,11 @@ def run_b200(args):
                    "l2": "256 MB buffer written between timed iterations (L2 flush)", "ok_paths_last_step": n_ok},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
-                "api": "BatchSplineInterpolator + BatchTOPPRA.solve_to_host (backward launch, K D2H overlapped with "
-                       "the forward launch), pinned host buffers"
+                "host_sync_every_step": {"value": total_paths * args.steps / (ms_e2e_sync * 1e-3), "unit": UNIT,
+                                         "ms_per_step": ms_e2e_sync / args.steps},
+                "api": "BatchSplineInterpolator + BatchTOPPRA.solve_to_host(sync=False) with pinned HOST inputs and "
+                       "outputs (backward launch, K D2H overlapped with the forward launch; results valid at "
+                       "inst.host_ready); host_sync_every_step = the same call with sync=True"
                        + (", NCCL all_gather of sd" if world > 1 else "")},
         "gpu_launches": 3 * args.steps,
         "kernels_ms": {"K0_spline_fit": k0, "K1_coeff": k1, "K2_scan": k2},

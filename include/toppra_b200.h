@@ -117,6 +117,14 @@ int tb_xbound_varying(const double *ppoly, const double *breaks, int breaks_shar
                       const double *grid, int grid_shared, int G, const double *vlim_grid, int vlim_shared,
                       double *records, int W, int R_total, int write_xbound, void *stream);
 
+/* JointVelocityConstraint alone (linear_joint_velocity.py:43-53, _CythonUtils.pyx:16-59): the velocity bound of every
+ * gridpoint into the xbound slots, one thread per (path, gridpoint), no acceleration rows.  vlim [dof][2] (lim_shared=1)
+ * or [B][dof][2]; write_xbound 1/2/3 as in tb_coeff_velacc.  With W = 2, R_total = 0 the output is the plain
+ * xbound [B][G][2] array that tb_scan_velacc reads. */
+int tb_xbound_velocity(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                       const double *grid, int grid_shared, int G, const double *vlim, int lim_shared, double *records,
+                       int W, int R_total, int write_xbound, void *stream);
+
 /* Row assembly for a generic CanonicalLinear constraint given its collocation parameters:
  *   a, b, c: [B][G][m];  F: [k][m] (F_mode=0, identical) or [B][G][k][m] (F_mode=1);
  *   g: [k] / [B][G][k];  F_mode=2: F = [I; -I] (k = 2m) with g: [k] shared (torque-limit form);
@@ -174,6 +182,18 @@ int tb_feasible_sets(const double *records, int W, int R, const double *grid, in
 int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,
                double *u, int *status, int *fail_stage, int *counters, void *stream);
+
+/* K2 fused with K1 for the JointVelocity + JointAcceleration problem (the headline case): no stage records at all.
+ * Every lane of the path's warp builds its own LP row in the stage prologue from the spline (same arithmetic as
+ * tb_coeff_velacc, so the rows are bit-identical to the materialised records); only the velocity bound comes from
+ * memory:  xbound [B][G][2] = tb_coeff_velacc(..., alim = NULL, records = xbound, W = 2, R_total = 0, row0 = 0,
+ * write_xbound = 1).  Same passes, flags and outputs as tb_scan_ex.  Returns TB_ERR_UNSUPPORTED when the problem does
+ * not fit one row per lane ((interp ? 4 : 2) * dof + 2 > 32) or the spline has too many segments; the caller then
+ * uses tb_coeff_velacc + tb_scan.  Replaces the same reference functions as tb_coeff_velacc + tb_scan. */
+int tb_scan_velacc(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof, const double *grid,
+                   int grid_shared, int B, int G, const double *alim, int lim_shared, int interp, const double *xbound,
+                   const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                   double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream);
 
 /* Stand-alone batched LPs, one warp per LP — device counterparts of the reference's Python shims
  * solve_lp2d / solve_lp1d (cy_seidel_solverwrapper.pyx:42-87).

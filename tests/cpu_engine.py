@@ -210,6 +210,23 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     return out
 
 
+def xbound_constant(ppoly, breaks, grid, vlim, records, R_total, write_xbound):
+    coeff_velacc(ppoly, breaks, grid, vlim, None, False, records, R_total, 0, write_xbound)
+
+
+def scan_velacc(ppoly, breaks, grid, alim, interp, xbound, sd_start=None, sd_end=None, sd_end_hi=None,
+                backward_only=False, counters=False, sd_forward=None, forward_from=None, fast_lower=False):
+    """Double of the fused vel+acc scan: materialise the acceleration rows with the K1 double, take the velocity bound
+    from `xbound`, run the record scan."""
+    B, _, nseg, dof = ppoly.shape
+    G = grid.shape[-1]
+    R = (4 if interp else 2) * dof
+    rec, _ = alloc_records(B, G, R, None)
+    coeff_velacc(ppoly, breaks, grid, None, alim, interp, rec, R, 0, 0)
+    rec[:, :, 3 * R:3 * R + 2] = xbound
+    return scan(rec, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters, sd_forward, forward_from, fast_lower)
+
+
 def _scan_sd(records, R, grid, sd_start, sd_end, slow):
     """TOPPRAsd passes (desired_duration_algorithm.py:42-121, 207-234): controllable sets, then a forward pass with no
     retry rule and x_next = clip(x + 2 delta u - 1e-5, K[i+1]); fastest: g = (-2 delta, -1), slowest: g = (2 delta, 1).
@@ -341,7 +358,7 @@ class _NoStream(object):
 
 
 PATCHED = ("spline_fit", "ppoly_eval", "record_doubles", "alloc_records", "init_bounds", "coeff_velacc",
-           "rows_canlinear", "xbound_varying", "scan", "scan_robust", "feasible_sets", "lp2d_batch", "lp1d_batch",
+           "rows_canlinear", "xbound_varying", "xbound_constant", "scan", "scan_velacc", "scan_robust", "feasible_sets", "lp2d_batch", "lp1d_batch",
            "time_grid", "constaccel_eval")
 
 

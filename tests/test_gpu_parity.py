@@ -151,6 +151,14 @@ def test_batch_cases_bit_exact(ta, golden, case):
     assert _eq(h["status"], g["status"])
     assert _eq(h["K"], g["K"]) and _eq(h["sd"], g["sd"]) and _eq(h["sdd"], g["sdd"])
     R = inst.R
+    assert inst.fused and inst.records is None  # vel+acc: rows are built inside the scan, only xbound is materialised
+    assert _eq(inst.xbound.cpu().numpy(), np.stack((np.maximum(-1e8, g["xbound"][:, :, 0]),
+                                                     np.minimum(1e8, g["xbound"][:, :, 1])), axis=-1))
+    # the same problem through materialised stage records (K1 -> K2): identical results, records == reference rows
+    inst = ta.BatchTOPPRA(_cons(ta, g), path, g["grid"], fused=False)
+    h2 = inst.compute_parameterization(float(g["sd_start"]), float(g["sd_end"])).to_host()
+    for key in ("status", "K", "sd", "sdd"):
+        assert _eq(h2[key], h[key]), key
     rec = inst.records.cpu().numpy()
     assert _eq(rec[:, :, 3 * R], np.maximum(-1e8, g["xbound"][:, :, 0]))
     assert _eq(rec[:, :, 3 * R + 1], np.minimum(1e8, g["xbound"][:, :, 1]))

@@ -86,7 +86,8 @@ def test_large_batch_properties(ta):
 
 
 def test_chunked_solve_equals_single_launch(ta):
-    """Batches whose records exceed the budget run chunk by chunk through one record buffer: identical bits."""
+    """Batches whose records exceed the budget run chunk by chunk through one record buffer (fused=False: materialised
+    stage records): identical bits to the single fused launch (rows built inside the scan)."""
     import torch
     B, G = 1000, 120
     ss, way, vlim, alim = make_batch_fast(B, seed=5)
@@ -95,7 +96,7 @@ def test_chunked_solve_equals_single_launch(ta):
     cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)]
     full = ta.BatchTOPPRA(cons, path, grid).compute_parameterization(0.0, 0.0)
     per_path = 8 * 86 * G
-    inst = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=per_path * 96 + 7)   # 96 paths per chunk, ragged tail
+    inst = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=per_path * 96 + 7, fused=False)   # 96 paths per chunk, ragged tail
     assert inst.chunk_size() == 96
     part = inst.compute_parameterization(0.0, 0.0)
     for key in ("K", "sd", "sdd", "status"):
@@ -103,7 +104,7 @@ def test_chunked_solve_equals_single_launch(ta):
     # per-path boundary speeds are sliced with the chunks
     s0 = np.where(np.arange(B) % 2 == 0, 0.0, 0.05)
     a = ta.BatchTOPPRA(cons, path, grid).compute_parameterization(s0, 0.0)
-    b = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=per_path * 96).compute_parameterization(s0, 0.0)
+    b = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=per_path * 96, fused=False).compute_parameterization(s0, 0.0)
     assert torch.equal(a.sd, b.sd) and torch.equal(a.status, b.status)
     assert float(a.sd[1, 0]) == 0.05 and float(a.sd[0, 0]) == 0.0
 
@@ -115,10 +116,16 @@ def test_cfg5_shard_size_chunked(ta):
     grid = np.linspace(0, 1, G)
     path = ta.BatchSplineInterpolator(ss, way)
     cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)]
-    inst = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=4 << 30)
+    inst = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=4 << 30, fused=False)
     assert inst.chunk_size() < B
     res = inst.compute_parameterization(0.0, 0.0)
     assert int((res.status != 0).sum()) == 0
+    import torch
+    one = ta.BatchTOPPRA(cons, path, grid)   # fused scan: the whole shard in ONE launch, no record buffer
+    assert one.fused and one.chunk_size() == B
+    res1 = one.compute_parameterization(0.0, 0.0)
+    for key in ("K", "sd", "sdd", "status"):
+        assert torch.equal(getattr(res, key), getattr(res1, key)), key
     assert bool((res.sd[:, 0] == 0).all()) and bool((res.sd[:, -1] == 0).all()) and bool((res.sd[:, 1:-1] > 0).all())
     x = res.sd * res.sd
     assert bool((x <= res.K[:, :, 1] * (1 + 1e-12) + 1e-15).all())

@@ -71,7 +71,7 @@ def test_chunked_batch_equals_single_launch_on_cpu(monkeypatch):
     cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)]
     one = ta.BatchTOPPRA(cons, path, grid).compute_parameterization(0.0, 0.0).to_host()
     W = ta.engine.record_doubles(28)
-    many = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=5 * G * W * 8).compute_parameterization(0.0, 0.0).to_host()
+    many = ta.BatchTOPPRA(cons, path, grid, max_record_bytes=5 * G * W * 8, fused=False).compute_parameterization(0.0, 0.0).to_host()
     for k in ("K", "sd", "sdd", "status"):
         assert np.array_equal(one[k], many[k]), k
     assert not one["status"].any()

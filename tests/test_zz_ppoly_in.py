@@ -73,7 +73,7 @@ def test_batch_from_ppoly(ta, golden):
     # per-path breaks, chunked solve
     bp2 = ta.BatchSplineInterpolator.from_ppoly(np.tile(g["ss"], (16, 1)), g["c"])
     W = ta.engine.record_doubles(28)
-    chunked = ta.BatchTOPPRA(_cons(ta, g), bp2, g["grid"], max_record_bytes=5 * len(g["grid"]) * W * 8)
+    chunked = ta.BatchTOPPRA(_cons(ta, g), bp2, g["grid"], max_record_bytes=5 * len(g["grid"]) * W * 8, fused=False)
     h2 = chunked.compute_parameterization(0.0, 0.0).to_host()
     assert np.array_equal(h2["K"], g["K"]) and np.array_equal(h2["sd"], g["sd"])
     for bad in (g["c"][0], np.zeros((2, 5, 4, 7))):

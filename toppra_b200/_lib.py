@@ -24,6 +24,8 @@ _PROTOS = {
                          _int, _int, _int, _int, ctypes.c_void_p], _int),
     "tb_xbound_varying": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _int, _c_dp, _int, _int, _int,
                            ctypes.c_void_p], _int),
+    "tb_xbound_velocity": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _int, _c_dp, _int, _int, _int,
+                            ctypes.c_void_p], _int),
     "tb_rows_canlinear": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp,
                            _int, _int, _int, ctypes.c_void_p], _int),
     "tb_init_bounds": ([_c_dp, _int, _int, _int, _int, ctypes.c_void_p], _int),
@@ -31,6 +33,8 @@ _PROTOS = {
                  ctypes.c_void_p], _int),
     "tb_scan_ex": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, _c_dp, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_ip,
                     _c_ip, _c_ip, ctypes.c_void_p], _int),
+    "tb_scan_velacc": ([_c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _int, _int, _c_dp, _int, _int, _c_dp, _c_dp, _c_dp,
+                        _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_ip, _c_ip, _c_ip, ctypes.c_void_p], _int),
     "tb_lp2d_batch": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_ip, _int, _int, _c_ip, _c_dp, _c_dp, _c_ip,
                        ctypes.c_void_p], _int),
     "tb_lp1d_batch": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _c_ip, _c_dp, _c_dp, _c_ip, ctypes.c_void_p],

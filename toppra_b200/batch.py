@@ -108,31 +108,33 @@ class BatchTOPPRA(object):
     gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
     """
 
-    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30, exact=True, validate=True):
+    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30, exact=True, validate=True,
+                 fused=None):
         if not isinstance(path, BatchSplineInterpolator):
             raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
         torch = engine.torch_mod()
         self.constraints = constraint_list
         self.path = path
         self.device = path.device
-        grid_host = None
-        if not isinstance(gridpoints, torch.Tensor):
-            gp = np.ascontiguousarray(gridpoints, dtype=np.float64)
-            if gp.ndim == 1:
-                grid_host = gp
-            if np.any(np.diff(gp, axis=-1) <= 0):
-                raise ValueError("Bad input gridpoints.")
+        gp = engine.host_view(gridpoints)  # None for CUDA tensors
+        grid_host = gp if (gp is not None and gp.ndim == 1) else None
         self.d_grid = engine.as_device(gridpoints, self.device)
         if self.d_grid.dim() not in (1, 2) or (self.d_grid.dim() == 2 and self.d_grid.shape[0] != path.B):
             raise ValueError("gridpoints must have shape (G,) or (B, G)")
         if validate:
-            # reference algorithm.py:107-120: gridpoints must be increasing and span exactly the path interval
-            # ("Invalid manually supplied gridpoints."); one small device reduction per setup
-            g, ss = self.d_grid, path.d_ss
-            code = ((g[..., 0] != ss[..., 0]).any() | (g[..., -1] != ss[..., -1]).any()).to(torch.int32)
-            if g.shape[-1] > 1:
-                code = code + 2 * (g[..., 1:] <= g[..., :-1]).any().to(torch.int32)
-            code = int(code)
+            # reference algorithm.py:107-120: gridpoints must span exactly the path interval ("Invalid manually supplied
+            # gridpoints.") and increase strictly ("Bad input gridpoints.").  Host data is checked on the host (no
+            # device synchronisation); CUDA tensors with one small reduction.
+            ss_host = getattr(path, "ss_host", None)
+            if gp is not None and ss_host is not None:
+                code = int(np.any(gp[..., 0] != ss_host[..., 0]) or np.any(gp[..., -1] != ss_host[..., -1]))
+                code += 2 * int(np.any(np.diff(gp, axis=-1) <= 0))
+            else:
+                g, ss = self.d_grid, path.d_ss
+                t = ((g[..., 0] != ss[..., 0]).any() | (g[..., -1] != ss[..., -1]).any()).to(torch.int32)
+                if g.shape[-1] > 1:
+                    t = t + 2 * (g[..., 1:] <= g[..., :-1]).any().to(torch.int32)
+                code = int(t)
             if code & 1:
                 raise ValueError("Invalid manually supplied gridpoints.")
             if code & 2:
@@ -155,6 +157,17 @@ class BatchTOPPRA(object):
         self.exact = bool(exact)
         self._grid_host = grid_host
         self.conic = conic_info(self.ctx, self.constraints)
+        # JointVelocity (optional) + JointAcceleration: the scan builds the LP rows itself from the spline
+        # (tb_scan_velacc, K1 fused into K2): no stage records, no chunking.  fused=False forces the record path.
+        kinds = [type(c) for c in constraint_list]
+        self.fused = (fused is not False and sorted(k.__name__ for k in kinds) in
+                      (["JointAccelerationConstraint"], ["JointAccelerationConstraint", "JointVelocityConstraint"])
+                      and engine.velacc_fused_supported(path.nseg, path.dof,
+                                                        constraint_list[kinds.index(JointAccelerationConstraint)].interpolation))
+        if fused and not self.fused:
+            raise ValueError("fused=True needs a [JointVelocityConstraint,] JointAccelerationConstraint problem that fits "
+                             "one LP row per lane (see tb_scan_velacc)")
+        self.xbound = None
 
     @property
     def B(self):
@@ -165,9 +178,42 @@ class BatchTOPPRA(object):
         return self.d_grid.shape[-1]
 
     def setup(self):
-        """K1: constraint coefficients -> stage records (done once; reused by every solve)."""
+        """K1: constraint coefficients -> stage records (done once; reused by every solve).  Fused vel+acc problems
+        only need the velocity bound xbound [B, G, 2]."""
+        if self.fused:
+            kinds = [type(c) for c in self.constraints]
+            acc = self.constraints[kinds.index(JointAccelerationConstraint)]
+            vel = self.constraints[kinds.index(JointVelocityConstraint)] if JointVelocityConstraint in kinds else None
+            for c in self.constraints:
+                if self.path.dof != c.get_dof():
+                    raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
+                        c.get_dof(), self.path.dof))
+            self._alim = acc.device_limits(self.device)
+            self._interp = acc.interpolation
+            self.R = acc.num_rows(self.ctx)
+            self.xbound = engine.xbound_velocity(self.path.d_ppoly, self.path.d_ss, self.d_grid,
+                                                 None if vel is None else vel.device_limits(self.device))
+            return self.xbound
         self.records, self.R = build_records(self.ctx, self.constraints)
         return self.records
+
+    def _ready(self):
+        if (self.xbound if self.fused else self.records) is None:
+            self.setup()
+
+    def _scan(self, s0, s1, sd_end_hi=None, **kw):
+        """One scan launch over the whole batch on whatever row source this problem uses."""
+        self._ready()
+        if self.fused:
+            return engine.scan_velacc(self.path.d_ppoly, self.path.d_ss, self.d_grid, self._alim, self._interp,
+                                      self.xbound, s0, s1, sd_end_hi, fast_lower=not self.exact, **kw)
+        if self.conic is None:
+            return engine.scan(self.records, self.R, self.d_grid, s0, s1, sd_end_hi, fast_lower=not self.exact, **kw)
+        if sd_end_hi is not None:
+            raise NotImplementedError("robust problems: compute_controllable_sets needs sdmin == sdmax")
+        kw.pop("forward_from", None)
+        return engine.scan_robust(self.records, self.R, self.conic[0], self.conic[1], self.conic[2], self.d_grid, s0, s1,
+                                  kw.get("backward_only", False), kw.get("counters", False))
 
     def _vel_tensor(self, v):
         if v is None:
@@ -201,12 +247,14 @@ class BatchTOPPRA(object):
                 pinned[key] = torch.empty(shape, dtype=dt).pin_memory()
         return pinned
 
-    def solve_to_host(self, sd_start=0.0, sd_end=0.0, pinned=None):
+    def solve_to_host(self, sd_start=0.0, sd_end=0.0, pinned=None, sync=True):
         """compute_parameterization + copy of (K, sd, sdd, status, fail_stage) to pinned host memory, with the D2H
         copy of K overlapped with the forward pass: the scan runs as a backward-only and a forward-only launch and K
         leaves on a second stream in between.  Returns the dict of pinned host TENSORS (same keys and types for every
-        problem kind: chunked and robust problems take the plain path); the host is synchronised before returning,
-        so the buffers are valid on return."""
+        problem kind: chunked and robust problems take the plain path).  sync=True (default): the host waits for the
+        copies, the buffers are valid on return.  sync=False (pipelined callers): nothing is waited for; the buffers
+        are valid once `self.host_ready` (a CUDA event recorded after the last copy) has completed —
+        `inst.host_ready.synchronize()`."""
         torch = engine.torch_mod()
         pinned = self._pinned_outputs(pinned)
         main = torch.cuda.current_stream(self.device)
@@ -215,20 +263,21 @@ class BatchTOPPRA(object):
             for key in pinned:
                 pinned[key].copy_(getattr(res, key), non_blocking=True)
             self.last_result = res
-            main.synchronize()
+            self.host_ready = torch.cuda.Event()
+            self.host_ready.record(main)
+            if sync:
+                self.host_ready.synchronize()
             return pinned
-        if self.records is None:
-            self.setup()
         s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-        back = engine.scan(self.records, self.R, self.d_grid, s0, s1, backward_only=True, fast_lower=not self.exact)
+        back = self._scan(s0, s1, backward_only=True)
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(ev)
             pinned["K"].copy_(back["K"], non_blocking=True)
-        fwd = engine.scan(self.records, self.R, self.d_grid, s0, s1, forward_from=back)
+        fwd = self._scan(s0, s1, forward_from=back)
         pinned["sd"].copy_(fwd["sd"], non_blocking=True)
         pinned["sdd"].copy_(fwd["u"], non_blocking=True)
         pinned["status"].copy_(fwd["status"], non_blocking=True)
@@ -236,11 +285,16 @@ class BatchTOPPRA(object):
         main.wait_stream(self._copy_stream)   # the step is complete (for events / callers) when K has landed too
         back["K"].record_stream(self._copy_stream)
         self.last_result = BatchResult(fwd)
-        main.synchronize()                    # host-visible: every copy above has landed
+        self.host_ready = torch.cuda.Event()
+        self.host_ready.record(main)
+        if sync:
+            self.host_ready.synchronize()     # host-visible: every copy above has landed
         return pinned
 
     def chunk_size(self):
         """Paths per chunk so that the record buffer stays within max_record_bytes."""
+        if self.fused:
+            return self.B  # no stage records
         rows = sum(c.num_rows(self.ctx) for c in self.constraints)
         per_path = 8 * engine.record_doubles(rows) * self.G
         return max(1, min(self.B, self.max_record_bytes // per_path))
@@ -252,10 +306,7 @@ class BatchTOPPRA(object):
         s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
         nchunk = self.chunk_size()
         if nchunk >= self.B:
-            if self.records is None:
-                self.setup()
-            return BatchResult(scan_any(self.records, self.R, self.d_grid, self.conic, s0, s1, counters=counters,
-                                        fast_lower=not self.exact))
+            return BatchResult(self._scan(s0, s1, counters=counters))
         B, G, dev = self.B, self.G, self.device
         out = dict(K=torch.empty((B, G, 2), dtype=torch.float64, device=dev),
                    sd=torch.empty((B, G), dtype=torch.float64, device=dev),
@@ -282,19 +333,17 @@ class BatchTOPPRA(object):
 
     def compute_controllable_sets(self, sdmin, sdmax):
         """K[B,G,2] with K[N] = [sdmin^2, sdmax^2] (reference reachability_algorithm.py:166-202) and status."""
-        if self.records is None:
-            self.setup()
         lo = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmin, dtype=np.float64), (self.B,)))
         hi = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmax, dtype=np.float64), (self.B,)))
         assert np.all(lo <= hi) and np.all(0 <= lo)
         same = bool(np.all(lo == hi))
-        out = scan_any(self.records, self.R, self.d_grid, self.conic, None, engine.as_device(lo, self.device),
-                       None if same else engine.as_device(hi, self.device), backward_only=True)
+        out = self._scan(None, engine.as_device(lo, self.device), None if same else engine.as_device(hi, self.device),
+                         backward_only=True)
         return out["K"], out["status"]
 
     def compute_feasible_sets(self):
-        if self.records is None:
-            self.setup()
+        if self.records is None:  # feasible sets read stage records (also for problems whose scan is fused)
+            self.records, self.R = build_records(self.ctx, self.constraints)
         if self.conic is not None:
             return engine.scan_robust(self.records, self.R, self.conic[0], self.conic[1], self.conic[2], self.d_grid,
                                       feasible_sets=True)["K"]

@@ -280,7 +280,7 @@ __global__ void rows_canlinear_kernel(const double *__restrict__ a, const double
 __global__ void xbound_varying_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks,
                                       const int breaks_shared, const long B, const int nseg, const int dof,
                                       const double *__restrict__ grid, const int grid_shared, const int G,
-                                      const double *__restrict__ vlim_grid, const int vlim_shared,
+                                      const double *__restrict__ vlim_grid, const int vlim_shared, const int per_grid,
                                       double *__restrict__ records, const int W, const int R_total, const int mode) {
   const long total = B * G;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -289,7 +289,9 @@ __global__ void xbound_varying_kernel(const double *__restrict__ ppoly, const do
     const double *x = breaks + (breaks_shared ? 0 : p * (nseg + 1));
     const double *c = ppoly + p * 4 * nseg * dof;
     const double s = grid[(grid_shared ? 0 : p * G) + gi];
-    const double *vl = vlim_grid + ((vlim_shared ? 0 : p * G) + gi) * (long)dof * 2;
+    // per_grid: limits per gridpoint (JointVelocityConstraintVarying); else one (dof, 2) array per path / batch
+    const double *vl = per_grid ? vlim_grid + ((vlim_shared ? 0 : p * G) + gi) * (long)dof * 2
+                                : vlim_grid + (vlim_shared ? 0 : p) * (long)dof * 2;
     const int seg = find_interval(x, nseg, s);
     float sdmin = -(float)JVEL_MAXSD, sdmax = (float)JVEL_MAXSD;
     for (int k = 0; k < dof && seg >= 0; ++k) {
@@ -419,7 +421,26 @@ extern "C" int tb_xbound_varying(const double *ppoly, const double *breaks, int 
   long blocks = (total + threads - 1) / threads;
   if (blocks > 148L * 64) blocks = 148L * 64;
   xbound_varying_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, vlim_grid, vlim_shared, records, W, R_total,
+      ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, vlim_grid, vlim_shared, 1, records, W, R_total,
       write_xbound);
   return check_launch("tb_xbound_varying");
+}
+
+extern "C" int tb_xbound_velocity(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                                  const double *grid, int grid_shared, int G, const double *vlim, int lim_shared,
+                                  double *records, int W, int R_total, int write_xbound, void *stream) {
+  using namespace tb;
+  if (!ppoly || !breaks || !grid || !vlim || !records || B <= 0 || nseg <= 0 || dof <= 0 || G <= 0 || R_total < 0 ||
+      W < 3 * R_total + 2 || write_xbound < 1 || write_xbound > 3) {
+    set_error("tb_xbound_velocity: bad argument");
+    return TB_ERR_ARG;
+  }
+  const long total = (long)B * G;
+  const int threads = 128;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148L * 64) blocks = 148L * 64;
+  xbound_varying_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, vlim, lim_shared, 0, records, W, R_total,
+      write_xbound);
+  return check_launch("tb_xbound_velocity");
 }

@@ -451,29 +451,76 @@ __device__ __forceinline__ void set_xnext_rows(const int lane, const double delt
 
 // CFLAGS >= 0: the scan-mode bits of `flags` (backward-only, forward-only, TOPPRAsd rules) are this compile-time
 // constant (the argument is ignored), so the unused passes and rules and their bookkeeping fold away; -1: run time.
-template <int RPL, int WARPS, int MINB, bool FAST, int CFLAGS = -1>
+// Row source of the FUSED scan (tb_scan_velacc): JointVelocity + JointAcceleration problems need no stage records at
+// all — lane r builds its own LP row from the path's spline in the stage prologue, with the arithmetic of K1
+// (tb_coeff.cu: PPoly derivative evaluation like scipy, interpolation lift a+ = q'(s_{i+1}) + 2 delta q''(s_{i+1}),
+// c = -amax / +amin), so the rows are bit-identical to the materialised records; only the velocity bound
+// (xbound [B][G][2], 16 B per gridpoint instead of 8 (3R+2)) still comes from memory.
+struct VelAccSrc {
+  const double *ppoly;   // [B][4][nseg][dof]
+  const double *breaks;  // [nseg+1] or [B][nseg+1]
+  const double *alim;    // [dof][2] or [B][dof][2]
+  const double *xbound;  // [B][G][2]
+  int breaks_shared, nseg, dof, lim_shared;
+};
+
+template <int RPL, int WARPS, int MINB, bool FAST, int CFLAGS = -1, bool FUSED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
             const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
             const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags_arg,
             double *__restrict__ Kout, double *__restrict__ sdout, double *__restrict__ uout,
-            int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters) {
+            int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters,
+            const VelAccSrc src) {
+  static_assert(!FUSED || RPL == 1, "the fused row source holds one row per lane");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = (WARPS == 1) ? 0 : (int)(threadIdx.x >> 5), lane = (WARPS == 1) ? (int)threadIdx.x : (int)(threadIdx.x & 31);
   const long path = (long)blockIdx.x * WARPS + warp;
   if (path >= B) return;
-  double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * SCAN_NBUF * W;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double)) + warp * SCAN_NBUF;
+  // shared-memory plan per warp.  records: ring of SCAN_NBUF stage records + mbarriers; FUSED: derivative coefficients
+  // of the path's PPoly dco [nseg][dof][5] + breakpoints [nseg+1] (in W doubles; W = that size rounded up to even)
+  double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (FUSED ? 1 : SCAN_NBUF) * W;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * (FUSED ? 1 : SCAN_NBUF) * W * sizeof(double)) + warp * SCAN_NBUF;
   const int N = G - 1, nC = R + 2;
   const unsigned rec_bytes = (unsigned)(W * sizeof(double));
   // Per-path base pointers live in shared memory: under the 64-register cap the compiler otherwise rebuilds them
   // from blockIdx and the kernel parameters (a chain of 64-bit multiplies) at every use inside the stage loops.
   const void *volatile *sptr = reinterpret_cast<const void *volatile *>(
-      smem_raw + (size_t)WARPS * SCAN_NBUF * W * sizeof(double) + (size_t)WARPS * SCAN_NBUF * sizeof(uint64_t)) + warp * 4;
+      smem_raw + (size_t)WARPS * (FUSED ? 1 : SCAN_NBUF) * W * sizeof(double) + (size_t)WARPS * SCAN_NBUF * sizeof(uint64_t)) + warp * 4;
   if (lane == 0) {
-    sptr[0] = records + (size_t)path * G * W;
+    sptr[0] = FUSED ? static_cast<const void *>(src.xbound + (size_t)path * G * 2)
+                    : static_cast<const void *>(records + (size_t)path * G * W);
     sptr[1] = grid + (grid_shared ? 0 : (size_t)path * G);
     sptr[2] = Kout + (size_t)path * G * 2;
+  }
+  // FUSED: this lane's row.  LP row r = lane: r - 2 = blk * dof + k; blk & 1: the negated copy (F = [I; -I]);
+  // blk >> 1: the lifted block evaluated at s_{i+1} (canlinear_colloc_to_interpolate, linear_constraint.py:84-192)
+  const double *dco = bufs, *sx = bufs + (FUSED ? src.nseg * src.dof * 6 : 0);
+  bool f_isrow = false, f_neg = false;
+  int f_second = 0, f_k = 0, f_seg = 0;
+  double f_c = -1.0;
+  if constexpr (FUSED) {
+    const int nseg = src.nseg, dof = src.dof;
+    const double *cpp = src.ppoly + (size_t)path * 4 * nseg * dof;
+    const double *xb = src.breaks + (src.breaks_shared ? 0 : (size_t)path * (nseg + 1));
+    double *dco_w = bufs, *sx_w = bufs + nseg * dof * 6;
+    for (int q = lane; q < nseg * dof; q += 32) {
+      // scipy PPoly.derivative: c'[j] = c[j] * (k - j); cspldd = cspld.derivative() (interpolator.py:419-421)
+      const double c0 = cpp[q], c1 = cpp[nseg * dof + q], c2 = cpp[2 * nseg * dof + q];
+      const double d0 = c0 * 3.0, d1 = c1 * 2.0, d2 = c2 * 1.0;
+      double *o = dco_w + q * 6;  // 48-byte entries: three 16-byte shared loads per evaluation
+      o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d0 * 2.0; o[4] = d1 * 1.0; o[5] = 0.0;
+    }
+    for (int q = lane; q <= nseg; q += 32) sx_w[q] = xb[q];
+    const int rr = lane - 2;
+    f_isrow = (lane >= 2) && (lane < nC);
+    const int blk = f_isrow ? rr / dof : 0;
+    f_k = f_isrow ? rr - blk * dof : 0;
+    f_neg = (blk & 1) != 0;
+    f_second = blk >> 1;
+    const double *al = src.alim + (src.lim_shared ? 0 : (size_t)path * dof * 2);
+    // F.c - g with c = 0, g = [amax; -amin] (tb_coeff.cu phase 1b)
+    f_c = f_isrow ? (f_neg ? (0.0 - (-al[f_k * 2 + 0])) : (0.0 - al[f_k * 2 + 1])) : -1.0;
   }
   __syncwarp();
   auto rec_path = [&]() { return static_cast<const double *>(sptr[0]); };
@@ -488,7 +535,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
   double *up = backward_only ? nullptr : uout + (size_t)path * (G > 1 ? G - 1 : 0);
 
-  if (lane == 0) {
+  if (!FUSED && lane == 0) {
 #pragma unroll
     for (int q = 0; q < SCAN_NBUF; ++q) mbar_init(&bars[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -501,7 +548,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   unsigned n_issued = 0, n_waited = 0;
   const uint32_t bufs_s = smem_u32(bufs), bars_s = smem_u32(bars);
   auto issue = [&](int stage) {
-    if (lane == 0) {
+    if (!FUSED && lane == 0) {
       const unsigned q = n_issued % SCAN_NBUF;
       mbar_expect_tx_s(bars_s + q * 8u, rec_bytes);
       bulk_g2s_s(bufs_s + q * rec_bytes, rec_path() + (size_t)stage * W, rec_bytes, bars_s + q * 8u);
@@ -510,11 +557,37 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   };
   auto acquire = [&]() -> const double * {
     const unsigned q = n_waited % SCAN_NBUF;
-    mbar_wait_s(bars_s + q * 8u, (n_waited / SCAN_NBUF) & 1);
+    if (!FUSED) mbar_wait_s(bars_s + q * 8u, (n_waited / SCAN_NBUF) & 1);
     ++n_waited;
     return bufs + (size_t)q * W;
   };
   constexpr int AHEAD = SCAN_NBUF - 1;
+  // FUSED: this lane's row of stage i = K1's arithmetic (tb_coeff.cu phases 1, 1b) at the lane's own gridpoint
+  // `s0`, `s1` = gridpoints i, i+1 (already loaded for delta).  The segment index of scipy's find_interval —
+  // max{j <= nseg-1 : x[j] <= s}, 0 below the first breakpoint — is monotone in s, so it is carried from stage to
+  // stage (DOWN in the backward pass, up in the forward pass) instead of searched: one comparison per stage.  A NaN
+  // gridpoint leaves the index alone and poisons ds, so the row is NaN like K1's.
+  auto fused_row = [&](const double s0, const double s1, const bool down, const double delta, double &ra, double &rb,
+                       double &rc) {
+    const double s = f_second ? s1 : s0;
+    if (down) { while (f_seg > 0 && s < sx[f_seg]) --f_seg; }
+    else { while (f_seg < src.nseg - 1 && s >= sx[f_seg + 1]) ++f_seg; }
+    // scipy evaluate_poly1: res = 0; z = 1; for each power: res += c * z; z *= ds
+    const double ds = s - sx[f_seg];
+    const double2 *o = reinterpret_cast<const double2 *>(dco + (f_seg * src.dof + f_k) * 6);
+    const double2 o01 = o[0], o23 = o[1], o45 = o[2];
+    double z = ds;
+    double v1 = 0.0 + o23.x;
+    v1 = v1 + o01.y * z;
+    z = z * ds;
+    v1 = v1 + o01.x * z;
+    double v2 = 0.0 + o45.x;
+    v2 = v2 + o23.y * ds;
+    const double va = f_second ? (v1 + (2 * delta) * v2) : v1;  // lift, linear_constraint.py:170
+    ra = f_isrow ? (f_neg ? -va : va) : 0.0;
+    rb = f_isrow ? (f_neg ? -v2 : v2) : 0.0;
+    rc = f_c;
+  };
 
   // instrumentation: projected re-solves, retries, fast-mode stages; the LP counts are derived from the stage counts
   int n_resolve = 0, n_retry = 0, n_fast = 0;
@@ -533,15 +606,31 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     fstage = fail_stage ? fail_stage[path] : -1;
     { const double *kq = Kp(); kn0 = kq[0]; kn1 = kq[1]; }
   }
-  for (int q = 0; !forward_only && q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
+  for (int q = 0; !FUSED && !forward_only && q < AHEAD && N - 1 - q >= 0; ++q) issue(N - 1 - q);
+  // FUSED: the velocity bound of the NEXT stage is loaded one stage ahead (its L2 latency hides behind this stage)
+  double2 xb_ahead = make_double2(0.0, 0.0);
+  if constexpr (FUSED) {
+    f_seg = src.nseg - 1;
+    if (!forward_only && N > 0) xb_ahead = reinterpret_cast<const double2 *>(rec_path())[N - 1];
+  }
   for (int i = forward_only ? -1 : N - 1; i >= 0; --i) {
-    const double *rec = acquire();
-    load_rows<RPL>(rec, R, nC, lane, a, b, c);
-    const double xlo = rec[3 * R], xhi = rec[3 * R + 1];
-    __syncwarp();
-    if (i - AHEAD >= 0) issue(i - AHEAD);
     const double *gq = gp();
-    const double delta = gq[i + 1] - gq[i];
+    const double g0 = gq[i], g1 = gq[i + 1];
+    const double delta = g1 - g0;
+    double xlo, xhi;
+    if constexpr (FUSED) {
+      fused_row(g0, g1, true, delta, a[0], b[0], c[0]);
+      xlo = xb_ahead.x;
+      xhi = xb_ahead.y;
+      if (i > 0) xb_ahead = reinterpret_cast<const double2 *>(rec_path())[i - 1];  // xbound [G][2] of this path
+    } else {
+      const double *rec = acquire();
+      load_rows<RPL>(rec, R, nC, lane, a, b, c);
+      xlo = rec[3 * R];
+      xhi = rec[3 * R + 1];
+      __syncwarp();
+      if (i - AHEAD >= 0) issue(i - AHEAD);
+    }
     set_xnext_rows<RPL>(lane, delta, kn0, kn1, a, b, c);
     // low/high: pyx:587-601 with x_min = x_max = NaN
     double uu, xx;
@@ -608,15 +697,21 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     // sd = sqrt(x) is applied in one coalesced sweep after the pass; until then sd[] holds x
     double x = x_start;
     if (lane == 0) sdp[0] = x;
-    for (int q = 0; q < AHEAD && q < N; ++q) issue(q);
+    for (int q = 0; !FUSED && q < AHEAD && q < N; ++q) issue(q);
     int i = 0;
+    if constexpr (FUSED) f_seg = 0;
     for (; i < N; ++i) {
-      const double *rec = acquire();
-      load_rows<RPL>(rec, R, nC, lane, a, b, c);
-      __syncwarp();
-      if (i + AHEAD < N) issue(i + AHEAD);
       const double *gq = gp();
-      const double delta = gq[i + 1] - gq[i];
+      const double g0 = gq[i], g1 = gq[i + 1];
+      const double delta = g1 - g0;
+      if constexpr (FUSED) {
+        fused_row(g0, g1, false, delta, a[0], b[0], c[0]);
+      } else {
+        const double *rec = acquire();
+        load_rows<RPL>(rec, R, nC, lane, a, b, c);
+        __syncwarp();
+        if (i + AHEAD < N) issue(i + AHEAD);
+      }
       const double *kq = Kp();
       const double k0 = kq[2 * (i + 1)], k1 = kq[2 * (i + 1) + 1];
       set_xnext_rows<RPL>(lane, delta, k0, k1, a, b, c);
@@ -797,6 +892,10 @@ constexpr int SCAN_WARPS = TB_SCAN_WARPS;  // 1: a finished path frees its slot 
 #define TB_SCAN_WARPS_PER_SM 32  // register budget of the dense build: 65536 / (32 * 32) -> 64 registers/thread (measured: 32 > 28 > 24)
 #endif
 
+#ifndef TB_SCAN_FUSED_WARPS_PER_SM
+#define TB_SCAN_FUSED_WARPS_PER_SM 32
+#endif
+
 template <int RPL>
 int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                 const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
@@ -829,8 +928,44 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
   }
   const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
   kern<<<blocks, SCAN_WARPS * 32, smem, stream>>>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi,
-                                                  flags, K, sd, u, status, fail_stage, counters);
+                                                  flags, K, sd, u, status, fail_stage, counters, VelAccSrc{});
   return check_launch("tb_scan");
+}
+
+// Fused vel+acc scan (one row per lane).  MINB = resident one-warp CTAs per SM the register budget is sized for.
+template <int MINB>
+int launch_scan_velacc_occ(const VelAccSrc &src, int W, int R, const double *grid, int grid_shared, int B, int G,
+                           const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                           double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+  const size_t smem = (size_t)SCAN_WARPS * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t) +
+                      SCAN_WARPS * 4 * sizeof(void *);
+  const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
+  const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
+  auto kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, -1, true> : scan_kernel<1, SCAN_WARPS, MINB, false, -1, true>;
+  if (mode == 0)
+    kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, 0, true> : scan_kernel<1, SCAN_WARPS, MINB, false, 0, true>;
+  else if (mode == TB_SCAN_BACKWARD_ONLY)
+    kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, TB_SCAN_BACKWARD_ONLY, true>
+                : scan_kernel<1, SCAN_WARPS, MINB, false, TB_SCAN_BACKWARD_ONLY, true>;
+  else if (mode == TB_SCAN_FORWARD_ONLY)
+    kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, TB_SCAN_FORWARD_ONLY, true>
+                : scan_kernel<1, SCAN_WARPS, MINB, false, TB_SCAN_FORWARD_ONLY, true>;
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+  kern<<<blocks, SCAN_WARPS * 32, smem, stream>>>(nullptr, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi,
+                                                  flags, K, sd, u, status, fail_stage, counters, src);
+  return check_launch("tb_scan_velacc");
+}
+
+int launch_scan_velacc(const VelAccSrc &src, int W, int R, const double *grid, int grid_shared, int B, int G,
+                       const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                       double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+  static const char *occ_env = getenv("TB_SCAN_FUSED_OCC");  // tuning: resident warps per SM (32 -> 64 regs, 28 -> 72)
+  const int occ = occ_env ? atoi(occ_env) : TB_SCAN_FUSED_WARPS_PER_SM;
+  if (occ == 28)
+    return launch_scan_velacc_occ<28>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
+                                      status, fail_stage, counters, stream);
+  return launch_scan_velacc_occ<32>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
+                                    status, fail_stage, counters, stream);
 }
 
 template <int RPL>
@@ -866,6 +1001,31 @@ extern "C" int tb_scan_ex(const double *records, int W, int R, const double *gri
   if (nC <= 64) return launch_scan<2>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
   if (nC <= 96) return launch_scan<3>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
   return launch_scan<4>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+}
+
+extern "C" int tb_scan_velacc(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof,
+                              const double *grid, int grid_shared, int B, int G, const double *alim, int lim_shared,
+                              int interp, const double *xbound, const double *sd_start, const double *sd_end,
+                              const double *sd_end_hi, int flags, double *K, double *sd, double *u, int *status,
+                              int *fail_stage, int *counters, void *stream) {
+  using namespace tb;
+  if (!ppoly || !breaks || !grid || !alim || !xbound || B <= 0 || G <= 0 || nseg <= 0 || dof <= 0) {
+    set_error("tb_scan_velacc: bad argument");
+    return TB_ERR_ARG;
+  }
+  const bool backward_only = (flags & TB_SCAN_BACKWARD_ONLY) != 0;
+  if (!K || !status || (!backward_only && (!sd || (G > 1 && !u)))) { set_error("tb_scan_velacc: null output"); return TB_ERR_ARG; }
+  if (((uintptr_t)xbound & 15) != 0) { set_error("tb_scan_velacc: xbound not 16-byte aligned"); return TB_ERR_ALIGN; }
+  const int R = (interp ? 4 : 2) * dof;
+  const int Wc = (nseg * dof * 6 + nseg + 1 + 1) & ~1;  // per-warp coefficient block (48-byte entries), doubles
+  if (R + 2 > 32 || Wc * 8 > 16 * 1024) {
+    set_error("tb_scan_velacc: %d rows / %d segments exceed the fused kernel (one row per lane, 16 KB of coefficients): "
+              "use tb_coeff_velacc + tb_scan", R, nseg);
+    return TB_ERR_UNSUPPORTED;
+  }
+  const VelAccSrc src{ppoly, breaks, alim, xbound, breaks_shared, nseg, dof, lim_shared};
+  return launch_scan_velacc(src, Wc, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status,
+                            fail_stage, counters, (cudaStream_t)stream);
 }
 
 extern "C" int tb_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,

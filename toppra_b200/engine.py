@@ -27,6 +27,14 @@ def as_device(x, device, dtype=None):
     return torch.as_tensor(arr, dtype=dtype).to(device, non_blocking=True).contiguous()
 
 
+def host_view(x):
+    """numpy view of host data (numpy array, sequence, or CPU tensor); None for CUDA tensors (no sync here)."""
+    torch = torch_mod()
+    if isinstance(x, torch.Tensor):
+        return None if x.is_cuda else x.detach().numpy()
+    return np.asarray(x, dtype=np.float64)
+
+
 def default_device(device=None):
     torch = torch_mod()
     if device is None:
@@ -193,6 +201,84 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
                                     _lib.ptr(u_arg),
                                     _lib.ptr(status), _lib.ptr(fail_stage), _lib.ptr(cnt), _lib.stream_ptr())
     _lib.check(rc, "tb_scan")
+    out = dict(K=K, sd=sd, u=u, status=status, fail_stage=fail_stage)
+    if counters:
+        out["counters"] = cnt
+    return out
+
+
+SCAN_FLAGS = dict(backward_only=1, sd_fast=4, sd_slow=12, forward_only=16, fast_lower=32)
+
+
+def velacc_fused_supported(nseg, dof, interp):
+    """tb_scan_velacc holds one LP row per lane and the spline's derivative coefficients in 16 KB of shared memory."""
+    return (4 if interp else 2) * dof + 2 <= 32 and 8 * ((nseg * dof * 6 + nseg + 2) & ~1) <= 16 * 1024
+
+
+def xbound_velocity(ppoly, breaks, grid, vlim, out=None):
+    """Velocity bound alone: xbound [B, G, 2] clipped to the solver box (+-1e8 when vlim is None) = K1 with no rows."""
+    torch = torch_mod()
+    B = ppoly.shape[0]
+    xb = torch.empty((B, grid.shape[-1], 2), dtype=torch.float64, device=ppoly.device) if out is None else out
+    if vlim is None:
+        init_bounds(xb, 0)
+    else:
+        xbound_constant(ppoly, breaks, grid, vlim, xb, 0, 1)
+    return xb
+
+
+def xbound_constant(ppoly, breaks, grid, vlim, records, R_total, write_xbound):
+    """JointVelocityConstraint alone into the xbound slots of `records` (tb_xbound_velocity, thread per gridpoint)."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    G = grid.shape[-1]
+    W = records.shape[-1]
+    check_grid_shapes(B, breaks, nseg + 1, grid, G)
+    if vlim.dim() not in (2, 3) or tuple(vlim.shape[-2:]) != (dof, 2) or (vlim.dim() == 3 and vlim.shape[0] != B):
+        raise ValueError("velocity limits must have shape (dof, 2) or (B, dof, 2); got %s" % (tuple(vlim.shape),))
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_xbound_velocity(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg, dof,
+                                            _lib.ptr(grid), 1 if grid.dim() == 1 else 0, G, _lib.ptr(vlim),
+                                            1 if vlim.dim() == 2 else 0, _lib.ptr(records), W, int(R_total),
+                                            int(write_xbound), _lib.stream_ptr())
+    _lib.check(rc, "tb_xbound_velocity")
+
+
+def scan_velacc(ppoly, breaks, grid, alim, interp, xbound, sd_start=None, sd_end=None, sd_end_hi=None,
+                backward_only=False, counters=False, sd_forward=None, forward_from=None, fast_lower=False):
+    """K2 fused with K1 for JointVelocity + JointAcceleration (tb_scan_velacc): rows are built inside the scan from
+    the spline; `xbound` [B, G, 2] from xbound_velocity().  Same outputs as scan()."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    G = grid.shape[-1]
+    dev = ppoly.device
+    check_grid_shapes(B, breaks, nseg + 1, grid, G)
+    if alim.dim() not in (2, 3) or tuple(alim.shape[-2:]) != (dof, 2) or (alim.dim() == 3 and alim.shape[0] != B):
+        raise ValueError("acceleration limits must have shape (dof, 2) or (B, dof, 2); got %s" % (tuple(alim.shape),))
+    if tuple(xbound.shape) != (B, G, 2):
+        raise ValueError("xbound must have shape (B, G, 2)")
+    for t, what in ((sd_start, "sd_start"), (sd_end, "sd_end"), (sd_end_hi, "sd_end_hi")):
+        check_path_vector(t, B, what)
+    if forward_from is not None:
+        K, status, fail_stage = forward_from["K"], forward_from["status"], forward_from["fail_stage"]
+    else:
+        K = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        fail_stage = torch.empty((B,), dtype=torch.int32, device=dev)
+    sd = None if backward_only else torch.empty((B, G), dtype=torch.float64, device=dev)
+    u = None if backward_only else torch.empty((B, max(G - 1, 0)), dtype=torch.float64, device=dev)
+    cnt = torch.zeros((B, 4), dtype=torch.int32, device=dev) if counters else None
+    u_arg = u if (u is None or u.numel() > 0) else torch.empty((1,), dtype=torch.float64, device=dev)
+    flags = ((1 if backward_only else 0) | ({None: 0, "fast": 4, "slow": 12}[sd_forward])
+             | (16 if forward_from is not None else 0) | (32 if fast_lower else 0))
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_scan_velacc(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, nseg, dof,
+                                        _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G, _lib.ptr(alim),
+                                        1 if alim.dim() == 2 else 0, 1 if interp else 0, _lib.ptr(xbound),
+                                        _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi), flags, _lib.ptr(K),
+                                        _lib.ptr(sd), _lib.ptr(u_arg), _lib.ptr(status), _lib.ptr(fail_stage),
+                                        _lib.ptr(cnt), _lib.stream_ptr())
+    _lib.check(rc, "tb_scan_velacc")
     out = dict(K=K, sd=sd, u=u, status=status, fail_stage=fail_stage)
     if counters:
         out["counters"] = cnt

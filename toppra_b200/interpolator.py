@@ -133,12 +133,14 @@ class BatchSplineInterpolator(object):
             raise ValueError("ss_waypoints must have shape (n,) or (B, n)")
         if self.n < 2:
             raise ValueError("at least 2 waypoints are needed")
+        self.ss_host = engine.host_view(ss_waypoints)  # None when the knots were given as a CUDA tensor
         if validate:
-            # scipy CubicSpline raises "`x` must be strictly increasing sequence."; dx = 0 would give inf/NaN here
-            if isinstance(ss_waypoints, torch.Tensor):
+            # scipy CubicSpline raises "`x` must be strictly increasing sequence."; dx = 0 would give inf/NaN here.
+            # Host inputs are checked on the host (no device synchronisation); CUDA tensors with one small reduction.
+            if self.ss_host is None:
                 increasing = not bool((self.d_ss[..., 1:] <= self.d_ss[..., :-1]).any())
             else:
-                increasing = bool(np.all(np.diff(np.asarray(ss_waypoints, dtype=np.float64), axis=-1) > 0))
+                increasing = bool(np.all(np.diff(self.ss_host, axis=-1) > 0))
             if not increasing:
                 raise ValueError("`ss_waypoints` must be a strictly increasing sequence.")
         self.bc_type = bc_type
@@ -173,6 +175,7 @@ class BatchSplineInterpolator(object):
         if bool((self.d_ss[..., 1:] <= self.d_ss[..., :-1]).any()):
             raise ValueError("breaks must be strictly increasing")
         self.bc_type = None
+        self.ss_host = engine.host_view(breaks)
         self.d_ppoly = c
         self.d_wp = engine.ppoly_eval(self.d_ppoly, self.d_ss, self.d_ss, 0)  # positions at the breaks
         return self
@@ -203,6 +206,7 @@ class BatchSplineInterpolator(object):
         view.B = hi - lo
         view.d_wp = self.d_wp[lo:hi]
         view.d_ss = self.d_ss if self.d_ss.dim() == 1 else self.d_ss[lo:hi]
+        view.ss_host = None if self.ss_host is None else (self.ss_host if self.ss_host.ndim == 1 else self.ss_host[lo:hi])
         view.d_ppoly = self.d_ppoly[lo:hi]
         return view
 
