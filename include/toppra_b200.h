@@ -39,7 +39,9 @@
  *      rec[0      .. R)   a-coefficients of the R static LP rows  (u multiplier)
  *      rec[R      .. 2R)  b-coefficients                          (x multiplier)
  *      rec[2R     .. 3R)  c-coefficients
- *      rec[3R], rec[3R+1] x lower / upper bound (xbound; +-1e8 when absent)
+ *      rec[3R], rec[3R+1] x lower / upper bound: the constraints' xbound INTERSECTED with the solver box [-1e8, 1e8]
+ *                         (seidelWrapper low/high, pyx:477-478,517-520; +-1e8 when absent) - the producers below
+ *                         clip, tb_scan does not
  *      rec[3R+2 .. W)     padding (R odd only)
  *   i.e. row r is  a*u + b*x + c <= 0, exactly a_arr/b_arr/c_arr[i, 2+r] of the reference's
  *   seidelWrapper; rows 0,1 of the reference (the x_next rows it rewrites per call) are synthesised

@@ -320,6 +320,46 @@ def main():
     print("torque: statuses", data["status"])
 
 
+def shortcut_rows_case():
+    """the degenerate-row and badly-scaled problems that stress the scan kernel's Seidel shortcuts, solved
+    by the REFERENCE's seidelWrapper.  The raw rows reach it through a LinearConstraint whose F is the identity and
+    g = 0 (rows = F.a, F.b, F.c - g = a, b, c exactly, cy_seidel_solverwrapper.pyx:483-510), xbound as given.
+    Only the outputs are stored (float64 K, sd, sdd + status); the inputs are regenerated from the seeds in
+    tests/problems.py:SHORTCUT_SETS."""
+    from problems import SHORTCUT_SETS
+
+    class RowsConstraint(constraint.LinearConstraint):
+        def __init__(self, rows, xbound):
+            super(RowsConstraint, self).__init__()
+            self.rows, self.xb = rows, xbound
+            self.identical = True
+            self.dof = 1
+
+        def compute_constraint_params(self, path, gridpoints, *args, **kwargs):
+            R = self.rows.shape[2]
+            return (self.rows[:, 0].copy(), self.rows[:, 1].copy(), self.rows[:, 2].copy(), np.eye(R), np.zeros(R), None,
+                    self.xb.copy())
+
+    codes = list(algo.ParameterizationReturnCode)
+    data = {}
+    for name, (gen, args) in SHORTCUT_SETS.items():
+        rows, xb = gen(*args)
+        B, G = rows.shape[:2]
+        grid = np.linspace(0, 1, G)
+        path = ta.SplineInterpolator([0, 1], [[0.0], [1.0]])
+        K = np.empty((B, G, 2)); sd = np.full((B, G), np.nan); sdd = np.full((B, G - 1), np.nan)
+        status = np.empty(B, dtype=np.int64)
+        for i in range(B):
+            inst = algo.TOPPRA([RowsConstraint(rows[i], xb[i])], path, gridpoints=grid, solver_wrapper="seidel")
+            u_, s_, _, K[i] = inst.compute_parameterization(0, 0, return_data=True)
+            status[i] = codes.index(inst.problem_data.return_code)
+            if s_ is not None:
+                sd[i], sdd[i] = s_, u_
+        data.update({name + "_K": K, name + "_sd": sd, name + "_sdd": sdd, name + "_status": status})
+        print("shortcut rows", name, "status histogram", np.bincount(status, minlength=5))
+    np.savez_compressed(os.path.join(HERE, "shortcut_rows.npz"), **data)
+
+
 def joint_torque_case():
     """JointTorqueConstraint (toppra/constraint/joint_torque.py:7-116): vel + torque with dry friction,
     both discretisation schemes, synthetic closed-form inverse dynamics of tests/problems.py."""
@@ -377,7 +417,9 @@ def other_paths_case():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "joint_torque":
+    if len(sys.argv) > 1 and sys.argv[1] == "shortcut_rows":
+        shortcut_rows_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "joint_torque":
         joint_torque_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "other_paths":
         other_paths_case()

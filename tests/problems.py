@@ -60,3 +60,61 @@ def make_torque_problem(seed, dof=6, nway=5):
     al = 10 + rng.rand(dof) * 2
     tl = 40 + rng.rand(dof) * 10
     return way, np.vstack((-vl, vl)).T, np.vstack((-al, al)).T, np.vstack((-tl, tl)).T
+
+
+# ---- raw stage rows that stress the Seidel shortcuts of the scan kernel: near-duplicate, scaled,
+#      parallel and slightly rotated copies of random rows (perturbations 1e-14 .. 1e-6), and badly scaled rows
+def degenerate_rows_batch(R0, G, B, seed):
+    """B problems of 2*R0 rows, G gridpoints: rows [B, G, 3, 2*R0], xbound [B, G, 2]."""
+    rng = np.random.RandomState(seed)
+    R = 2 * R0
+    rows = np.empty((B, G, 3, R))
+    xb = np.empty((B, G, 2))
+    for i in range(B):
+        a = rng.randn(G, R0)
+        b = rng.randn(G, R0)
+        c = -rng.rand(G, R0) * 10 ** rng.uniform(-1, 1)
+        eps = 10 ** rng.uniform(-14, -6)
+        kind = i % 4
+        if kind == 0:
+            a2, b2, c2 = a * (1 + eps * rng.randn(G, R0)), b * (1 + eps * rng.randn(G, R0)), c * (1 + eps * rng.randn(G, R0))
+        elif kind == 1:
+            sc = 10 ** rng.uniform(-3, 3, size=(G, R0))
+            a2, b2, c2 = a * sc, b * sc, c * sc + eps * rng.randn(G, R0)
+        elif kind == 2:
+            a2, b2, c2 = a.copy(), b.copy(), c + eps * rng.randn(G, R0)
+        else:
+            a2, b2, c2 = a + eps * rng.randn(G, R0), b.copy(), c.copy()
+        perm = rng.permutation(R)
+        rows[i, :, 0] = np.concatenate((a, a2), 1)[:, perm]
+        rows[i, :, 1] = np.concatenate((b, b2), 1)[:, perm]
+        rows[i, :, 2] = np.concatenate((c, c2), 1)[:, perm]
+        xb[i, :, 0] = 0.0
+        xb[i, :, 1] = 10 ** rng.uniform(-2, 3)
+    return rows, xb
+
+
+def badly_scaled_rows_batch(R, G, B, seed):
+    """Coefficients down to 1e-8 (rows look 'parallel' to the 1e-10 test of pyx:339-345), optima up to the +-1e10
+    sentinel of the 1-D LP (pyx:376-383); a third of the problems vary smoothly along the path (warm starts stay valid)."""
+    rng = np.random.RandomState(seed)
+    rows = np.empty((B, G, 3, R))
+    xb = np.empty((B, G, 2))
+    for it in range(B):
+        sa, sb, sc = 10 ** rng.uniform(-8, 1), 10 ** rng.uniform(-8, 1), 10 ** rng.uniform(-3, 5)
+        if it % 3 == 0:
+            a = np.cumsum(rng.randn(G, R) * 0.05, 0) * sa + rng.randn(1, R) * sa
+            b = np.cumsum(rng.randn(G, R) * 0.05, 0) * sb + rng.randn(1, R) * sb
+        else:
+            a, b = rng.randn(G, R) * sa, rng.randn(G, R) * sb
+        rows[it, :, 0], rows[it, :, 1], rows[it, :, 2] = a, b, -rng.rand(G, R) * sc
+        xb[it, :, 0] = 0.0
+        xb[it, :, 1] = 1e8 if it % 2 else 10 ** rng.uniform(-2, 9)
+    return rows, xb
+
+
+SHORTCUT_SETS = {  # name -> (generator, args): the problems of tests/golden/shortcut_rows.npz
+    "deg6": (degenerate_rows_batch, (6, 24, 1500, 105)),
+    "deg20": (degenerate_rows_batch, (20, 16, 1500, 119)),
+    "scaled14": (badly_scaled_rows_batch, (14, 20, 1200, 6)),
+}

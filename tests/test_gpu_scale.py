@@ -207,40 +207,22 @@ def test_skip_ahead_is_bit_identical_on_many_paths(ta):
     assert cnt[:, 2].mean() < 2.5 * (G - 1)
 
 
-@pytest.mark.parametrize("R0,G", [(6, 24), (20, 16)])
-def test_seidel_shortcuts_on_degenerate_rows(ta, R0, G):
+@pytest.mark.parametrize("name", ["deg6", "deg20", "scaled14"])
+def test_seidel_shortcuts_on_stress_rows_vs_reference_golden(ta, golden, name):
     """The K2 shortcuts (csrc/tb_scan.cu, A: jump to the last visited row, B: skip the first warm-start re-solve) must
-    fall back to the ordinary walk whenever a decision is close to the TINY threshold: raw rows with near-duplicate,
-    scaled, parallel and slightly rotated copies (perturbations 1e-14 .. 1e-6), bit-for-bit against the sequential
-    oracle.  2*R0 + 2 rows: one and two rows per lane."""
+    fall back to the ordinary walk whenever a decision is close to the TINY threshold.  Raw rows with near-duplicate,
+    scaled, parallel and slightly rotated copies (perturbations 1e-14 .. 1e-6) and badly scaled rows (coefficients down
+    to 1e-8, optima up to the 1e10 sentinel): 4200 problems, one and two rows per lane, bit for bit against the
+    REFERENCE's own seidelWrapper results (tests/golden/shortcut_rows.npz, generated by make_golden.py shortcut_rows
+    from the unmodified reference).  The kernel's per-path re-solve counters must also equal those of the scalar
+    shortcut model (oracle/shortcut_model.c), which ties the model campaigns to the kernel's decisions."""
     import torch
     from oracle import oracle as orc
-    B = 1500
-    rng = np.random.RandomState(99 + R0)
-    R = 2 * R0
-    rows = np.empty((B, G, 3, R))
-    xb = np.empty((B, G, 2))
-    for i in range(B):
-        a = rng.randn(G, R0)
-        b = rng.randn(G, R0)
-        c = -rng.rand(G, R0) * 10 ** rng.uniform(-1, 1)
-        eps = 10 ** rng.uniform(-14, -6)
-        kind = i % 4
-        if kind == 0:
-            a2, b2, c2 = a * (1 + eps * rng.randn(G, R0)), b * (1 + eps * rng.randn(G, R0)), c * (1 + eps * rng.randn(G, R0))
-        elif kind == 1:
-            sc = 10 ** rng.uniform(-3, 3, size=(G, R0))
-            a2, b2, c2 = a * sc, b * sc, c * sc + eps * rng.randn(G, R0)
-        elif kind == 2:
-            a2, b2, c2 = a.copy(), b.copy(), c + eps * rng.randn(G, R0)
-        else:
-            a2, b2, c2 = a + eps * rng.randn(G, R0), b.copy(), c.copy()
-        perm = rng.permutation(R)
-        rows[i, :, 0] = np.concatenate((a, a2), 1)[:, perm]
-        rows[i, :, 1] = np.concatenate((b, b2), 1)[:, perm]
-        rows[i, :, 2] = np.concatenate((c, c2), 1)[:, perm]
-        xb[i, :, 0] = 0.0
-        xb[i, :, 1] = 10 ** rng.uniform(-2, 3)
+    from problems import SHORTCUT_SETS
+    g = golden("shortcut_rows")
+    gen, args = SHORTCUT_SETS[name]
+    rows, xb = gen(*args)
+    B, G, _, R = rows.shape
     grid = np.linspace(0, 1, G)
     dev = torch.device("cuda:0")
     rec, W = ta.engine.alloc_records(B, G, R, dev)
@@ -248,18 +230,23 @@ def test_seidel_shortcuts_on_degenerate_rows(ta, R0, G):
     host[:, :, 0:R] = rows[:, :, 0]
     host[:, :, R:2 * R] = rows[:, :, 1]
     host[:, :, 2 * R:3 * R] = rows[:, :, 2]
-    host[:, :, 3 * R] = xb[:, :, 0]
-    host[:, :, 3 * R + 1] = xb[:, :, 1]
+    # the xbound slots hold the bound intersected with the solver box, as every record producer writes them
+    # (seidelWrapper low/high init, pyx:477-478,517-520; scaled14 has xbound_hi up to 1e9)
+    host[:, :, 3 * R] = np.maximum(xb[:, :, 0], -1e8)
+    host[:, :, 3 * R + 1] = np.minimum(xb[:, :, 1], 1e8)
     rec.copy_(torch.from_numpy(host))
     z = torch.zeros(B, dtype=torch.float64, device=dev)
     out = ta.engine.scan(rec, R, torch.from_numpy(grid).to(dev), z, z, z, counters=True)
-    K, sd, u, st = (out[k].cpu().numpy() for k in ("K", "sd", "u", "status"))
-    nok = 0
-    for i in range(B):
-        o = orc.solve_rows(rows[i], xb[i], grid, 0.0, 0.0)
-        assert o["status"] == st[i], i
-        assert np.array_equal(K[i], o["K"], equal_nan=True), i
-        if o["status"] == 0:
-            nok += 1
-            assert np.array_equal(sd[i], o["sd"]) and np.array_equal(u[i], o["u"]), i
-    assert nok > B // 2
+    K, sd, u, st, cnt = (out[k].cpu().numpy() for k in ("K", "sd", "u", "status", "counters"))
+    assert np.array_equal(st, g[name + "_status"])
+    assert np.array_equal(K, g[name + "_K"], equal_nan=True)
+    ok = st == 0
+    assert ok.sum() > B // 2
+    assert np.array_equal(sd, g[name + "_sd"], equal_nan=True) and np.array_equal(u, g[name + "_sdd"], equal_nan=True)
+    # re-solve counters: kernel == scalar model of the shortcut rules, path by path
+    for i in range(0, B, 7):
+        with orc.shortcut_model() as sm:
+            orc.solve_rows(rows[i], xb[i], grid, 0.0, 0.0)
+            stt = sm.stats()
+        assert stt["mismatches"] == 0
+        assert cnt[i, 2] == stt["resolves_model"], (i, cnt[i], stt)

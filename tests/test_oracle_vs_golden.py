@@ -264,3 +264,26 @@ def test_forward_retry_rule(golden):
         o = orc.solve_rows(r[t + "rows"], r[t + "xb"], r[t + "grid"], float(r[t + "sd_start"]), 0.0)
         assert o["status"] == int(r[t + "status"]), i
         assert _eq(o["K"], r[t + "K"]) and _eq(o["sd"], r[t + "sd"]) and _eq(o["u"], r[t + "sdd"]), i
+
+
+@pytest.mark.parametrize("name", ["deg6", "deg20", "scaled14"])
+def test_shortcut_stress_rows_vs_reference_golden(golden, name):
+    """the near-degenerate / badly scaled raw-row problems that stress the scan kernel's Seidel shortcuts.
+    The golden holds the REFERENCE's own seidelWrapper results on them (tests/golden/make_golden.py shortcut_rows);
+    the restatement must reproduce them bit for bit, so the GPU-vs-oracle tests on these inputs are pinned too."""
+    from problems import SHORTCUT_SETS
+    g = golden("shortcut_rows")
+    gen, args = SHORTCUT_SETS[name]
+    rows, xb = gen(*args)
+    B, G = rows.shape[:2]
+    grid = np.linspace(0, 1, G)
+    nfail = 0
+    for i in range(B):
+        o = orc.solve_rows(rows[i], xb[i], grid, 0.0, 0.0)
+        assert o["status"] == g[name + "_status"][i], i
+        assert np.array_equal(o["K"], g[name + "_K"][i], equal_nan=True), i
+        if o["status"] == 0:
+            assert np.array_equal(o["sd"], g[name + "_sd"][i]) and np.array_equal(o["u"], g[name + "_sdd"][i]), i
+        else:
+            nfail += 1
+    assert nfail == int((g[name + "_status"] != 0).sum())

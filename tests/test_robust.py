@@ -162,3 +162,84 @@ def test_gpu_toppra_conic_api(ta, seed):
     assert traj is not None and 0 < traj.duration < 20
     with pytest.raises(AssertionError):
         ta.algorithm.TOPPRA([vel_c, ro_acc_c], path, solver_wrapper="seidel")   # reference :78-84
+
+
+# ---- optimality: independent certificate + unrelated solver ------------------------------------
+def _cfg4_problem(seed, G=200):
+    """cfg 4: limits of cfg 2, RobustLinearConstraint(acc-interp, ELL, Interpolation); rows/xbound from the linear oracle."""
+    ss = np.linspace(0, 1, 5)
+    grid = np.linspace(0, 1, G)
+    way, vlim, alim = make_path(seed)
+    lin = orc.solve_velacc(orc.cubic_spline_fit(ss, way), ss, grid, vlim, alim, True, 0, 0, want_rows=True)
+    return grid, lin
+
+
+def test_oracle_controllable_sets_are_extremal():
+    """Every K endpoint of the restatement is feasible and either sits on the x box or is infeasible one part in 1e9
+    further out, evaluated by tests/robust_check.py which does not know the closed form (8 cfg-4 paths x 199 stages)."""
+    from robust_check import certify_controllable_sets
+    n_ext = 0
+    for seed in range(3000, 3008):
+        grid, lin = _cfg4_problem(seed)
+        r = orc.solve_rows_robust(lin["rows"], lin["xbound"], grid, 0, 28, ELL)
+        assert r["status"] == 0
+        _, ext, _ = certify_controllable_sets(lin["rows"], lin["xbound"], grid, r["K"], ELL)
+        n_ext += ext
+    assert n_ext >= 8 * 199  # every upper end is an interior extremal point (the lower ends sit on x = 0 here)
+    # a non-zero terminal velocity lifts the lower ends off the box near the end of the path: min-x certified too
+    n_low = 0
+    for seed in range(3000, 3004):
+        grid, lin = _cfg4_problem(seed)
+        r = orc.solve_rows_robust(lin["rows"], lin["xbound"], grid, 0, 28, ELL, 0.0, 0.1)
+        assert r["status"] == 0 and abs(r["K"][-1, 0] - 0.01) < 1e-15
+        _, ext, _ = certify_controllable_sets(lin["rows"], lin["xbound"], grid, r["K"], ELL)
+        n_low += ext - 199
+    assert n_low > 0
+
+
+def test_oracle_vs_slsqp_on_sampled_stage_problems():
+    """>= 200 stage SOCPs (max x and min x) re-solved with scipy SLSQP on the cone form of
+    ecos_solverwrapper.py:112-188: agreement to 1e-7 (relative + absolute), the tolerance DESIGN.md states for cfg 4."""
+    from robust_check import slsqp_extreme_x, ECOS_INFTY, ECOS_MAXX
+    rng = np.random.RandomState(0)
+    done = 0
+    for seed in range(3000, 3012):
+        grid, lin = _cfg4_problem(seed)
+        r = orc.solve_rows_robust(lin["rows"], lin["xbound"], grid, 0, 28, ELL)
+        K, rows, xb = r["K"], lin["rows"], lin["xbound"]
+        for i in rng.choice(len(grid) - 1, size=20, replace=False):
+            a, b, c = rows[i, 0], rows[i, 1], rows[i, 2]
+            td = 2 * (grid[i + 1] - grid[i])
+            lo, hi = max(xb[i, 0], -ECOS_INFTY), min(xb[i, 1], ECOS_MAXX, ECOS_INFTY)
+            xmid = 0.5 * (K[i, 0] + K[i, 1])
+            umid = (0.5 * (K[i + 1, 0] + K[i + 1, 1]) - xmid) / td
+            for sign, ref in ((1, K[i, 1]), (-1, K[i, 0])):
+                xs = slsqp_extreme_x(a, b, c, ELL, td, K[i + 1, 0], K[i + 1, 1], lo, hi, sign, np.array([umid, xmid]))
+                if xs is None:
+                    continue
+                assert abs(max(xs, 0.0) - ref) <= 1e-7 * (1 + abs(ref)), (seed, i, sign, xs, ref)
+                done += 1
+    assert done >= 200
+
+
+@pytest.mark.gpu
+def test_gpu_controllable_sets_are_extremal(ta):
+    """The same certificate on the KERNEL's output: 64 cfg-4 paths (seeds 3000+b), every stage."""
+    from robust_check import certify_controllable_sets
+    B, G = 64, 200
+    ss, way, vlim, alim = make_batch(B, 3000)
+    grid = np.linspace(0, 1, G)
+    path = ta.BatchSplineInterpolator(ss, way)
+    base = ta.constraint.JointAccelerationConstraint(alim)
+    cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.RobustLinearConstraint(base, ELL, 1)]
+    inst = ta.BatchTOPPRA(cons, path, grid)
+    h = inst.compute_parameterization(0.0, 0.0).to_host()
+    assert not h["status"].any()
+    R = inst.R
+    rec = inst.records.cpu().numpy()
+    n_ext = 0
+    for b in range(B):
+        rows = rec[b, :, :3 * R].reshape(G, 3, R)
+        _, ext, _ = certify_controllable_sets(rows, rec[b, :, 3 * R:3 * R + 2], grid, h["K"][b], ELL)
+        n_ext += ext
+    assert n_ext >= B * (G - 1)
