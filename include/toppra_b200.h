@@ -137,6 +137,23 @@ int tb_rows_canlinear(const double *a, const double *b, const double *c, const d
                       int B, int G, int m, int k, const double *grid, int grid_shared, int interp, double *records,
                       int W, int R_total, int row0, void *stream);
 
+/* SecondOrderConstraint on device (toppra/constraint/linear_second_order.py:114-173, BASELINE cfg 3): the reference
+ * calls a user Python inv_dyn 3 (N+1) times per path; here the inverse dynamics is a DEVICE MODEL from a small
+ * registry, evaluated from the spline by one thread per (path, gridpoint), and the joint-torque rows
+ * (F = [I; -I], g = [tau_max; -tau_min], + sign(q') * friction, Interpolation lift) go straight into the records.
+ *   model / params (device pointer, nparams doubles):
+ *     TB_INVDYN_COUPLED_COSINE  tau_i = p0 qdd_i + p1 sum_j cos(q_i - q_j) qdd_j + p2 sin(q_i) |qd|^2 + p3 sin(q_i)   (4)
+ *     TB_INVDYN_PENDULUMS       tau_i = p[2i] qdd_i + p[2i+1] sin(q_i)                                               (2 dof)
+ *   taulim [dof][2] (lim_shared=1) or [B][dof][2]; friction [dof] or NULL; writes rows [row0, row0 + (interp?4:2)*dof).
+ *   Models outside the registry use the host/tensor callback + tb_rows_canlinear.  fp64, not bit-identical to a numpy
+ *   inv_dyn (libm sin/cos, BLAS dot order): parity tolerance 1e-9 relative on K / sd. */
+#define TB_INVDYN_COUPLED_COSINE 0
+#define TB_INVDYN_PENDULUMS 1
+int tb_coeff_second_order(int model, const double *params, int nparams, const double *ppoly, const double *breaks,
+                          int breaks_shared, int B, int nseg, int dof, const double *grid, int grid_shared, int G,
+                          const double *taulim, int lim_shared, const double *friction, int interp, double *records, int W,
+                          int R_total, int row0, void *stream);
+
 /* Fill the xbound slots of every record with the defaults (-1e8, +1e8) (no velocity constraint). */
 int tb_init_bounds(double *records, int B, int G, int W, int R_total, void *stream);
 

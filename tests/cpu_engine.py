@@ -210,6 +210,35 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     return out
 
 
+def coeff_second_order(model, params, ppoly, breaks, grid, taulim, friction, interp, records, R_total, row0):
+    """Double of tb_coeff_second_order: the registry's models in numpy, rows assembled by the rows_canlinear double."""
+    pp, br, gr = _np(ppoly), _np(breaks), _np(grid)
+    B, _, nseg, dof = pp.shape
+    G = gr.shape[-1]
+    prm = np.asarray(params, dtype=np.float64).reshape(-1)
+    a, b, c = np.empty((B, G, dof)), np.empty((B, G, dof)), np.empty((B, G, dof))
+    for p_ in range(B):
+        g = np.ascontiguousarray(_per_path(gr, p_))
+        q, qd, qdd = (orc.ppoly_eval(pp[p_], _per_path(br, p_), g, o) for o in (0, 1, 2))
+        sq, cq = np.sin(q), np.cos(q)
+        if model == "coupled_cosine":
+            m0, m1, h, g0 = prm
+            c[p_] = g0 * sq
+            a[p_] = m0 * qd + m1 * (cq * (cq * qd).sum(-1, keepdims=True) + sq * (sq * qd).sum(-1, keepdims=True))
+            b[p_] = (m0 * qdd + m1 * (cq * (cq * qdd).sum(-1, keepdims=True) + sq * (sq * qdd).sum(-1, keepdims=True))
+                     + h * sq * (qd * qd).sum(-1, keepdims=True))
+        else:
+            c[p_] = prm[1::2] * sq
+            a[p_] = prm[0::2] * qd
+            b[p_] = prm[0::2] * qdd
+        if friction is not None:
+            c[p_] = c[p_] + np.sign(qd) * _np(friction)
+    tl = _np(taulim)
+    gaug = np.concatenate((tl[..., 1], -tl[..., 0]), axis=-1)
+    return rows_canlinear(torch.from_numpy(a), torch.from_numpy(b), torch.from_numpy(c), None, torch.from_numpy(gaug),
+                          2 if gaug.ndim == 1 else 3, grid, interp, records, R_total, row0)
+
+
 def xbound_constant(ppoly, breaks, grid, vlim, records, R_total, write_xbound):
     coeff_velacc(ppoly, breaks, grid, vlim, None, False, records, R_total, 0, write_xbound)
 
@@ -358,7 +387,7 @@ class _NoStream(object):
 
 
 PATCHED = ("spline_fit", "ppoly_eval", "record_doubles", "alloc_records", "init_bounds", "coeff_velacc",
-           "rows_canlinear", "xbound_varying", "xbound_constant", "scan", "scan_velacc", "scan_robust", "feasible_sets", "lp2d_batch", "lp1d_batch",
+           "rows_canlinear", "coeff_second_order", "xbound_varying", "xbound_constant", "scan", "scan_velacc", "scan_robust", "feasible_sets", "lp2d_batch", "lp1d_batch",
            "time_grid", "constaccel_eval")
 
 

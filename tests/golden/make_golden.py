@@ -320,6 +320,29 @@ def main():
     print("torque: statuses", data["status"])
 
 
+def torque_g500_case():
+    """BASELINE cfg 3 at its stated shape (6-DOF, 500 gridpoints, vel + acc + SecondOrder torque rows -> nC = 50),
+    4 paths with seeds 2000+b solved by the reference with the numpy inv_dyn of tests/problems.py."""
+    from problems import make_torque_problem, inv_dyn_numpy
+    codes = list(algo.ParameterizationReturnCode)
+    outs = []
+    for seed in range(2000, 2004):
+        way, vlim, alim, taulim = make_torque_problem(seed)
+        ssw = np.linspace(0, 1, 5)
+        grid = np.linspace(0, 1, 500)
+        path = ta.SplineInterpolator(ssw, way)
+        pc_tau = constraint.SecondOrderConstraint.joint_torque_constraint(inv_dyn_numpy, taulim, np.zeros(6))
+        inst = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim), pc_tau],
+                           path, gridpoints=grid, solver_wrapper="seidel")
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        outs.append(dict(way=way, vlim=vlim, alim=alim, taulim=taulim, K=K, sd=sd, sdd=sdd,
+                         status=codes.index(inst.problem_data.return_code)))
+    data = stack(outs)
+    data.update(ss=np.linspace(0, 1, 5), grid=np.linspace(0, 1, 500))
+    np.savez_compressed(os.path.join(HERE, "torque_dof6_g500.npz"), **data)
+    print("torque g500: statuses", data["status"])
+
+
 def shortcut_rows_case():
     """the degenerate-row and badly-scaled problems that stress the scan kernel's Seidel shortcuts, solved
     by the REFERENCE's seidelWrapper.  The raw rows reach it through a LinearConstraint whose F is the identity and
@@ -419,6 +442,8 @@ def other_paths_case():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "shortcut_rows":
         shortcut_rows_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "torque_g500":
+        torque_g500_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "joint_torque":
         joint_torque_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "other_paths":

@@ -26,6 +26,8 @@ _PROTOS = {
                            ctypes.c_void_p], _int),
     "tb_xbound_velocity": ([_c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _int, _c_dp, _int, _int, _int,
                             ctypes.c_void_p], _int),
+    "tb_coeff_second_order": ([_int, _c_dp, _int, _c_dp, _c_dp, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp, _int,
+                               _c_dp, _int, _c_dp, _int, _int, _int, ctypes.c_void_p], _int),
     "tb_rows_canlinear": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _int, _int, _c_dp, _int, _int, _c_dp,
                            _int, _int, _int, ctypes.c_void_p], _int),
     "tb_init_bounds": ([_c_dp, _int, _int, _int, _int, ctypes.c_void_p], _int),

@@ -9,7 +9,11 @@ The three inverse-dynamics evaluations per gridpoint are USER code.  Two ways to
     (what the reference does); the coefficient rows F.a, F.b, F.c - g and the interpolation lift are then
     assembled on the GPU (csrc/tb_coeff.cu: tb_rows_canlinear);
   * `batched=True`: `inv_dyn(q, qd, qdd)` on CUDA tensors of shape (M, dof) -> (M, m); three calls in total for
-    the whole batch x grid, everything stays on the device (the form BatchTOPPRA uses at scale)."""
+    the whole batch x grid, everything stays on the device (general fallback for arbitrary models);
+  * `device_model=(name, params)` (joint_torque_constraint only): the inverse dynamics is one of the models compiled
+    into the library (`engine.DEVICE_MODELS`, include/toppra_b200.h TB_INVDYN_*): ONE kernel evaluates q, q', q'' and
+    the three inverse-dynamics terms per gridpoint and writes the torque rows straight into the stage records
+    (tb_coeff_second_order) — the path BatchTOPPRA uses for BASELINE cfg 3."""
 import numpy as np
 
 from .constraint import DiscretizationType
@@ -31,6 +35,7 @@ class SecondOrderConstraint(LinearConstraint):
         self.dof = dof
         self.custom_term = custom_term
         self.batched = batched
+        self.device_model = None  # (name, params): inverse dynamics evaluated by tb_coeff_second_order
         self._eye_form = None  # (g [k] or [B,k], friction [m] or None): F = [I;-I] fast form
         self._format_string = "    Kind: Generalized Second-order constraint\n"
         self._format_string = "    Dimension:\n"
@@ -46,9 +51,13 @@ class SecondOrderConstraint(LinearConstraint):
         joint_friction = np.asarray(joint_friction, dtype=np.float64)
         stacked_eyes = np.vstack((np.eye(dof), -np.eye(dof)))
         g_aug = np.concatenate((taulim[..., 1], -taulim[..., 0]), axis=-1)
-        batched = kwargs.get("batched", False)
+        device_model = kwargs.pop("device_model", None)
+        batched = kwargs.get("batched", False) or device_model is not None
+        kwargs["batched"] = batched
         if taulim.ndim == 3 and not batched:
-            raise ValueError("batched torque limits need batched=True")
+            raise ValueError("batched torque limits need batched=True or a device_model")
+        if device_model is not None and device_model[0] not in engine.DEVICE_MODELS:
+            raise ValueError("unknown device model %r (known: %s)" % (device_model[0], sorted(engine.DEVICE_MODELS)))
         g_single = g_aug if g_aug.ndim == 1 else g_aug[0]
         constraint_F = lambda _: stacked_eyes  # noqa: E731
         constraint_g = lambda _: g_single  # noqa: E731
@@ -58,6 +67,8 @@ class SecondOrderConstraint(LinearConstraint):
             custom_term = lambda path, s: np.sign(path(s, 1)) * joint_friction  # noqa: E731
         obj = cls(inv_dyn, constraint_F, constraint_g, dof, custom_term, **kwargs)
         obj._eye_form = (g_aug, joint_friction)
+        obj._taulim = taulim
+        obj.device_model = device_model
         return obj
 
     @property
@@ -135,6 +146,15 @@ class SecondOrderConstraint(LinearConstraint):
         if ctx.bpath.dof != self.dof:
             raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
                 self.dof, ctx.bpath.dof))
+        if self.device_model is not None:
+            tl = engine.as_device(self._taulim, ctx.device)
+            if tl.dim() == 3:
+                tl = tl[ctx.lo:ctx.hi].contiguous()
+            fric = self._eye_form[1]
+            fric_d = engine.as_device(fric, ctx.device) if np.any(fric != 0) else None
+            engine.coeff_second_order(self.device_model[0], self.device_model[1], ctx.bpath.d_ppoly, ctx.bpath.d_ss,
+                                      ctx.d_grid, tl, fric_d, self.interpolation, records, R_total, row0)
+            return
         a, b, c = self._colloc_device(ctx)
         if self._eye_form is not None:
             g = self._eye_form[0]

@@ -57,7 +57,10 @@ extern "C" int tb_solve_velacc_host(int device, const double *ss, const double *
   int rc = 0;
   const int nseg = n - 1;
   const int R = (interp ? 4 : 2) * dof;
-  const int W = tb_record_doubles(R);
+  // vel+acc problems that fit one LP row per lane take the fused scan (no stage records): K1 shrinks to the velocity
+  // bound [B][G][2]; larger ones materialise the records (K1 -> K2)
+  const bool fused = (R + 2 <= 32) && (((size_t)nseg * dof * 6 + nseg + 2) * sizeof(double) <= 16 * 1024);
+  const int W = fused ? 2 : tb_record_doubles(R);
   const size_t nlim = (size_t)(lim_shared ? 1 : B) * dof * 2;
   // one device arena
   size_t off = 0;
@@ -87,14 +90,27 @@ extern "C" int tb_solve_velacc_host(int device, const double *ss, const double *
   rc = tb_spline_fit((double *)(d + o_ss), 1, (double *)(d + o_wp), B, n, dof, TB_BC_NOT_A_KNOT, nullptr,
                      TB_BC_NOT_A_KNOT, nullptr, (double *)(d + o_pp), ws_doubles > 0 ? (double *)(d + o_ws) : nullptr, st);
   if (rc) goto done;
-  rc = tb_coeff_velacc((double *)(d + o_pp), (double *)(d + o_ss), 1, B, nseg, dof, (double *)(d + o_grid), 1, G,
-                       vlim ? (double *)(d + o_vl) : nullptr, (double *)(d + o_al), lim_shared, interp,
-                       (double *)(d + o_rec), W, R, 0, 1, st);
-  if (rc) goto done;
-  rc = tb_scan((double *)(d + o_rec), W, R, (double *)(d + o_grid), 1, B, G, sd_start ? (double *)(d + o_s0) : nullptr,
-               sd_end ? (double *)(d + o_s1) : nullptr, (double *)(d + o_K), (double *)(d + o_sd), (double *)(d + o_u),
-               (int *)(d + o_st), nullptr, st);
-  if (rc) goto done;
+  if (fused) {
+    rc = vlim ? tb_xbound_velocity((double *)(d + o_pp), (double *)(d + o_ss), 1, B, nseg, dof, (double *)(d + o_grid), 1,
+                                   G, (double *)(d + o_vl), lim_shared, (double *)(d + o_rec), 2, 0, 1, st)
+              : tb_init_bounds((double *)(d + o_rec), B, G, 2, 0, st);
+    if (rc) goto done;
+    rc = tb_scan_velacc((double *)(d + o_pp), (double *)(d + o_ss), 1, nseg, dof, (double *)(d + o_grid), 1, B, G,
+                        (double *)(d + o_al), lim_shared, interp, (double *)(d + o_rec),
+                        sd_start ? (double *)(d + o_s0) : nullptr, sd_end ? (double *)(d + o_s1) : nullptr, nullptr, 0,
+                        (double *)(d + o_K), (double *)(d + o_sd), (double *)(d + o_u), (int *)(d + o_st), nullptr,
+                        nullptr, st);
+    if (rc) goto done;
+  } else {
+    rc = tb_coeff_velacc((double *)(d + o_pp), (double *)(d + o_ss), 1, B, nseg, dof, (double *)(d + o_grid), 1, G,
+                         vlim ? (double *)(d + o_vl) : nullptr, (double *)(d + o_al), lim_shared, interp,
+                         (double *)(d + o_rec), W, R, 0, 1, st);
+    if (rc) goto done;
+    rc = tb_scan((double *)(d + o_rec), W, R, (double *)(d + o_grid), 1, B, G, sd_start ? (double *)(d + o_s0) : nullptr,
+                 sd_end ? (double *)(d + o_s1) : nullptr, (double *)(d + o_K), (double *)(d + o_sd), (double *)(d + o_u),
+                 (int *)(d + o_st), nullptr, st);
+    if (rc) goto done;
+  }
   TB_CUDA(cudaMemcpyAsync(K, d + o_K, sizeof(double) * (size_t)B * G * 2, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(sd, d + o_sd, sizeof(double) * (size_t)B * G, cudaMemcpyDeviceToHost, st));
   if (G > 1) TB_CUDA(cudaMemcpyAsync(u, d + o_u, sizeof(double) * (size_t)B * (G - 1), cudaMemcpyDeviceToHost, st));

@@ -317,6 +317,114 @@ __global__ void xbound_varying_kernel(const double *__restrict__ ppoly, const do
   }
 }
 
+// ---- SecondOrderConstraint on device (BASELINE cfg 3) -------------------------------------------------------------
+// SecondOrderConstraint.compute_constraint_params (toppra/constraint/linear_second_order.py:142-173):
+//     c = tau(q, 0, 0);  a = tau(q, 0, q') - c;  b = tau(q, q', q'') - c;  c += sign(q') * friction  (:138)
+// for the joint-torque factory (:114-140): F = [I; -I], g = [tau_max; -tau_min], Interpolation lift
+// (linear_constraint.py:134-163).  The reference calls a user Python inv_dyn 3 (N+1) times per path; here the inverse
+// dynamics is a DEVICE MODEL picked from a small registry (TB_INVDYN_*), evaluated by one thread per (path, gridpoint)
+// straight from the spline: no [B*G, dof] intermediates, no host round trip.  Each thread writes the first row block
+// of its own record and the lifted block of the PREVIOUS record (a+ = a_i + 2 delta_{i-1} b_i), so nothing is
+// evaluated twice; the last gridpoint duplicates itself (linear_constraint.py:141-153).
+//   TB_INVDYN_COUPLED_COSINE: tau_i = p0 qdd_i + p1 sum_j cos(q_i - q_j) qdd_j + p2 sin(q_i) |qd|^2 + p3 sin(q_i)
+//                             (SURVEY.md section 8d cfg 3: p = (2, 0.3, 0.1, 4.9));  cos(q_i - q_j) is expanded
+//                             into cos q_i cos q_j + sin q_i sin q_j: dof sincos instead of dof^2 cosines
+//   TB_INVDYN_PENDULUMS:      tau_i = p[2i] qdd_i + p[2i+1] sin(q_i)   (independent joints; params [dof][2])
+constexpr int SO_MAX_DOF = 16;
+
+template <int MODEL>
+__device__ __forceinline__ void inv_dyn_terms(const int dof, const double *__restrict__ prm, const double *q,
+                                              const double *qd, const double *qdd, double *a, double *b, double *c) {
+  double sq[SO_MAX_DOF], cq[SO_MAX_DOF];
+  for (int k = 0; k < dof; ++k) sincos(q[k], &sq[k], &cq[k]);
+  if (MODEL == TB_INVDYN_COUPLED_COSINE) {
+    const double m0 = prm[0], m1 = prm[1], h = prm[2], gr = prm[3];
+    double cs1 = 0.0, ss1 = 0.0, cs2 = 0.0, ss2 = 0.0, v2 = 0.0;
+    for (int k = 0; k < dof; ++k) {
+      cs1 += cq[k] * qd[k]; ss1 += sq[k] * qd[k];      // M(q) q'  (tau(q, 0, q') - c)
+      cs2 += cq[k] * qdd[k]; ss2 += sq[k] * qdd[k];    // M(q) q''
+      v2 += qd[k] * qd[k];
+    }
+    for (int k = 0; k < dof; ++k) {
+      c[k] = gr * sq[k];
+      a[k] = m0 * qd[k] + m1 * (cq[k] * cs1 + sq[k] * ss1);
+      b[k] = m0 * qdd[k] + m1 * (cq[k] * cs2 + sq[k] * ss2) + h * sq[k] * v2;
+    }
+  } else {
+    for (int k = 0; k < dof; ++k) {
+      c[k] = prm[2 * k + 1] * sq[k];
+      a[k] = prm[2 * k] * qd[k];
+      b[k] = prm[2 * k] * qdd[k];
+    }
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+second_order_rows_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks, const int breaks_shared,
+                         const long B, const int nseg, const int dof, const double *__restrict__ grid,
+                         const int grid_shared, const int G, const double *__restrict__ prm,
+                         const double *__restrict__ taulim, const int lim_shared, const double *__restrict__ friction,
+                         const int interp, double *__restrict__ records, const int W, const int R_total,
+                         const int row0) {
+  const long total = B * G;
+  const int N = G - 1;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int gi = (int)(idx % G);
+    const long p = idx / G;
+    const double *x = breaks + (breaks_shared ? 0 : p * (nseg + 1));
+    const double *cpp = ppoly + p * 4 * nseg * dof;
+    const double *gp = grid + (grid_shared ? 0 : p * G);
+    const double *tl = taulim + (lim_shared ? 0 : p * dof * 2);
+    const double s = gp[gi];
+    const int seg = find_interval(x, nseg, s);
+    double q[SO_MAX_DOF], qd[SO_MAX_DOF], qdd[SO_MAX_DOF], a[SO_MAX_DOF], b[SO_MAX_DOF], c[SO_MAX_DOF];
+    const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = 0; k < dof; ++k) {
+      q[k] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 0);
+      qd[k] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 1);
+      qdd[k] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 2);
+    }
+    inv_dyn_terms<MODEL>(dof, prm, q, qd, qdd, a, b, c);
+    if (friction)
+      for (int k = 0; k < dof; ++k) {  // np.sign(q') * joint_friction, linear_second_order.py:138
+        const double sg = (qd[k] > 0) ? 1.0 : ((qd[k] < 0) ? -1.0 : 0.0);
+        c[k] = c[k] + sg * friction[k];
+      }
+    double *rec = records + idx * (long)W;
+    const int m = dof, k2 = 2 * dof;
+    // first block of this record: rows [0, m) = +(a, b, c) - tau_max, rows [m, 2m) = -(a, b, c) + tau_min
+    for (int k = 0; k < m; ++k) {
+      const double gmax = tl[k * 2 + 1], gmin = -tl[k * 2 + 0];  // g = [tau_max; -tau_min]
+      rec[row0 + k] = a[k];
+      rec[R_total + row0 + k] = b[k];
+      rec[2 * R_total + row0 + k] = c[k] - gmax;
+      rec[row0 + m + k] = -a[k];
+      rec[R_total + row0 + m + k] = -b[k];
+      rec[2 * R_total + row0 + m + k] = -c[k] - gmin;
+    }
+    if (interp) {
+      // lifted block of the previous record (and of this one at the last gridpoint, which duplicates itself)
+      for (int tgt = (gi > 0 ? gi - 1 : gi); tgt <= gi; ++tgt) {
+        if (tgt == gi && gi != N) continue;
+        const bool lift = tgt < gi;
+        const double two_delta = lift ? 2 * (gp[gi] - gp[tgt]) : 0.0;
+        double *rt = records + (p * G + tgt) * (long)W;
+        for (int k = 0; k < m; ++k) {
+          const double gmax = tl[k * 2 + 1], gmin = -tl[k * 2 + 0];
+          const double av = lift ? a[k] + two_delta * b[k] : a[k];
+          rt[row0 + k2 + k] = av;
+          rt[R_total + row0 + k2 + k] = b[k];
+          rt[2 * R_total + row0 + k2 + k] = c[k] - gmax;
+          rt[row0 + k2 + m + k] = -av;
+          rt[R_total + row0 + k2 + m + k] = -b[k];
+          rt[2 * R_total + row0 + k2 + m + k] = -c[k] - gmin;
+        }
+      }
+    }
+  }
+}
+
 // Fill the xbound slots (and padding) with the defaults +-1e8 when no constraint supplies them.
 __global__ void init_bounds_kernel(double *__restrict__ records, const long BG, const int W, const int R_total) {
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < BG; idx += (long)gridDim.x * blockDim.x) {
@@ -424,6 +532,40 @@ extern "C" int tb_xbound_varying(const double *ppoly, const double *breaks, int 
       ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, vlim_grid, vlim_shared, 1, records, W, R_total,
       write_xbound);
   return check_launch("tb_xbound_varying");
+}
+
+extern "C" int tb_coeff_second_order(int model, const double *params, int nparams, const double *ppoly, const double *breaks,
+                                     int breaks_shared, int B, int nseg, int dof, const double *grid, int grid_shared,
+                                     int G, const double *taulim, int lim_shared, const double *friction, int interp,
+                                     double *records, int W, int R_total, int row0, void *stream) {
+  using namespace tb;
+  if (!params || !ppoly || !breaks || !grid || !taulim || !records || B <= 0 || nseg <= 0 || dof <= 0 || G <= 0) {
+    set_error("tb_coeff_second_order: bad argument");
+    return TB_ERR_ARG;
+  }
+  if (dof > SO_MAX_DOF) { set_error("tb_coeff_second_order: dof=%d > %d", dof, SO_MAX_DOF); return TB_ERR_UNSUPPORTED; }
+  const int need = (model == TB_INVDYN_COUPLED_COSINE) ? 4 : ((model == TB_INVDYN_PENDULUMS) ? 2 * dof : -1);
+  if (need < 0) { set_error("tb_coeff_second_order: unknown device model %d", model); return TB_ERR_UNSUPPORTED; }
+  if (nparams != need) { set_error("tb_coeff_second_order: model %d takes %d parameters, got %d", model, need, nparams); return TB_ERR_ARG; }
+  const int nrows = (interp ? 4 : 2) * dof;
+  if (row0 < 0 || row0 + nrows > R_total || W < 3 * R_total + 2) {
+    set_error("tb_coeff_second_order: rows [%d,%d) do not fit R_total=%d / W=%d", row0, row0 + nrows, R_total, W);
+    return TB_ERR_ARG;
+  }
+  const long total = (long)B * G;
+  const int threads = 128;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148L * 64) blocks = 148L * 64;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model == TB_INVDYN_COUPLED_COSINE)
+    second_order_rows_kernel<TB_INVDYN_COUPLED_COSINE><<<(unsigned)blocks, threads, 0, st>>>(
+        ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
+        records, W, R_total, row0);
+  else
+    second_order_rows_kernel<TB_INVDYN_PENDULUMS><<<(unsigned)blocks, threads, 0, st>>>(
+        ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
+        records, W, R_total, row0);
+  return check_launch("tb_coeff_second_order");
 }
 
 extern "C" int tb_xbound_velocity(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,

@@ -153,6 +153,33 @@ def coeff_velacc(ppoly, breaks, grid, vlim, alim, interp, records, R_total, row0
     _lib.check(rc, "tb_coeff_velacc")
 
 
+DEVICE_MODELS = {"coupled_cosine": 0, "pendulums": 1}  # TB_INVDYN_* of include/toppra_b200.h
+
+
+def coeff_second_order(model, params, ppoly, breaks, grid, taulim, friction, interp, records, R_total, row0):
+    """Joint-torque rows of a SecondOrderConstraint whose inverse dynamics is a DEVICE MODEL (tb_coeff_second_order):
+    evaluated on the GPU from the spline, written straight into `records`.  taulim [dof,2] or [B,dof,2] (device),
+    friction [dof] device tensor or None.  Returns the number of rows written."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    G = grid.shape[-1]
+    W = records.shape[-1]
+    check_grid_shapes(B, breaks, nseg + 1, grid, G)
+    if taulim.dim() not in (2, 3) or tuple(taulim.shape[-2:]) != (dof, 2) or (taulim.dim() == 3 and taulim.shape[0] != B):
+        raise ValueError("torque limits must have shape (dof, 2) or (B, dof, 2); got %s" % (tuple(taulim.shape),))
+    if friction is not None and tuple(friction.shape) != (dof,):
+        raise ValueError("joint friction must have shape (dof,)")
+    prm = as_device(np.asarray(params, dtype=np.float64).reshape(-1), records.device)
+    with torch.cuda.device(records.device):
+        rc = _lib.load().tb_coeff_second_order(int(DEVICE_MODELS[model]), _lib.ptr(prm), int(prm.numel()), _lib.ptr(ppoly),
+                                               _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg, dof,
+                                               _lib.ptr(grid), 1 if grid.dim() == 1 else 0, G, _lib.ptr(taulim),
+                                               1 if taulim.dim() == 2 else 0, _lib.ptr(friction), 1 if interp else 0,
+                                               _lib.ptr(records), W, int(R_total), int(row0), _lib.stream_ptr())
+    _lib.check(rc, "tb_coeff_second_order")
+    return (4 if interp else 2) * dof
+
+
 def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
     """Generic CanonicalLinear rows.  a,b,c: [B,G,m]; F/g per F_mode (see include/toppra_b200.h)."""
     torch = torch_mod()
