@@ -26,6 +26,12 @@ METRIC = "paths/sec (7-DOF, 200 gridpoints, vel+accel)"
 UNIT = "paths/s"
 
 
+def workload_text(B, dof, G):
+    """One string for both arms (the driver compares the arms' `config.workload`)."""
+    return ("configs[1]: batch %d random %d-DOF cubic-spline paths (5 waypoints), %d gridpoints, "
+            "JointVelocity+JointAcceleration(interp), per GPU" % (B, dof, G))
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -37,6 +43,10 @@ def parse_args():
     ap.add_argument("--dof", type=int, default=7)
     ap.add_argument("--cpu-sample", type=int, default=0, help="paths in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="1,3,4,5", help="BASELINE configs reported in the `configs` block besides the "
+                    "headline cfg 2 (comma list out of 1,3,4,5; 'none' to skip)")
+    ap.add_argument("--cfg3-batch", type=int, default=65536)
+    ap.add_argument("--cfg5-batch", type=int, default=1 << 20)
     return ap.parse_args()
 
 
@@ -126,15 +136,17 @@ class CpuArm(object):
         self.nproc = n
 
     def _calibrate(self, ss, way, vlim, alim, grid):
-        cands = sorted({c for c in (4, 8, 16, 32, 64, 128, self.cores) if c <= self.cores}) or [1]
+        """Pool size = min(visible CPUs, cgroup quota), or half of it when that is measurably faster (SMT siblings):
+        two candidates, each timed on >= 2 s of work so that the choice and the reported value are stable run to run."""
+        cands = sorted({max(1, self.cores // 2), self.cores})
         best, best_rate, log = cands[-1], 0.0, []
         for n in cands:
             self._make_pool(n)
-            S = min(way.shape[0], max(64, 8 * n))
-            self.run(ss, way[:min(S, 4 * n)], vlim[:min(S, 4 * n)], alim[:min(S, 4 * n)], grid)  # import warm-up
+            self.run(ss, way[:min(way.shape[0], 4 * n)], vlim[:4 * n], alim[:4 * n], grid)  # import warm-up
+            S = min(way.shape[0], max(64, 300 * n))  # ~150 paths/s per core -> ~2 s
             rate = S / self.run(ss, way[:S], vlim[:S], alim[:S], grid)
             log.append("%d:%.0f" % (n, rate))
-            if rate > best_rate:
+            if rate > best_rate * 1.03:   # prefer the smaller pool unless the larger one is clearly faster
                 best, best_rate = n, rate
         self.cores = best
         self.note += "; pool-size calibration (procs:paths/s) " + " ".join(log)
@@ -182,7 +194,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch %d random %d-DOF spline paths, %d gridpoints, vel+accel" % (args.batch, dof, G),
+        "config": {"workload": workload_text(args.batch, dof, G),
                    "sample_paths_per_step": S, "solver": "reference seidelWrapper (Cython, -O1) via TOPPRA(..., 'seidel')"
                    if arm.kind == "reference" else "oracle C port (reference build absent)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
@@ -237,6 +249,205 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
 
+
+
+# ----------------------------------------------------------------------------------------------------------
+# `configs` block: the other BASELINE.json configurations on the same box, after the headline measurement
+# ----------------------------------------------------------------------------------------------------------
+def extra_configs(args, torch, dist, ta, dev, world, rank, peak):
+    """cfg 1 (B = 1 latency), cfg 3 (6-DOF, 500 gridpoints, vel + acc + torque rows, 65536 paths per GPU), cfg 4 (robust,
+    4096 paths per GPU) and cfg 5 (2^20 paths STRONG-scaled over the ranks, chunked all-gather of the results inside the
+    timed region) through the public API with device-resident inputs; CUDA events, max over ranks.  Each entry: paths/s,
+    ms split (fit / records / scan), status histogram over all ranks, and the scan kernel's roofline against the
+    materialised-record algorithmic bytes of SURVEY.md section 8d."""
+    from problems import make_batch_fast
+    want = [] if args.configs == "none" else [int(c) for c in args.configs.split(",") if c]
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allminmax(x):
+        t = torch.tensor([x, -x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [-float(t[1].item()), float(t[0].item())]
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(steps):
+            r = fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / steps, r
+
+    def hist(status):
+        h = torch.bincount(status.to(torch.int64), minlength=5)[:5].clone()
+        if world > 1:
+            dist.all_reduce(h)
+        return dict(zip(("Ok", "ErrUnknown", "ErrShortPath", "FailUncontrollable", "ErrForwardPassFail"), h.cpu().tolist()))
+
+    def roof(R, G, B, ms):
+        by = (2 * G * (3 * R + 2) * 8 + G * 16 + G * 8 + (G - 1) * 8 + 8) * B
+        return {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": by / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": by, "ms_per_launch": ms}
+
+    def staged(cons, d_ss, d_way, d_grid, steps=3):
+        """fit / records (or xbound) / scan, timed separately on a fresh instance (single-chunk problems only)."""
+        fit, path = timed(lambda: ta.BatchSplineInterpolator(d_ss, d_way, validate=False), steps, 2)
+        inst = ta.BatchTOPPRA(cons, path, d_grid, validate=False)
+        if inst.chunk_size() < inst.B:
+            return {"fit_ms": allmax(fit), "chunk_paths": inst.chunk_size()}, None
+        rec, _ = timed(inst.setup, steps, 2)
+        scan, _ = timed(lambda: inst.compute_parameterization(0.0, 0.0), steps, 2)
+        return {"fit_ms": allmax(fit), "records_ms": allmax(rec), "scan_ms": allmax(scan),
+                "scan_ms_ranks_min_max": allminmax(scan)}, scan
+
+    if 1 in want:
+        # cfg 1: one 7-DOF path, 100 gridpoints (examples/plot_kinematics.py, seed 9): latency of the single-path drop-in
+        # API (host in, host out, every sync included) and of the B = 1 batched call
+        np.random.seed(9)
+        way1 = np.random.randn(5, 7)
+        vl, al = 10 + np.random.rand(7) * 20, 10 + np.random.rand(7) * 2
+        ss1, grid1 = np.linspace(0, 1, 5), np.linspace(0, 1, 100)
+
+        def one_api():
+            path = ta.SplineInterpolator(ss1, way1)
+            inst = ta.algorithm.TOPPRA([ta.constraint.JointVelocityConstraint(vl), ta.constraint.JointAccelerationConstraint(al)],
+                                       path, gridpoints=grid1, solver_wrapper="seidel")
+            return inst.compute_parameterization(0, 0)
+
+        def one_batch():
+            path = ta.BatchSplineInterpolator(ss1, way1[None], device=dev)
+            inst = ta.BatchTOPPRA([ta.constraint.JointVelocityConstraint(vl), ta.constraint.JointAccelerationConstraint(al)],
+                                  path, grid1)
+            return inst.compute_parameterization(0.0, 0.0).to_host()
+
+        lat = {}
+        for name, fn in (("TOPPRA.compute_parameterization", one_api), ("BatchTOPPRA_B1_to_host", one_batch)):
+            for _ in range(5):
+                fn()
+            ts = []
+            for _ in range(30):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            lat[name] = {"median_ms": 1e3 * float(np.median(ts)), "min_ms": 1e3 * float(np.min(ts))}
+        d_w1 = torch.as_tensor(way1[None]).to(dev)
+        d_s1, d_g1 = torch.as_tensor(ss1).to(dev), torch.as_tensor(grid1).to(dev)
+        c1 = [ta.constraint.JointVelocityConstraint(vl), ta.constraint.JointAccelerationConstraint(al)]
+        for c in c1:
+            c.device_limits(dev)
+        k_ms, _ = timed(lambda: ta.BatchTOPPRA(c1, ta.BatchSplineInterpolator(d_s1, d_w1, validate=False), d_g1,
+                                               validate=False).compute_parameterization(0.0, 0.0), 20, 5)
+        out["cfg1"] = {"workload": "configs[0]: one 7-DOF path, 100 gridpoints, vel+acc (seed 9), wall clock on the host "
+                                   "incl. H2D/D2H and every synchronisation", "latency": lat,
+                       "device_resident_step_ms": k_ms, "n_gpus_used": 1}
+
+    if 3 in want:
+        B, G, dof = args.cfg3_batch, 500, 6
+        ss, way, vlim, alim = make_batch_fast(B, seed=2000 + rank, dof=dof)
+        tl = 40 + np.random.RandomState(7 + rank).rand(B, dof) * 10
+        taulim = np.stack((-tl, tl), axis=-1)
+        cons = [ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim),
+                ta.constraint.SecondOrderConstraint.joint_torque_constraint(
+                    None, taulim, np.zeros(dof), device_model=("coupled_cosine", [2.0, 0.3, 0.1, 4.9]))]
+        for c in cons[:2]:
+            c.device_limits(dev)
+        d_way, d_ss = torch.as_tensor(way).to(dev), torch.as_tensor(ss).to(dev)
+        d_grid = torch.as_tensor(np.linspace(0, 1, G)).to(dev)
+
+        def step3():
+            path = ta.BatchSplineInterpolator(d_ss, d_way, validate=False)
+            return ta.BatchTOPPRA(cons, path, d_grid, validate=False).compute_parameterization(0.0, 0.0)
+
+        ms, res = timed(step3, 3, 2)
+        ms = allmax(ms)
+        h = hist(res.status)
+        del res
+        # stage split on a sub-batch that fits one record buffer (the full batch runs chunked)
+        nsub = min(B, 16384)
+        sub = [ta.constraint.JointVelocityConstraint(vlim[:nsub]), ta.constraint.JointAccelerationConstraint(alim[:nsub]),
+               ta.constraint.SecondOrderConstraint.joint_torque_constraint(
+                   None, taulim[:nsub], np.zeros(dof), device_model=("coupled_cosine", [2.0, 0.3, 0.1, 4.9]))]
+        split, scan_ms = staged(sub, d_ss, d_way[:nsub].contiguous(), d_grid)
+        split["split_measured_on_paths"] = nsub
+        out["cfg3"] = {"workload": "configs[2]: %d 6-DOF paths per GPU, 500 gridpoints, JointVelocity + JointAcceleration + "
+                                   "SecondOrder torque rows (R = 48, nC = 50), inverse dynamics by the library's device "
+                                   "model 'coupled_cosine' inside tb_coeff_second_order" % B,
+                       "paths_per_s": B * world / (ms * 1e-3), "ms_per_step": ms, "scaling": "weak", "status": h,
+                       "split": split, "roofline": roof(48, G, nsub, scan_ms) if scan_ms else None}
+        del d_way, cons, sub
+        torch.cuda.empty_cache()
+
+    if 4 in want:
+        B, G, dof = args.batch, 200, 7
+        ss, way, vlim, alim = make_batch_fast(B, seed=3000 + rank, dof=dof)
+        cons = [ta.constraint.JointVelocityConstraint(vlim),
+                ta.constraint.RobustLinearConstraint(ta.constraint.JointAccelerationConstraint(alim), [1e-3, 5e-2, 9e-3], 1)]
+        cons[0].device_limits(dev)
+        d_way, d_ss = torch.as_tensor(way).to(dev), torch.as_tensor(ss).to(dev)
+        d_grid = torch.as_tensor(np.linspace(0, 1, G)).to(dev)
+
+        def step4():
+            path = ta.BatchSplineInterpolator(d_ss, d_way, validate=False)
+            return ta.BatchTOPPRA(cons, path, d_grid, validate=False).compute_parameterization(0.0, 0.0)
+
+        ms, res = timed(step4, 5, 3)
+        ms = allmax(ms)
+        split, scan_ms = staged(cons, d_ss, d_way, d_grid)
+        out["cfg4"] = {"workload": "configs[3]: robust TOPP-RA, %d 7-DOF paths per GPU, 200 gridpoints, JointVelocity + "
+                                   "RobustLinearConstraint(JointAcceleration, ellipsoid [1e-3, 5e-2, 9e-3], interpolation): "
+                                   "3 two-variable SOCPs per stage (tb_scan_robust)" % B,
+                       "paths_per_s": B * world / (ms * 1e-3), "ms_per_step": ms, "scaling": "weak", "status": hist(res.status),
+                       "split": split, "roofline": roof(28, G, B, scan_ms) if scan_ms else None,
+                       "parity": "unpinned (no ECOS): optimality certificate + SLSQP cross-check in tests/test_robust.py"}
+        del d_way, res
+        torch.cuda.empty_cache()
+
+    if 5 in want:
+        from toppra_b200.distributed import ShardedSolver
+        Btot, G, dof = args.cfg5_batch, 200, 7
+        Btot -= Btot % world
+        shard = Btot // world
+        ss, way, vlim, alim = make_batch_fast(shard, seed=1000 + rank, dof=dof)
+        d_way, d_ss = torch.as_tensor(way).to(dev), torch.as_tensor(ss).to(dev)
+        d_vlim, d_alim = torch.as_tensor(vlim).to(dev), torch.as_tensor(alim).to(dev)
+        d_grid = torch.as_tensor(np.linspace(0, 1, G)).to(dev)
+        solver = ShardedSolver(Btot, G, dev, nchunks=max(2, 8 // world), gather=True)
+
+        ms, full = timed(lambda: solver.solve(d_ss, d_way, d_grid, d_vlim, d_alim), 3, 2)
+        ms = allmax(ms)
+        solver.kernel_events = []
+        solver.solve(d_ss, d_way, d_grid, d_vlim, d_alim, record_events=True)
+        torch.cuda.synchronize()
+        k_ms = sum(a.elapsed_time(b) for a, b in solver.kernel_events)   # this rank's K0 + xbound + scan, all chunks
+        lo = rank * shard if solver.gather else 0
+        h = hist(full["status"][lo:lo + shard])
+        out["cfg5"] = {"workload": "configs[4]: %d 7-DOF paths, 200 gridpoints, vel+acc, sharded contiguously over %d GPU(s) "
+                                   "(%d per GPU, %d chunks per shard); NCCL all-gather of K, sd, sdd, status per chunk on a "
+                                   "side stream INSIDE the timed region, results in global order on every rank"
+                                   % (Btot, world, shard, solver.nchunks),
+                       "paths_per_s": Btot / (ms * 1e-3), "ms_per_step": ms, "scaling": "strong", "status": h,
+                       "kernels_ms_ranks_min_max": allminmax(k_ms), "gather_exposed_ms": ms - allmax(k_ms),
+                       "gathered_bytes_per_rank": int(sum(v.numel() * v.element_size() for v in full.values())) if world > 1 else 0,
+                       "roofline": roof(28, G, shard, k_ms)}
+        del solver, full, d_way
+        torch.cuda.empty_cache()
+    return out
 
 def run_b200(args):
     import torch
@@ -396,6 +607,7 @@ def run_b200(args):
     scan_mode["fast_lower"] = True
     ms_fast = timed(step_device, args.steps, max(args.warmup, 3))
     scan_mode["fast_lower"] = False
+    ms_rec = timed(step_records, args.steps, max(args.warmup, 3))
 
     status = h_out["status"].numpy()
     n_ok = int((status == 0).sum())
@@ -406,35 +618,64 @@ def run_b200(args):
     k1 = float(np.mean([e[1].elapsed_time(e[2]) for e in k_events]))
     k2 = float(np.mean([e[2].elapsed_time(e[3]) for e in k_events]))
 
+    peaks0 = {}
+    try:
+        peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # per-rank K2 time (SCALE: explains the max-over-ranks step time)
+    k2_ranks = torch.tensor([k2, -k2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(k2_ranks, op=dist.ReduceOp.MAX)
+    k2_min, k2_max = -float(k2_ranks[1].item()), float(k2_ranks[0].item())
+    try:
+        configs = extra_configs(args, torch, dist, ta, dev, world, rank, float(peaks0.get("hbm_gbs", 6650.0)))
+    except Exception as exc:  # never lose the headline line
+        configs = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (K2 scan) and of K1, algorithmic bytes per SURVEY.md §8d / DESIGN.md
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    # roofline of the dominant kernel: the fused scan (tb_scan_velacc).  SURVEY.md section 8d's contract: report against the
+    # MATERIALISED-record algorithmic bytes (rows read twice + outputs) and note what the fused form really moves.
+    peak = float(peaks0.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks0 else "fallback 6.65 TB/s"
     bytes_k1 = (4 * (nway - 1) * dof * 8 + G * (3 * R + 2) * 8) * B
     bytes_k2 = (2 * G * (3 * R + 2) * 8 + G * 16 + G * 8 + (G - 1) * 8 + 8) * B
+    bytes_fused = (4 * (nway - 1) * dof * 8 + G * 16 + G * 16 + G * 8 + (G - 1) * 8 + 8) * B
+    bytes_xb = (4 * (nway - 1) * dof * 8 + G * 16) * B
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    roof = {"kernel": "scan_kernel (K2)", "bound": "hbm", "achieved": bytes_k2 / (k2 * 1e-3) / 1e9, "peak": peak,
+    roof = {"kernel": "scan_kernel<FUSED> (tb_scan_velacc: K1 rows built inside K2)", "bound": "hbm",
+            "achieved": bytes_k2 / (k2 * 1e-3) / 1e9, "peak": peak,
             "unit": "GB/s", "frac": bytes_k2 / (k2 * 1e-3) / 1e9 / peak,
-            "traffic": (traffic or {}).get("scan_kernel_bytes_per_launch"), "peak_source": peak_src,
+            "traffic": (traffic or {}).get("scan_velacc_bytes_per_launch"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bytes_k2, "ms_per_launch": k2,
-            "note": "K2 is a latency/issue-bound sequential scan (597 dependent LPs per path); see lp_solves_per_s"}
-    roof_k1 = {"kernel": "coeff_velacc_kernel (K1)", "bound": "hbm", "achieved": bytes_k1 / (k1 * 1e-3) / 1e9,
-               "peak": peak, "unit": "GB/s", "frac": bytes_k1 / (k1 * 1e-3) / 1e9 / peak,
-               "traffic": (traffic or {}).get("coeff_velacc_kernel_bytes_per_launch"),
-               "algorithmic_bytes_per_launch": bytes_k1, "ms_per_launch": k1}
+            "fused_bytes_per_launch": bytes_fused,
+            "note": "algorithmic bytes = the materialised-record figure of SURVEY 8d (281,600 B/path); the fused kernel "
+                    "itself reads spline + velocity bound and writes K, sd, u (fused_bytes_per_launch): the scan is a "
+                    "latency/issue-bound chain of 597 dependent LPs per path, see lp_solves_per_s and profiles/"}
+    roof_k1 = {"kernel": "xbound_velocity_kernel (K1 of the fused path: velocity bound only)", "bound": "hbm",
+               "achieved": bytes_xb / (k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+               "frac": bytes_xb / (k1 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": bytes_xb, "ms_per_launch": k1}
+    rk0 = float(np.mean([e[0].elapsed_time(e[1]) for e in rec_events]))
+    rk1 = float(np.mean([e[1].elapsed_time(e[2]) for e in rec_events]))
+    rk2 = float(np.mean([e[2].elapsed_time(e[3]) for e in rec_events]))
+    records_path = {
+        "what": "the same batch through materialised stage records (generic constraint lists: K0 -> K1 coeff_velacc -> "
+                "K2 record scan); not part of `value`",
+        "ms_per_step": ms_rec / args.steps, "kernels_ms": {"K0": rk0, "K1_coeff_velacc": rk1, "K2_scan_records": rk2},
+        "roofline_k1": {"bound": "hbm", "achieved": bytes_k1 / (rk1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": bytes_k1 / (rk1 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": bytes_k1,
+                        "traffic": (traffic or {}).get("coeff_velacc_kernel_bytes_per_launch")},
+        "roofline_k2": {"bound": "hbm", "achieved": bytes_k2 / (rk2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": bytes_k2 / (rk2 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": bytes_k2,
+                        "traffic": (traffic or {}).get("scan_kernel_bytes_per_launch")}}
 
     h2d = int(h_way.numel() + h_vlim.numel() + h_alim.numel() + h_ss.numel() + h_grid.numel()) * 8
     d2h = int(h_out["K"].numel() + h_out["sd"].numel() + h_out["sdd"].numel()) * 8 + int(h_out["status"].numel()) * 8
@@ -442,8 +683,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch %d random %d-DOF cubic-spline paths (5 waypoints), %d gridpoints, "
-                               "JointVelocity+JointAcceleration(interp), per GPU" % (B, dof, G),
+        "config": {"workload": workload_text(B, dof, G),
                    "global_batch": total_paths, "parallelism": "paths sharded over %d GPU(s), no data-path collective" % world,
                    "l2": "256 MB buffer written between timed iterations (L2 flush)", "ok_paths_last_step": n_ok},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -455,8 +695,9 @@ def run_b200(args):
                        "inst.host_ready); host_sync_every_step = the same call with sync=True"
                        + (", NCCL all_gather of sd" if world > 1 else "")},
         "gpu_launches": 3 * args.steps,
-        "kernels_ms": {"K0_spline_fit": k0, "K1_coeff": k1, "K2_scan": k2},
-        "roofline": roof, "roofline_k1": roof_k1,
+        "kernels_ms": {"K0_spline_fit": k0, "K1_xbound": k1, "K2_scan_velacc": k2, "K2_ranks_min_max": [k2_min, k2_max]},
+        "configs": configs,
+        "roofline": roof, "roofline_k1": roof_k1, "records_path": records_path,
         "lp_solves_per_s": 597.0 / 199 * (G - 1) * B / (k2 * 1e-3),
         "opt_in_fast_lower_bound": {
             "value": total_paths * args.steps / (ms_fast * 1e-3), "unit": UNIT, "ms_per_step": ms_fast / args.steps,

@@ -147,7 +147,10 @@ class BatchTOPPRA(object):
                                      % (type(c).__name__, name, lim.shape, path.dof, path.B, path.dof))
         self.ctx = RecordContext(path, self.d_grid, grid_host, None)
         self.records = None
-        self.R = None
+        try:  # static LP rows per stage (nC = R + 2); user-defined constraints report theirs at setup()
+            self.R = int(sum(c.num_rows(self.ctx) for c in constraint_list))
+        except NotImplementedError:
+            self.R = None
         # Stage records cost 8 * (3R + 2) * G bytes per path (138 KB at 7-DOF / 200 gridpoints): batches whose
         # records exceed `max_record_bytes` are solved in chunks through one reused record buffer.
         self.max_record_bytes = int(max_record_bytes)

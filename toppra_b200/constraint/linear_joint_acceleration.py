@@ -30,6 +30,20 @@ class JointAccelerationConstraint(LinearConstraint):
         self.identical = True
         self._d_cache = {}
 
+    @classmethod
+    def from_device(cls, d_alim, discretization_scheme=DiscretizationType.Interpolation):
+        """Limits already resident on the GPU: a (dof, 2) or (B, dof, 2) float64 CUDA tensor (toppra_b200 extension)."""
+        obj = cls.__new__(cls)
+        LinearConstraint.__init__(obj)
+        if d_alim.dim() not in (2, 3) or d_alim.shape[-1] != 2:
+            raise ValueError("device limits must have shape (dof, 2) or (B, dof, 2)")
+        obj.alim, obj.dof = d_alim, int(d_alim.shape[-2])
+        obj.set_discretization_type(discretization_scheme)
+        obj._format_string = "    Acceleration limit: (device tensor)\n"
+        obj.identical = True
+        obj._d_cache = {str(d_alim.device): d_alim}
+        return obj
+
     def device_limits(self, device):
         key = str(device)
         if key not in self._d_cache:

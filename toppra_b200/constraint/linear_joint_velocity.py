@@ -52,6 +52,19 @@ class JointVelocityConstraint(LinearConstraint):
             for i in range(self.vlim.shape[0]):
                 self._format_string += "      J{:d}: {:}".format(i + 1, self.vlim[i]) + "\n"
 
+    @classmethod
+    def from_device(cls, d_vlim):
+        """Limits already resident on the GPU: a (dof, 2) or (B, dof, 2) float64 CUDA tensor (toppra_b200 extension for
+        pipelines whose inputs never touch the host; the caller vouches for lower < upper)."""
+        obj = cls.__new__(cls)
+        LinearConstraint.__init__(obj)
+        if d_vlim.dim() not in (2, 3) or d_vlim.shape[-1] != 2:
+            raise ValueError("device limits must have shape (dof, 2) or (B, dof, 2)")
+        obj.vlim, obj.dof = d_vlim, int(d_vlim.shape[-2])
+        obj._format_string = "    Velocity limit: (device tensor)\n"
+        obj._d_cache = {str(d_vlim.device): d_vlim}
+        return obj
+
     def device_limits(self, device):
         key = str(device)
         if key not in self._d_cache:

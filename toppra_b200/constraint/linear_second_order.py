@@ -147,7 +147,10 @@ class SecondOrderConstraint(LinearConstraint):
             raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
                 self.dof, ctx.bpath.dof))
         if self.device_model is not None:
-            tl = engine.as_device(self._taulim, ctx.device)
+            cache = self.__dict__.setdefault("_d_taulim", {})   # limits stay resident across solves and chunks
+            if str(ctx.device) not in cache:
+                cache[str(ctx.device)] = engine.as_device(self._taulim, ctx.device)
+            tl = cache[str(ctx.device)]
             if tl.dim() == 3:
                 tl = tl[ctx.lo:ctx.hi].contiguous()
             fric = self._eye_form[1]
