@@ -178,9 +178,22 @@ int tb_scan_robust(const double *records, int W, int R, int conic_row0, int coni
                    int flags, double *K, double *sd, double *u, int *status, int *fail_stage, int *counters,
                    void *stream);
 
-/* Feasible sets X[B][G][2] (compute_feasible_sets). */
+/* Feasible sets X[B][G][2] (compute_feasible_sets, reachability_algorithm.py:131-164).
+ * tb_feasible_sets_ex: flags = TB_SCAN_UBOUND for records that carry a u-bound pair (see tb_scan_ex). */
 int tb_feasible_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                      double *X, void *stream);
+int tb_feasible_sets_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                        int flags, double *X, void *stream);
+
+/* Reachable sets (compute_reachable_sets(sdmin, sdmax), reachability_algorithm.py:378-431) of B paths in one launch:
+ * the feasible-set pass followed by the forward recursion L[i+1] = _one_step_forward(i, L[i], X[i+1]) — one kernel
+ * because the reference's solver wrapper carries its warm-start slots from the first pass into the second.
+ *   sdmin, sdmax: [B] (sdmax NULL = sdmin; sdmin NULL = zeros);  X out, L out: [B][G][2];
+ *   L rows after a failed stage stay 0 like the reference's np.zeros; fail_stage (nullable) [B]: index of the first
+ *   NaN row of L, -1 if none.  flags: 0 or TB_SCAN_UBOUND. */
+int tb_reachable_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                      const double *sdmin, const double *sdmax, int flags, double *X, double *L, int *fail_stage,
+                      void *stream);
 
 /* Extended K2 entry:
  *   sd_end_hi (nullable): [B] upper terminal velocity, K[N] = [sd_end^2, sd_end_hi^2]
@@ -198,9 +211,24 @@ int tb_feasible_sets(const double *records, int W, int R, const double *grid, in
                                    arithmetic returns xbound_lo +- ~1e-16; falls back to the Seidel LP otherwise.
                                    Deviation from the reference: <= ~1e-15 on K and sd (tests: 1e-12). */
 #define TB_SCAN_FEASIBLE_SETS 2 /* tb_scan_robust only: K receives the feasible sets X (compute_feasible_sets) */
+#define TB_SCAN_UBOUND 64       /* the records carry a u-bound pair behind the x-bound pair: record = a[R] | b[R] | c[R] | xlo |
+                                   xhi | ulo | uhi (W >= 3R+4): `ubound` of a constraint intersected into low/high[:, 0]
+                                   (seidelWrapper.__init__, cy_seidel_solverwrapper.pyx:512-515).  Not with TB_SCAN_FAST_LOWER. */
 int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K, double *sd,
                double *u, int *status, int *fail_stage, int *counters, void *stream);
+
+/* Ragged batches (per-path gridpoint counts, e.g. from tb_propose_gridpoints): grid is [B][G] (grid_shared = 0) padded to
+ * the longest path, glen [B] (device int32, nullable = all G) holds each path's count 1 <= glen[p] <= G.  Strides stay G;
+ * K / sd / u entries at and past a path's own end are NaN.  Everything else as tb_scan_ex / tb_scan_velacc. */
+int tb_scan_ragged(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                   const int *glen, const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags,
+                   double *K, double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream);
+int tb_scan_velacc_ragged(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof,
+                          const double *grid, int grid_shared, int B, int G, const int *glen, const double *alim,
+                          int lim_shared, int interp, const double *xbound, const double *sd_start, const double *sd_end,
+                          const double *sd_end_hi, int flags, double *K, double *sd, double *u, int *status,
+                          int *fail_stage, int *counters, void *stream);
 
 /* K2 fused with K1 for the JointVelocity + JointAcceleration problem (the headline case): no stage records at all.
  * Every lane of the path's warp builds its own LP row in the stage prologue from the spline (same arithmetic as
@@ -213,6 +241,35 @@ int tb_scan_velacc(const double *ppoly, const double *breaks, int breaks_shared,
                    int grid_shared, int B, int G, const double *alim, int lim_shared, int interp, const double *xbound,
                    const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
                    double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream);
+
+/* propose_gridpoints (toppra/interpolator.py:49-122) for B paths, one warp per path: adaptive bisection of the path
+ * interval until every segment is at most max_seg_length long and its estimated interpolation error
+ * 0.5 max_k |q_k''(mid)| len^2 is at most max_err_threshold, then doubling up to min_nb_points.  The grids are RAGGED:
+ *   grid_out [B][Gmax] (tail padded with the path end), glen out [B] = gridpoints per path, scratch [B][Gmax];
+ *   status out [B]: 0 ok, 1 = the reference would raise "Unable to find a good gridpoint for this path"
+ *   (max_iteration passes used up), TB_ERR_UNSUPPORTED = more than Gmax points needed.
+ * Feed grid_out / glen to tb_scan_ragged / tb_scan_velacc_ragged. */
+int tb_propose_gridpoints(const double *ppoly, const double *breaks, int breaks_shared, int B, int nseg, int dof,
+                          double max_err_threshold, int max_iteration, double max_seg_length, int min_nb_points,
+                          int Gmax, double *grid_out, double *scratch, int *glen, int *status, void *stream);
+
+/* TOPPRAsd (desired_duration_algorithm.py:139-191): bisection on alpha so that the blend alpha * fastest +
+ * (1 - alpha) * slowest parameterisation has the desired duration (_compute_duration :10-17, running sum in stage order).
+ *   x_fast / x_slow [B][G], u_fast / u_slow [B][G-1]: squared velocities and accelerations of the two forward passes
+ *   (tb_scan_ex with TB_SCAN_SD_FORWARD [| TB_SCAN_SD_SLOW]); desired_duration [B]; status_in (nullable) [B]: paths
+ *   with TB_STATUS_FAIL_UNCONTROLLABLE get NaN outputs and keep that status;
+ *   sd out [B][G] = sqrt(blend), sdd out [B][G-1]; info out [B][4] = (alpha, fastest duration, slowest duration,
+ *   bisection steps); status out [B]: Ok or ErrUnknown (NaN in sd).  max_iter <= 0: 200 (the reference has no cap). */
+int tb_sd_bisect(const double *x_fast, const double *u_fast, const double *x_slow, const double *u_slow,
+                 const double *grid, int grid_shared, int B, int G, const double *desired_duration, double atol,
+                 int max_iter, const int *status_in, double *sd, double *sdd, double *info, int *status, void *stream);
+
+/* ParametrizeSpline time stamps (toppra/parametrizer.py:171-186): t_i = t_{i-1} + ds / mean(sd) with the two
+ * data-dependent rules (mean speed <= 1e-8 -> 5 s; increments < 1e-8 are dropped from the knot list).
+ *   sd, grid [B][G] (grid [G] if grid_shared); glen nullable (ragged); t_out, s_out [B][G]: kept time stamps and
+ *   gridpoints, compacted, tail padded with the last kept entry; nkeep out [B]. */
+int tb_spline_time_stamps(const double *sd, const double *grid, int grid_shared, const int *glen, int B, int G,
+                          double *t_out, double *s_out, int *nkeep, void *stream);
 
 /* Stand-alone batched LPs, one warp per LP — device counterparts of the reference's Python shims
  * solve_lp2d / solve_lp1d (cy_seidel_solverwrapper.pyx:42-87).

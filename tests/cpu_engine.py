@@ -49,15 +49,22 @@ def record_doubles(R):
     return (3 * int(R) + 2 + 1) & ~1
 
 
-def alloc_records(B, G, R, device):
-    W = record_doubles(R)
+def alloc_records(B, G, R, device, ubound=False):
+    W = ((3 * int(R) + 4 + 1) & ~1) if ubound else record_doubles(R)
     return torch.full((B, G, W), float("nan"), dtype=torch.float64), W
+
+
+def has_ubound(records, R):
+    return records.shape[-1] >= 3 * int(R) + 4
 
 
 def init_bounds(records, R):
     records[:, :, 3 * R] = VAR_MIN
     records[:, :, 3 * R + 1] = VAR_MAX
     records[:, :, 3 * R + 2:] = 0.0
+    if has_ubound(records, R):
+        records[:, :, 3 * R + 2] = VAR_MIN
+        records[:, :, 3 * R + 3] = VAR_MAX
 
 
 def _write_xbound(rec, R_total, xb, mode):
@@ -103,7 +110,7 @@ def coeff_velacc(ppoly, breaks, grid, vlim, alim, interp, records, R_total, row0
             rec[b, :, 2 * R_total + row0:2 * R_total + row0 + R] = torch.from_numpy(c)
     if write_xbound:
         _write_xbound(rec, R_total, xb, write_xbound)
-        rec[:, :, 3 * R_total + 2:] = 0.0
+        rec[:, :, 3 * R_total + (4 if has_ubound(rec, R_total) else 2):] = 0.0   # padding; a u-bound pair is kept
 
 
 def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
@@ -164,15 +171,33 @@ def _rows_of(records, R, b):
     return rows, rec[:, 3 * R:3 * R + 2]
 
 
+def _wrapper(records, R, b, grid, n=None):
+    """The oracle's stateful seidelWrapper restatement over path b's records (first n gridpoints of a ragged batch)."""
+    rows, xb = _rows_of(records, R, b)
+    ub = _np(records[b])[:, 3 * R + 2:3 * R + 4] if has_ubound(records, R) else None
+    if n is not None:
+        rows, xb, grid = rows[:n], xb[:n], grid[:n]
+        ub = None if ub is None else ub[:n]
+    return orc.Wrapper(np.ascontiguousarray(grid), np.ascontiguousarray(rows), np.ascontiguousarray(xb),
+                       None if ub is None else np.ascontiguousarray(ub))
+
+
 def _scalar(t, b, default=0.0):
     return default if t is None else float(_np(t).reshape(-1)[b])
 
 
+def check_glen(glen, B, grid):
+    if glen is not None and (tuple(glen.shape) != (B,) or grid.dim() != 2):
+        raise ValueError("glen must have shape (B,) and the grid (B, G)")
+
+
 def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False,
-         sd_forward=None, forward_from=None, fast_lower=False):
+         sd_forward=None, forward_from=None, fast_lower=False, glen=None):
     B, G, W = records.shape
     if sd_forward is not None:
         return _scan_sd(records, R, grid, sd_start, sd_end, sd_forward == "slow")
+    if glen is not None:
+        return _scan_ragged(records, R, grid, sd_start, sd_end, _np(glen))
     gr = _np(grid)
     K = np.zeros((B, G, 2))
     sd = np.full((B, G), np.nan)
@@ -181,8 +206,7 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     fail = np.full(B, -1, dtype=np.int32)
     cnt = np.zeros((B, 4), dtype=np.int32)
     for b in range(B):
-        rows, xb = _rows_of(records, R, b)
-        w = orc.Wrapper(_per_path(gr, b), rows, xb)
+        w = _wrapper(records, R, b, _per_path(gr, b))
         s0, s1 = _scalar(sd_start, b), _scalar(sd_end, b)
         if backward_only:
             K[b] = w.compute_controllable_sets(s1, _scalar(sd_end_hi, b, s1))
@@ -208,6 +232,22 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     if counters:
         out["counters"] = torch.from_numpy(cnt)
     return out
+
+
+def _scan_ragged(records, R, grid, sd_start, sd_end, glen):
+    """Ragged batch: path b uses its first glen[b] gridpoints; everything past them is NaN (tb_scan_ragged)."""
+    B, G, W = records.shape
+    gr = _np(grid)
+    K, sd, u = np.full((B, G, 2), np.nan), np.full((B, G), np.nan), np.full((B, G - 1), np.nan)
+    status, fail = np.zeros(B, dtype=np.int32), np.full(B, -1, dtype=np.int32)
+    for b in range(B):
+        n = int(glen[b])
+        o = _wrapper(records, R, b, gr[b], n).compute_parameterization(_scalar(sd_start, b), _scalar(sd_end, b))
+        K[b, :n], status[b] = o["K"], o["status"]
+        if o["status"] != 3:
+            sd[b, :n], u[b, :n - 1] = o["sd"], o["u"]
+    return dict(K=torch.from_numpy(K), sd=torch.from_numpy(sd), u=torch.from_numpy(u), status=torch.from_numpy(status),
+                fail_stage=torch.from_numpy(fail))
 
 
 def coeff_second_order(model, params, ppoly, breaks, grid, taulim, friction, interp, records, R_total, row0):
@@ -244,7 +284,7 @@ def xbound_constant(ppoly, breaks, grid, vlim, records, R_total, write_xbound):
 
 
 def scan_velacc(ppoly, breaks, grid, alim, interp, xbound, sd_start=None, sd_end=None, sd_end_hi=None,
-                backward_only=False, counters=False, sd_forward=None, forward_from=None, fast_lower=False):
+                backward_only=False, counters=False, sd_forward=None, forward_from=None, fast_lower=False, glen=None):
     """Double of the fused vel+acc scan: materialise the acceleration rows with the K1 double, take the velocity bound
     from `xbound`, run the record scan."""
     B, _, nseg, dof = ppoly.shape
@@ -253,7 +293,8 @@ def scan_velacc(ppoly, breaks, grid, alim, interp, xbound, sd_start=None, sd_end
     rec, _ = alloc_records(B, G, R, None)
     coeff_velacc(ppoly, breaks, grid, None, alim, interp, rec, R, 0, 0)
     rec[:, :, 3 * R:3 * R + 2] = xbound
-    return scan(rec, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters, sd_forward, forward_from, fast_lower)
+    return scan(rec, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters, sd_forward, forward_from, fast_lower,
+                glen)
 
 
 def _scan_sd(records, R, grid, sd_start, sd_end, slow):
@@ -266,9 +307,8 @@ def _scan_sd(records, R, grid, sd_start, sd_end, slow):
     xs, us = np.full((B, G), np.nan), np.full((B, G - 1), np.nan)
     status, fail = np.zeros(B, dtype=np.int32), np.full(B, -1, dtype=np.int32)
     for b in range(B):
-        rows, xb = _rows_of(records, R, b)
         g = _per_path(gr, b)
-        w = orc.Wrapper(g, rows, xb)
+        w = _wrapper(records, R, b, g)
         s0, s1 = _scalar(sd_start, b), _scalar(sd_end, b)
         K[b] = w.compute_controllable_sets(s1, s1)
         x0 = s0 * s0
@@ -317,9 +357,133 @@ def feasible_sets(records, R, grid):
     gr = _np(grid)
     X = np.empty((B, G, 2))
     for b in range(B):
-        rows, xb = _rows_of(records, R, b)
-        X[b] = orc.Wrapper(_per_path(gr, b), rows, xb).compute_feasible_sets()
+        X[b] = _wrapper(records, R, b, _per_path(gr, b)).compute_feasible_sets()
     return torch.from_numpy(X)
+
+
+def reachable_sets(records, R, grid, sdmin=None, sdmax=None):
+    """compute_reachable_sets (reachability_algorithm.py:378-431) on the oracle's STATEFUL wrapper: the feasible-set pass
+    first, then the forward recursion through solve_stagewise_optim with the warm-start slots it left behind."""
+    B, G, W = records.shape
+    gr = _np(grid)
+    X, L, fs = np.empty((B, G, 2)), np.zeros((B, G, 2)), np.full(B, -1, dtype=np.int32)
+    for b in range(B):
+        g = _per_path(gr, b)
+        w = _wrapper(records, R, b, g)
+        X[b] = w.compute_feasible_sets()
+        s0 = _scalar(sdmin, b)
+        L[b, 0] = [s0 ** 2, _scalar(sdmax, b, s0) ** 2]
+        deltas = np.diff(g)
+        for i in range(G - 1):
+            dq = deltas[i - 1]
+            obj = np.array([-2 * dq, -1.0])
+            o1 = w.solve_stagewise_optim(i, None, obj, L[b, i, 0], L[b, i, 1], X[b, i + 1, 0], X[b, i + 1, 1])
+            o0 = w.solve_stagewise_optim(i, None, -obj, L[b, i, 0], L[b, i, 1], X[b, i + 1, 0], X[b, i + 1, 1])
+            L[b, i + 1] = [o0[1] + 2 * dq * o0[0], o1[1] + 2 * dq * o1[0]]
+            if L[b, i + 1, 0] < 0:
+                L[b, i + 1, 0] = 0
+            if np.isnan(L[b, i + 1]).any():
+                fs[b] = i + 1
+                break
+    return dict(X=torch.from_numpy(X), L=torch.from_numpy(L), fail_stage=torch.from_numpy(fs))
+
+
+def propose_gridpoints(ppoly, breaks, max_err_threshold=1e-4, max_iteration=100, max_seg_length=0.05, min_nb_points=100,
+                       max_points=2048):
+    """interpolator.py:49-122 per path on the oracle's PPoly evaluation."""
+    pp, br = _np(ppoly), _np(breaks)
+    B = pp.shape[0]
+    grid = np.zeros((B, max_points))
+    glen, status = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        x = _per_path(br, b)
+        pts = [x[0], x[-1]]
+        it = 0
+        for it in range(max_iteration):
+            arr = np.asarray(pts)
+            mids, dist = 0.5 * (arr[:-1] + arr[1:]), arr[1:] - arr[:-1]
+            qss = orc.ppoly_eval(pp[b], x, mids, 2)
+            new = [mids[j] for j in range(len(mids))
+                   if dist[j] > max_seg_length or np.max(np.abs(0.5 * qss[j] * dist[j] ** 2)) > max_err_threshold]
+            pts = sorted(pts + new)
+            if not new:
+                break
+        while len(pts) < min_nb_points:
+            arr = np.asarray(pts)
+            pts = sorted(pts + list(0.5 * (arr[:-1] + arr[1:])))
+        if it == max_iteration - 1:
+            status[b] = 1
+        n = min(len(pts), max_points)
+        if len(pts) > max_points:
+            status[b] = -2
+        grid[b, :n], grid[b, n:], glen[b] = pts[:n], pts[-1], n
+    return torch.from_numpy(grid), torch.from_numpy(glen), torch.from_numpy(status)
+
+
+def _duration(xs, deltas):
+    sds = np.sqrt(xs)
+    t = 0
+    for i in range(len(deltas)):
+        t += 2 * deltas[i] / (sds[i + 1] + sds[i] + 1e-9)
+    return t
+
+
+def sd_bisect(x_fast, u_fast, x_slow, u_slow, grid, desired, atol=1e-5, status_in=None, max_iter=200):
+    """desired_duration_algorithm.py:139-191 per path."""
+    xf, uf, xs, us, gr, want = (_np(t) for t in (x_fast, u_fast, x_slow, u_slow, grid, desired))
+    B, G = xf.shape
+    sd, u = np.full((B, G), np.nan), np.full((B, G - 1), np.nan)
+    info, status = np.zeros((B, 4)), np.zeros(B, dtype=np.int32)
+    st_in = None if status_in is None else _np(status_in)
+    for b in range(B):
+        if st_in is not None and st_in[b] == 3:
+            status[b], info[b, :3] = 3, np.nan
+            continue
+        deltas = np.diff(_per_path(gr, b))
+        with np.errstate(invalid="ignore"):
+            d_fast, d_slow = _duration(xf[b], deltas), _duration(xs[b], deltas)
+            its = 0
+            if d_fast > want[b]:
+                alpha = 1.0
+            elif d_slow < want[b]:
+                alpha = 0.0
+            else:
+                lo, hi, diff, alpha = 1.0, 0.0, 10, 0.5
+                while diff > atol and its < max_iter:
+                    its += 1
+                    alpha = 0.5 * (lo + hi)
+                    d = _duration(alpha * xf[b] + (1 - alpha) * xs[b], deltas)
+                    if d < want[b]:
+                        lo, diff = alpha, want[b] - d
+                    else:
+                        hi, diff = alpha, d - want[b]
+            sd[b] = np.sqrt(alpha * xf[b] + (1 - alpha) * xs[b])
+        u[b] = alpha * uf[b] + (1 - alpha) * us[b]
+        status[b] = 1 if np.isnan(sd[b]).any() else 0
+        info[b] = [alpha, d_fast, d_slow, its]
+    return dict(sd=torch.from_numpy(sd), u=torch.from_numpy(u), info=torch.from_numpy(info), status=torch.from_numpy(status))
+
+
+def spline_time_stamps(sd, grid, glen=None):
+    """parametrizer.py:171-186 per path (compacted, tail padded with the last kept entry)."""
+    v, gr = _np(sd), _np(grid)
+    B, G = v.shape
+    t, s, nk = np.zeros((B, G)), np.zeros((B, G)), np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        g = _per_path(gr, b)
+        n = G if glen is None else int(_np(glen)[b])
+        acc, keep_t, keep_s = 0.0, [0.0], [g[0]]
+        for i in range(1, n):
+            avg = (v[b, i - 1] + v[b, i]) / 2
+            ds = g[i] - g[i - 1]
+            dt = ds / avg if avg > 1e-8 else 5
+            acc = acc + dt
+            if not dt < 1e-8:
+                keep_t.append(acc)
+                keep_s.append(g[i])
+        k = len(keep_t)
+        t[b, :k], s[b, :k], t[b, k:], s[b, k:], nk[b] = keep_t, keep_s, keep_t[-1], keep_s[-1], k
+    return torch.from_numpy(t), torch.from_numpy(s), torch.from_numpy(nk)
 
 
 # ---- LP shims -------------------------------------------------------------------------------------------------------------
@@ -388,7 +552,8 @@ class _NoStream(object):
 
 PATCHED = ("spline_fit", "ppoly_eval", "record_doubles", "alloc_records", "init_bounds", "coeff_velacc",
            "rows_canlinear", "coeff_second_order", "xbound_varying", "xbound_constant", "scan", "scan_velacc", "scan_robust", "feasible_sets", "lp2d_batch", "lp1d_batch",
-           "time_grid", "constaccel_eval")
+           "time_grid", "constaccel_eval", "has_ubound", "check_glen", "reachable_sets", "propose_gridpoints", "sd_bisect",
+           "spline_time_stamps")
 
 
 def install(monkeypatch):

@@ -439,6 +439,125 @@ def other_paths_case():
     print("other paths: statuses", [int(data[t + "_status"]) for t in ("sp_auto", "sp_yd", "poly")])
 
 
+def frows_batch_case():
+    """Rows f1-f3 + ubound for BATCHES (VERDICT r1 "next" #8, #9): 16 paths each through the reference's own
+    propose_gridpoints (ragged grids), compute_reachable_sets, TOPPRAsd, ParametrizeSpline, and a user-defined
+    LinearConstraint that returns a ubound (seidelWrapper.__init__, cy_seidel_solverwrapper.pyx:512-515)."""
+    import toppra.interpolator as interp
+    from toppra.parametrizer import ParametrizeSpline
+    B, dof = 16, 7
+    ss = np.linspace(0, 1, 5)
+    probs = [make_path(5000 + b, dof=dof) for b in range(B)]       # (way, vlim, alim)
+    way = np.stack([p[0] for p in probs])
+    vlim = np.stack([p[1] for p in probs])
+    alim = np.stack([p[2] for p in probs])
+    vlim[:4] *= 0.04                                              # some velocity-limited paths
+    data = dict(ss=ss, way=way, vlim=vlim, alim=alim)
+
+    # ---- propose_gridpoints (interpolator.py:49-122): two parameter sets, ragged results, padded with NaN
+    for tag, kw in (("pg_default", {}), ("pg_toppra", dict(max_err_threshold=1e-3, min_nb_points=100)),
+                    ("pg_coarse", dict(max_err_threshold=5e-2, max_seg_length=0.3, min_nb_points=20))):
+        grids = [np.asarray(interp.propose_gridpoints(ta.SplineInterpolator(ss, way[b]), **kw)) for b in range(B)]
+        glen = np.array([len(g) for g in grids], dtype=np.int32)
+        pad = np.full((B, glen.max()), np.nan)
+        for b, g in enumerate(grids):
+            pad[b, :len(g)] = g
+        data[tag + "_grid"], data[tag + "_len"] = pad, glen
+    # solve on the ragged pg_toppra grids (what TOPPRA(gridpoints=None) does)
+    Gmax = data["pg_toppra_grid"].shape[1]
+    rK, rsd, rsdd, rst = (np.full((B, Gmax, 2), np.nan), np.full((B, Gmax), np.nan), np.full((B, Gmax - 1), np.nan),
+                          np.zeros(B, dtype=np.int32))
+    for b in range(B):
+        n = data["pg_toppra_len"][b]
+        o, _ = solve_ref(ss, way[b], vlim[b], alim[b], data["pg_toppra_grid"][b, :n])
+        rK[b, :n], rsd[b, :n], rsdd[b, :n - 1], rst[b] = o["K"], o["sd"], o["sdd"], o["status"]
+    data.update(ragged_K=rK, ragged_sd=rsd, ragged_sdd=rsdd, ragged_status=rst)
+
+    # ---- reachable sets, TOPPRAsd, ParametrizeSpline on a shared 120-point grid
+    grid = np.linspace(0, 1, 120)
+    data["grid"] = grid
+    sdmin = np.where(np.arange(B) % 3 == 0, 0.0, 0.2)
+    sdmax = np.where(np.arange(B) % 2 == 0, sdmin, sdmin + 0.5)   # equal pairs take the 1-variable branch at stage 0
+    L = np.zeros((B, 120, 2))
+    X = np.zeros((B, 120, 2))
+    sd_out, sdd_out, sd_status = np.zeros((B, 120)), np.zeros((B, 119)), np.zeros(B, dtype=np.int32)
+    desired = np.zeros(B)
+    ps_t, ps_n = np.full((B, 120), np.nan), np.zeros(B, dtype=np.int32)
+    ts_eval = np.linspace(0, 1, 33)
+    ps_q, ps_qd, ps_qdd = (np.zeros((B, 33, dof)) for _ in range(3))
+    ps_dur = np.zeros(B)
+    for b in range(B):
+        cons = lambda: [constraint.JointVelocityConstraint(vlim[b]), constraint.JointAccelerationConstraint(alim[b])]  # noqa: E731
+        path = ta.SplineInterpolator(ss, way[b])
+        inst = algo.TOPPRA(cons(), path, gridpoints=grid, solver_wrapper="seidel")
+        X[b] = inst.compute_feasible_sets()
+        inst = algo.TOPPRA(cons(), path, gridpoints=grid, solver_wrapper="seidel")
+        L[b] = inst.compute_reachable_sets(sdmin[b], sdmax[b])
+        # fastest duration first, then a desired duration below / inside / above the achievable range
+        o, _ = solve_ref(ss, way[b], vlim[b], alim[b], grid)
+        fastest = np.sum(2 * np.diff(grid) / (o["sd"][1:] + o["sd"][:-1]))
+        desired[b] = fastest * (0.5, 1.7, 3.0, 1e6)[b % 4]
+        sdi = algo.TOPPRAsd(cons(), path, gridpoints=grid, solver_wrapper="seidel")
+        sdi.set_desired_duration(desired[b])
+        sdd_d, sd_d, _, _ = sdi.compute_parameterization(0, 0, return_data=True)
+        sd_out[b], sdd_out[b] = sd_d, sdd_d
+        sd_status[b] = list(algo.ParameterizationReturnCode).index(sdi.problem_data.return_code)
+        # ParametrizeSpline on the time-optimal velocities; path 5 gets two stationary gridpoints (5 s rule), path 6 a
+        # huge speed (increment below 1e-8 -> dropped knot)
+        vel = o["sd"].copy()
+        if b == 5:
+            vel[40:42] = 0.0
+        if b == 6:
+            vel[60:62] = 1e9
+        traj = ParametrizeSpline(path, grid, vel)
+        n = len(traj.ss_waypoints)
+        ps_t[b, :n], ps_n[b] = traj.ss_waypoints, n
+        ps_dur[b] = traj.duration
+        te = ts_eval * traj.duration
+        ps_q[b], ps_qd[b], ps_qdd[b] = traj(te), traj(te, 1), traj(te, 2)
+        data.setdefault("ps_vel", np.zeros((B, 120)))[b] = vel
+    data.update(X=X, L=L, sdmin=sdmin, sdmax=sdmax, sd_desired=desired, sd_sd=sd_out, sd_sdd=sdd_out, sd_status=sd_status,
+                ps_t=ps_t, ps_n=ps_n, ps_dur=ps_dur, ps_ts=ts_eval, ps_q=ps_q, ps_qd=ps_qd, ps_qdd=ps_qdd)
+
+    # ---- ubound from a constraint: acceleration rows + a u-interval that tightens with s (and an x-bound), 8 paths
+    class UBoundConstraint(constraint.LinearConstraint):
+        def __init__(self, acc, ulim):
+            super(UBoundConstraint, self).__init__()
+            self.acc, self.ulim = acc, ulim
+            self.discretization_type = acc.discretization_type
+            self.identical = True
+
+        def get_dof(self):
+            return self.acc.get_dof()
+
+        def compute_constraint_params(self, path, gridpoints, *a):
+            pa, pb, pc, F, g, _, _ = self.acc.compute_constraint_params(path, gridpoints)
+            n = len(gridpoints)
+            ub = np.stack((-self.ulim * (1.0 + gridpoints), self.ulim * (2.0 - gridpoints)), axis=1)
+            xb = np.stack((np.zeros(n), 40.0 + 30 * gridpoints), axis=1)
+            return pa, pb, pc, F, g, ub, xb
+
+    ub_K, ub_sd, ub_sdd, ub_status, ub_X, ub_L = ([] for _ in range(6))
+    ulims = np.array([0.3, 0.1, 0.12, 0.08, 0.6, 0.4, 0.5, 0.2])
+    for b in range(8):
+        path = ta.SplineInterpolator(ss, way[b])
+        mk = lambda: [constraint.JointVelocityConstraint(vlim[b]),  # noqa: E731
+                      UBoundConstraint(constraint.JointAccelerationConstraint(alim[b]), ulims[b])]
+        inst = algo.TOPPRA(mk(), path, gridpoints=grid, solver_wrapper="seidel")
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        ub_K.append(K)
+        ub_status.append(list(algo.ParameterizationReturnCode).index(inst.problem_data.return_code))
+        ub_sd.append(np.full(120, np.nan) if sd is None else sd)
+        ub_sdd.append(np.full(119, np.nan) if sdd is None else sdd)
+        ub_X.append(algo.TOPPRA(mk(), path, gridpoints=grid, solver_wrapper="seidel").compute_feasible_sets())
+        ub_L.append(algo.TOPPRA(mk(), path, gridpoints=grid, solver_wrapper="seidel").compute_reachable_sets(0.0, 0.3))
+    data.update(ub_ulim=ulims, ub_K=np.stack(ub_K), ub_sd=np.stack(ub_sd), ub_sdd=np.stack(ub_sdd),
+                ub_status=np.array(ub_status, dtype=np.int32), ub_X=np.stack(ub_X), ub_L=np.stack(ub_L))
+    np.savez_compressed(os.path.join(HERE, "frows_batch.npz"), **data)
+    print("frows_batch: grid lengths", data["pg_toppra_len"], "| sd status", sd_status, "| kept knots", ps_n,
+          "| ubound status", ub_status)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "shortcut_rows":
         shortcut_rows_case()
@@ -448,7 +567,10 @@ if __name__ == "__main__":
         joint_torque_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "other_paths":
         other_paths_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "frows_batch":
+        frows_batch_case()
     else:
         main()
         joint_torque_case()
         other_paths_case()
+        frows_batch_case()

@@ -10,16 +10,17 @@ from . import constants, exceptions
 from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, PolynomialPath, PPolyPath,
                            SplineInterpolator, propose_gridpoints)
 from .simplepath import SimplePath
-from .parametrizer import BatchParametrizeConstAccel, ParametrizeConstAccel, ParametrizeSpline
+from .parametrizer import (BatchParametrizeConstAccel, BatchParametrizeSpline, ParametrizeConstAccel,
+                           ParametrizeSpline)
 from . import constraint
 from . import solverwrapper
 from . import algorithm
-from .batch import BatchResult, BatchTOPPRA, solve_batch
+from .batch import BatchResult, BatchTOPPRA, BatchTOPPRAsd, solve_batch
 
 __version__ = "0.1.0"
 
 logging.getLogger("toppra_b200").addHandler(logging.NullHandler())
 
 __all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "PPolyPath", "PolynomialPath", "SimplePath", "SplineInterpolator", "propose_gridpoints",
-           "ParametrizeConstAccel", "ParametrizeSpline", "BatchParametrizeConstAccel", "constraint", "solverwrapper", "algorithm", "BatchResult",
-           "BatchTOPPRA", "solve_batch", "constants", "exceptions"]
+           "ParametrizeConstAccel", "ParametrizeSpline", "BatchParametrizeConstAccel", "BatchParametrizeSpline", "constraint", "solverwrapper", "algorithm", "BatchResult",
+           "BatchTOPPRA", "BatchTOPPRAsd", "solve_batch", "constants", "exceptions"]

@@ -47,6 +47,18 @@ _PROTOS = {
     "tb_constaccel_eval": ([_c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _int, _int, _c_dp, _int,
                             _int, _int, _c_dp, ctypes.c_void_p], _int),
     "tb_feasible_sets": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
+    "tb_feasible_sets_ex": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _int, _c_dp, ctypes.c_void_p], _int),
+    "tb_reachable_sets": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_dp, _c_dp, _int, _c_dp, _c_dp, _c_ip,
+                           ctypes.c_void_p], _int),
+    "tb_scan_ragged": ([_c_dp, _int, _int, _c_dp, _int, _int, _int, _c_ip, _c_dp, _c_dp, _c_dp, _int, _c_dp, _c_dp, _c_dp,
+                        _c_ip, _c_ip, _c_ip, ctypes.c_void_p], _int),
+    "tb_scan_velacc_ragged": ([_c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _int, _int, _c_ip, _c_dp, _int, _int, _c_dp,
+                               _c_dp, _c_dp, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_ip, _c_ip, _c_ip, ctypes.c_void_p], _int),
+    "tb_propose_gridpoints": ([_c_dp, _c_dp, _int, _int, _int, _int, ctypes.c_double, _int, ctypes.c_double, _int, _int,
+                               _c_dp, _c_dp, _c_ip, _c_ip, ctypes.c_void_p], _int),
+    "tb_sd_bisect": ([_c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _c_dp, ctypes.c_double, _int, _c_ip, _c_dp,
+                      _c_dp, _c_dp, _c_ip, ctypes.c_void_p], _int),
+    "tb_spline_time_stamps": ([_c_dp, _c_dp, _int, _c_ip, _int, _int, _c_dp, _c_dp, _c_ip, ctypes.c_void_p], _int),
     "tb_solve_velacc_host": ([_int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _c_dp, _c_dp, _int, _int, _c_dp,
                               _c_dp, _c_dp, _c_dp, _c_dp, _c_ip], _int),
 }

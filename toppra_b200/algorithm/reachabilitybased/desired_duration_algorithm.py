@@ -1,9 +1,11 @@
 """TOPPRAsd — TOPP-RA with a specified duration; same surface as the reference
-`toppra/algorithm/reachabilitybased/desired_duration_algorithm.py:20-234` (SURVEY §8 f3).
+`toppra/algorithm/reachabilitybased/desired_duration_algorithm.py:20-234` (SURVEY section 8 f3).
 
-The fastest and the slowest parameterisations are two launches of the scan kernel (csrc/tb_scan.cu, flags
-TB_SCAN_SD_FORWARD / TB_SCAN_SD_SLOW: the reference's TOPPRAsd forward rules — no retry, x_next - 1e-5 clip); the
-bisection on their convex combination is O(N) host arithmetic on two vectors, written like the reference."""
+Everything runs on the GPU: the controllable sets and the fastest pass are one scan launch (csrc/tb_scan.cu, flag
+TB_SCAN_SD_FORWARD: the reference's TOPPRAsd forward rules — no retry, x_next - 1e-5 clip), the slowest pass a second one
+(TB_SCAN_SD_SLOW), and the bisection on the blend alpha * fastest + (1 - alpha) * slowest is tb_sd_bisect
+(csrc/tb_frows.cu), which keeps the reference's running duration sum.  This class is the B = 1 case of
+`toppra_b200.BatchTOPPRAsd`."""
 import logging
 
 import numpy as np
@@ -14,25 +16,19 @@ from .. import algorithm as algo
 logger = logging.getLogger(__name__)
 
 
-def _compute_duration(xs, deltas):
-    sds = np.sqrt(xs)
-    t = 0
-    for i in range(len(deltas)):
-        t += 2 * deltas[i] / (sds[i + 1] + sds[i] + 1e-9)
-    return t
-
-
 class TOPPRAsd(ReachabilityAlgorithm):
-    """TOPPRA with specified duration: bisection between the fastest and the slowest parameterisation."""
+    """TOPPRA with specified duration: a convex combination of the fastest and the slowest parameterisation."""
 
     def set_desired_duration(self, desired_duration: float):
         self.desired_duration = desired_duration
 
     def compute_parameterization(self, sd_start, sd_end, return_data=False, atol=1e-5):
+        """(sdd_vec, sd_vec, v_vec[, K]) like the reference; (None, None, None[, K]) when the instance is not
+        controllable.  An unachievable duration returns the fastest / slowest parameterisation (reference :143-152)."""
         assert sd_end >= 0 and sd_start >= 0, "Path velocities must be positive"
-        fast = self.solver_wrapper.parameterize(sd_start, sd_end, sd_forward="fast")
-        K = fast["K"]
-        if algo.STATUS_CODES[fast["status"]] == algo.ParameterizationReturnCode.FailUncontrollable:
+        res = self.solver_wrapper.parameterize_sd(sd_start, sd_end, self.desired_duration, atol)
+        K = res["K"]
+        if algo.STATUS_CODES[res["status"]] == algo.ParameterizationReturnCode.FailUncontrollable:
             if np.isnan(K).any():
                 logger.warning("The set of controllable velocities at the beginning is empty!")
             else:
@@ -41,44 +37,17 @@ class TOPPRAsd(ReachabilityAlgorithm):
             self._problem_data.return_code = algo.ParameterizationReturnCode.FailUncontrollable
             return (None, None, None, K) if return_data else (None, None, None)
         self.problem_data.K = K
-        slow = self.solver_wrapper.parameterize(sd_start, sd_end, sd_forward="slow")
-        deltas = self.solver_wrapper.get_deltas()
-        # with sd_forward the kernel returns the squared velocities x (TOPPRAsd combines those)
-        xs, us = fast["sd"], fast["u"]
-        xs_slow, us_slow = slow["sd"], slow["u"]
-        N = self._N
-        v_vec_alpha = np.zeros((N, self.solver_wrapper.get_no_vars() - 2))
-        duration = _compute_duration(xs, deltas)
-        duration_slow = _compute_duration(xs_slow, deltas)
-        if duration > self.desired_duration:
+        alpha, fastest, slowest = res["alpha"], res["duration_fast"], res["duration_slow"]
+        if fastest > self.desired_duration:
             logger.warning("Desired duration %f seconds is not achievable. Returning the fastest parameterization "
-                           "with duration %f seconds", self.desired_duration, duration)
-            alpha = 1.0
-        elif duration_slow < self.desired_duration:
+                           "with duration %f seconds", self.desired_duration, fastest)
+        elif slowest < self.desired_duration:
             logger.warning("Desired duration %f seconds is not achievable. Returning the slowest parameterization "
-                           "with duration %f seconds", self.desired_duration, duration_slow)
-            alpha = .0
-        else:
-            alpha_low, alpha_high, diff = 1.0, 0.0, 10
-            while diff > atol:
-                alpha = 0.5 * (alpha_low + alpha_high)
-                duration_alpha = _compute_duration(alpha * xs + (1 - alpha) * xs_slow, deltas)
-                if duration_alpha < self.desired_duration:
-                    alpha_low = alpha
-                    diff = self.desired_duration - duration_alpha
-                else:
-                    alpha_high = alpha
-                    diff = duration_alpha - self.desired_duration
-        xs_alpha = alpha * xs + (1 - alpha) * xs_slow
-        us_alpha = alpha * us + (1 - alpha) * us_slow
-        sd_vec = np.sqrt(xs_alpha)
-        sdd_vec = np.copy(us_alpha)
-        self.problem_data.sd_vec = sd_vec
-        self.problem_data.sdd_vec = sdd_vec
-        if np.isnan(sd_vec).any():
-            self.problem_data.return_code = algo.ParameterizationReturnCode.ErrUnknown
-        else:
-            self.problem_data.return_code = algo.ParameterizationReturnCode.Ok
+                           "with duration %f seconds", self.desired_duration, slowest)
+        self.alpha = alpha
+        self.problem_data.sd_vec, self.problem_data.sdd_vec = res["sd"], res["u"]
+        self.problem_data.return_code = algo.STATUS_CODES[res["blend_status"]]
+        v_vec = np.zeros((self._N, self.solver_wrapper.get_no_vars() - 2))
         if return_data:
-            return sdd_vec, sd_vec, v_vec_alpha, K
-        return sdd_vec, sd_vec, v_vec_alpha
+            return res["u"], res["sd"], v_vec, K
+        return res["u"], res["sd"], v_vec

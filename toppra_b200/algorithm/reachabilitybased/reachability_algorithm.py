@@ -58,37 +58,15 @@ class ReachabilityAlgorithm(ParameterizationAlgorithm):
             logger.warning("A numerical error occurs: The controllable set can't be computed.")
         return K
 
-    def _one_step_forward(self, i, L_current, feasible_set_next):
-        """One forward step of the reachable-set recursion (reference :378-407, including its use of
-        deltas[i - 1]); two stage LPs through the solver wrapper's per-stage interface."""
-        res = np.zeros(2)
-        if np.isnan(L_current).any() or i < 0 or i > self._N:
-            res[:] = np.nan
-            return res
-        deltas = self.solver_wrapper.get_deltas()[i - 1]
-        g_upper = np.array([-2 * deltas, -1.0])
-        opt_1 = self.solver_wrapper.solve_stagewise_optim(i, None, g_upper, L_current[0], L_current[1],
-                                                          feasible_set_next[0], feasible_set_next[1])
-        x_upper = opt_1[1] + 2 * deltas * opt_1[0]
-        opt_0 = self.solver_wrapper.solve_stagewise_optim(i, None, -g_upper, L_current[0], L_current[1],
-                                                          feasible_set_next[0], feasible_set_next[1])
-        x_lower = opt_0[1] + 2 * deltas * opt_0[0]
-        res[:] = [x_lower, x_upper]
-        return res
-
     def compute_reachable_sets(self, sdmin, sdmax):
-        """Sets of reachable squared velocities L (N+1, 2) (reference :409-431).  Not a hot path: 2N small launches."""
+        """Sets of reachable squared velocities L (N+1, 2) (reference :378-431): the feasible-set pass and the forward
+        recursion run as ONE launch of tb_reachable_sets (csrc/tb_scan.cu) — the B = 1 case of
+        `BatchTOPPRA.compute_reachable_sets`.  Rows after a failed stage stay 0 like the reference's."""
         assert sdmin <= sdmax and 0 <= sdmin
-        feasible_sets = self.compute_feasible_sets()
-        L = np.zeros((self._N + 1, 2))
-        L[0] = [sdmin ** 2, sdmax ** 2]
-        for i in range(0, self._N):
-            L[i + 1] = self._one_step_forward(i, L[i], feasible_sets[i + 1])
-            if L[i + 1, 0] < 0:
-                L[i + 1, 0] = 0
-            if np.isnan(L[i + 1]).any():
-                logger.warning("L[{:d}]={:}. Path not parametrizable.".format(i + 1, L[i + 1]))
-                return L
+        X, L, fail_stage = self.solver_wrapper.reachable_sets(sdmin, sdmax)
+        self._problem_data.X = X
+        if fail_stage >= 0:
+            logger.warning("L[{:d}]={:}. Path not parametrizable.".format(fail_stage, L[fail_stage]))
         return L
 
     def compute_parameterization(self, sd_start, sd_end, return_data=False):

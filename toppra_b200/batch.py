@@ -44,10 +44,13 @@ def build_records(ctx, constraints, out=None):
             raise NotImplementedError("constraint type %s cannot be turned into stage rows" % c.get_constraint_type())
     rows = [c.num_rows(ctx) for c in constraints]
     R = int(sum(rows))
+    ubound = any(getattr(c, "has_ubound", lambda _ctx: False)(ctx) for c in constraints)
+    if ubound and conic:
+        raise NotImplementedError("toppra_b200: a constraint with a ubound next to a robust (conic) constraint")
     if out is not None:
         records = out[:ctx.B]
     else:
-        records, _ = engine.alloc_records(ctx.B, ctx.G, R, ctx.device)
+        records, _ = engine.alloc_records(ctx.B, ctx.G, R, ctx.device, ubound=ubound)
     kinds = [type(c) for c in constraints]
     if (len(constraints) == 2 and JointVelocityConstraint in kinds and JointAccelerationConstraint in kinds):
         # headline case: one fused K1 launch writes the velocity bound and the acceleration rows
@@ -108,20 +111,42 @@ class BatchTOPPRA(object):
     gridpoints: (G,) shared by all paths, or (B, G); must start/end at the path interval.
     """
 
-    def __init__(self, constraint_list, path, gridpoints, max_record_bytes=32 << 30, exact=True, validate=True,
-                 fused=None):
+    def __init__(self, constraint_list, path, gridpoints=None, max_record_bytes=32 << 30, exact=True, validate=True,
+                 fused=None, glen=None, gridpt_max_err_threshold=1e-3, gridpt_min_nb_points=100):
         if not isinstance(path, BatchSplineInterpolator):
             raise TypeError("BatchTOPPRA needs a BatchSplineInterpolator")
         torch = engine.torch_mod()
         self.constraints = constraint_list
         self.path = path
         self.device = path.device
+        if gridpoints is None:
+            # reference algorithm.py:100-106: gridpoints proposed per path (interpolator.propose_gridpoints) -> RAGGED
+            # grids [B, Gmax] + lengths, solved in one launch (tb_scan_ragged / tb_scan_velacc_ragged)
+            gridpoints, glen = path.propose_gridpoints(max_err_threshold=gridpt_max_err_threshold,
+                                                       min_nb_points=gridpt_min_nb_points)
+            validate = False   # the proposed grids span the path interval and increase by construction
+        self.glen = None if glen is None else engine.as_device(glen, self.device, dtype=torch.int32)
         gp = engine.host_view(gridpoints)  # None for CUDA tensors
         grid_host = gp if (gp is not None and gp.ndim == 1) else None
         self.d_grid = engine.as_device(gridpoints, self.device)
         if self.d_grid.dim() not in (1, 2) or (self.d_grid.dim() == 2 and self.d_grid.shape[0] != path.B):
             raise ValueError("gridpoints must have shape (G,) or (B, G)")
-        if validate:
+        if self.glen is not None:
+            engine.check_glen(self.glen, path.B, self.d_grid)
+        if validate and self.glen is not None:
+            # ragged grids: the last REAL gridpoint of every path must be the end of its interval; padding is ignored
+            g, ss = self.d_grid, path.d_ss
+            last = torch.gather(g, 1, (self.glen.to(torch.int64) - 1).clamp(min=0).unsqueeze(1))[:, 0]
+            col = torch.arange(g.shape[1], device=g.device).unsqueeze(0)
+            real = col[:, 1:] < self.glen.unsqueeze(1)
+            t = ((g[:, 0] != ss[..., 0]).any() | (last != ss[..., -1]).any()).to(torch.int32)
+            t = t + 2 * ((g[:, 1:] <= g[:, :-1]) & real).any().to(torch.int32)
+            code = int(t)
+            if code & 1:
+                raise ValueError("Invalid manually supplied gridpoints.")
+            if code & 2:
+                raise ValueError("Bad input gridpoints.")
+        elif validate:
             # reference algorithm.py:107-120: gridpoints must span exactly the path interval ("Invalid manually supplied
             # gridpoints.") and increase strictly ("Bad input gridpoints.").  Host data is checked on the host (no
             # device synchronisation); CUDA tensors with one small reduction.
@@ -209,9 +234,12 @@ class BatchTOPPRA(object):
         self._ready()
         if self.fused:
             return engine.scan_velacc(self.path.d_ppoly, self.path.d_ss, self.d_grid, self._alim, self._interp,
-                                      self.xbound, s0, s1, sd_end_hi, fast_lower=not self.exact, **kw)
+                                      self.xbound, s0, s1, sd_end_hi, fast_lower=not self.exact, glen=self.glen, **kw)
         if self.conic is None:
-            return engine.scan(self.records, self.R, self.d_grid, s0, s1, sd_end_hi, fast_lower=not self.exact, **kw)
+            return engine.scan(self.records, self.R, self.d_grid, s0, s1, sd_end_hi, fast_lower=not self.exact,
+                               glen=self.glen, **kw)
+        if self.glen is not None:
+            raise NotImplementedError("robust problems on ragged grids")
         if sd_end_hi is not None:
             raise NotImplementedError("robust problems: compute_controllable_sets needs sdmin == sdmax")
         kw.pop("forward_from", None)
@@ -310,6 +338,8 @@ class BatchTOPPRA(object):
         nchunk = self.chunk_size()
         if nchunk >= self.B:
             return BatchResult(self._scan(s0, s1, counters=counters))
+        if self.glen is not None:
+            raise NotImplementedError("ragged grids with chunked stage records: raise max_record_bytes or split the batch")
         B, G, dev = self.B, self.G, self.device
         out = dict(K=torch.empty((B, G, 2), dtype=torch.float64, device=dev),
                    sd=torch.empty((B, G), dtype=torch.float64, device=dev),
@@ -344,13 +374,52 @@ class BatchTOPPRA(object):
                          backward_only=True)
         return out["K"], out["status"]
 
+    def compute_reachable_sets(self, sdmin, sdmax):
+        """Reachable sets L [B, G, 2] of every path (reference compute_reachable_sets, reachability_algorithm.py:378-431)
+        in one launch of tb_reachable_sets (feasible-set pass + forward recursion).  Returns (L, X, fail_stage)."""
+        if self.conic is not None or self.glen is not None:
+            raise NotImplementedError("compute_reachable_sets: linear problems on a common grid length only")
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmin, dtype=np.float64), (self.B,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(sdmax, dtype=np.float64), (self.B,)))
+        assert np.all(lo <= hi) and np.all(0 <= lo)
+        if self.records is None:
+            self.records, self.R = build_records(self.ctx, self.constraints)
+        out = engine.reachable_sets(self.records, self.R, self.d_grid, engine.as_device(lo, self.device),
+                                    engine.as_device(hi, self.device))
+        return out["L"], out["X"], out["fail_stage"]
+
     def compute_feasible_sets(self):
+        if self.glen is not None:
+            raise NotImplementedError("compute_feasible_sets on ragged grids")
         if self.records is None:  # feasible sets read stage records (also for problems whose scan is fused)
             self.records, self.R = build_records(self.ctx, self.constraints)
         if self.conic is not None:
             return engine.scan_robust(self.records, self.R, self.conic[0], self.conic[1], self.conic[2], self.d_grid,
                                       feasible_sets=True)["K"]
         return engine.feasible_sets(self.records, self.R, self.d_grid)
+
+
+class BatchTOPPRAsd(BatchTOPPRA):
+    """TOPPRAsd (reference desired_duration_algorithm.py:20-234) for B paths: every path gets the convex combination of
+    its fastest and slowest parameterisation whose duration is `desired_duration` (scalar or [B]); unachievable
+    durations return the fastest / slowest one.  Three launches: two scans (TB_SCAN_SD_FORWARD [| TB_SCAN_SD_SLOW]) and
+    the per-path bisection tb_sd_bisect (csrc/tb_frows.cu)."""
+
+    def set_desired_duration(self, desired_duration):
+        self.desired_duration = desired_duration
+
+    def compute_parameterization(self, sd_start=0.0, sd_end=0.0, atol=1e-5):
+        if self.conic is not None or self.glen is not None or self.chunk_size() < self.B:
+            raise NotImplementedError("BatchTOPPRAsd: linear problems on a common grid length in one chunk only")
+        s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
+        want = np.ascontiguousarray(np.broadcast_to(np.asarray(self.desired_duration, dtype=np.float64), (self.B,)))
+        fast = self._scan(s0, s1, sd_forward="fast")
+        slow = self._scan(s0, s1, sd_forward="slow")
+        out = engine.sd_bisect(fast["sd"], fast["u"], slow["sd"], slow["u"], self.d_grid,
+                               engine.as_device(want, self.device), atol, status_in=fast["status"])
+        res = BatchResult(dict(K=fast["K"], sd=out["sd"], u=out["u"], status=out["status"], fail_stage=fast["fail_stage"]))
+        res.alpha, res.duration_fast, res.duration_slow = out["info"][:, 0], out["info"][:, 1], out["info"][:, 2]
+        return res
 
 
 def solve_batch(ss_waypoints, waypoints, gridpoints, vlim, alim, sd_start=0.0, sd_end=0.0,

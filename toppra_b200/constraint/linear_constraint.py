@@ -31,17 +31,30 @@ class LinearConstraint(Constraint):
             return 0
         return F.shape[0] if self.identical else F.shape[1]
 
+    def has_ubound(self, ctx):
+        """True if this constraint returns a `ubound` (then the stage records carry a u-bound pair, TB_SCAN_UBOUND).
+        Constraints with their own device implementation never do; user-defined subclasses are asked through their
+        host 7-tuple."""
+        if type(self).append_records is not LinearConstraint.append_records:
+            return False
+        return self._host_params(ctx)[5] is not None
+
     def append_records(self, ctx, records, R_total, row0):
-        """Write this constraint's rows [row0, row0+num_rows) and intersect its x bounds into `records`.
+        """Write this constraint's rows [row0, row0+num_rows) and intersect its x / u bounds into `records`.
 
         Default implementation for user-defined subclasses: take the host 7-tuple from
         `compute_constraint_params` (single path only) and assemble F.a, F.b, F.c - g on the device
         (seidelWrapper.__init__, cy_seidel_solverwrapper.pyx:474-520)."""
         torch = engine.torch_mod()
         a, b, c, F, g, ubound, xbound = self._host_params(ctx)
-        if ubound is not None:
-            raise NotImplementedError("toppra_b200: ubound from a constraint is not supported")
         dev = records.device
+        if ubound is not None:
+            # seidelWrapper.__init__ (pyx:512-515): low[i, 0] = max(low, ubound[i, 0]), high[i, 0] = min(high, ubound[i, 1])
+            if not engine.has_ubound(records, R_total):
+                raise ValueError("stage records without a u-bound pair: allocate them with alloc_records(..., ubound=True)")
+            ub = engine.as_device(np.asarray(ubound, dtype=np.float64)[None], dev)
+            records[:, :, 3 * R_total + 2] = torch.maximum(records[:, :, 3 * R_total + 2], ub[:, :, 0])
+            records[:, :, 3 * R_total + 3] = torch.minimum(records[:, :, 3 * R_total + 3], ub[:, :, 1])
         if a is not None:
             d = lambda x: engine.as_device(np.asarray(x, dtype=np.float64)[None], dev)  # noqa: E731
             if self.identical:

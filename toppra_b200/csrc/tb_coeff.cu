@@ -88,7 +88,10 @@ coeff_velacc_kernel(const double *__restrict__ ppoly, const double *__restrict__
       else if (kind == 1) code = (unsigned short)((second ? 3 * dof + k : 2 * dof + k) | (neg << 15));
       else code = (unsigned short)(neg ? 5 * dof + k : 4 * dof + k);
     } else if (w >= 3 * R_total) {
-      if (write_xbound) code = (unsigned short)(w == 3 * R_total ? 6 * dof : (w == 3 * R_total + 1 ? 6 * dof + 1 : 6 * dof + 2));
+      // xlo | xhi | padding zeros; records with a u-bound pair (W >= 3R+4, TB_SCAN_UBOUND) keep those two slots
+      const bool ub_slot = (W >= 3 * R_total + 4) && (w == 3 * R_total + 2 || w == 3 * R_total + 3);
+      if (write_xbound && !ub_slot)
+        code = (unsigned short)(w == 3 * R_total ? 6 * dof : (w == 3 * R_total + 1 ? 6 * dof + 1 : 6 * dof + 2));
     }
     tab[w] = code;
   }
@@ -431,7 +434,13 @@ __global__ void init_bounds_kernel(double *__restrict__ records, const long BG, 
     double *rec = records + idx * W;
     rec[3 * R_total] = VAR_MIN;
     rec[3 * R_total + 1] = VAR_MAX;
-    for (int j = 3 * R_total + 2; j < W; ++j) rec[j] = 0.0;
+    int j = 3 * R_total + 2;
+    if (W >= 3 * R_total + 4) {  // records with a u-bound pair (TB_SCAN_UBOUND): u in [-1e8, 1e8] by default
+      rec[j] = VAR_MIN;
+      rec[j + 1] = VAR_MAX;
+      j += 2;
+    }
+    for (; j < W; ++j) rec[j] = 0.0;
   }
 }
 

@@ -464,24 +464,37 @@ struct VelAccSrc {
   int breaks_shared, nseg, dof, lim_shared;
 };
 
-template <int RPL, int WARPS, int MINB, bool FAST, int CFLAGS = -1, bool FUSED = false>
+// UB: the stage records carry a u-bound pair (ulo, uhi) behind the x-bound pair (TB_SCAN_UBOUND: `ubound` of a
+// constraint, intersected into low/high[:, 0] by seidelWrapper.__init__, pyx:512-515); otherwise u in [-1e8, 1e8].
+// glen (optional): ragged batches, path p has glen[p] <= G gridpoints (strides stay G; outputs past glen[p] are NaN).
+template <int RPL, int WARPS, int MINB, bool FAST, int CFLAGS = -1, bool FUSED = false, bool UB = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 scan_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
             const int grid_shared, const int B, const int G, const double *__restrict__ sd_start,
             const double *__restrict__ sd_end, const double *__restrict__ sd_end_hi, const int flags_arg,
             double *__restrict__ Kout, double *__restrict__ sdout, double *__restrict__ uout,
             int *__restrict__ status, int *__restrict__ fail_stage, int *__restrict__ counters,
-            const VelAccSrc src) {
+            const int *__restrict__ glen, const VelAccSrc src) {
   static_assert(!FUSED || RPL == 1, "the fused row source holds one row per lane");
+  static_assert(!(FUSED && UB), "velocity + acceleration problems have no u-bound");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = (WARPS == 1) ? 0 : (int)(threadIdx.x >> 5), lane = (WARPS == 1) ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  const int warp = (WARPS == 1) ? 0 : (int)(threadIdx.x >> 5);
+  int lane;
+  if (WARPS == 1) {
+    // read once and keep: the optimiser otherwise re-reads the special register (S2R, ~20 cycles) at every use when it
+    // runs short of registers
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(lane));
+  } else {
+    lane = (int)(threadIdx.x & 31);
+  }
   const long path = (long)blockIdx.x * WARPS + warp;
   if (path >= B) return;
   // shared-memory plan per warp.  records: ring of SCAN_NBUF stage records + mbarriers; FUSED: derivative coefficients
   // of the path's PPoly dco [nseg][dof][5] + breakpoints [nseg+1] (in W doubles; W = that size rounded up to even)
   double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (FUSED ? 1 : SCAN_NBUF) * W;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * (FUSED ? 1 : SCAN_NBUF) * W * sizeof(double)) + warp * SCAN_NBUF;
-  const int N = G - 1, nC = R + 2;
+  const int Gp = glen ? min(max(glen[path], 1), G) : G;  // this path's gridpoints
+  const int N = Gp - 1, nC = R + 2;
   const unsigned rec_bytes = (unsigned)(W * sizeof(double));
   // Per-path base pointers live in shared memory: under the 64-register cap the compiler otherwise rebuilds them
   // from blockIdx and the kernel parameters (a chain of 64-bit multiplies) at every use inside the stage loops.
@@ -589,7 +602,10 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     rc = f_c;
   };
 
-  // instrumentation: projected re-solves, retries, fast-mode stages; the LP counts are derived from the stage counts
+  // instrumentation: projected re-solves, retries, fast-mode stages; the LP counts are derived from the stage counts.
+  // Only the run-time-flag build (CFLAGS < 0) carries the counters: the launchers route instrumented launches there, so
+  // the specialised builds do not spend three registers on them.
+  constexpr bool COUNT = (CFLAGS < 0);
   int n_resolve = 0, n_retry = 0, n_fast = 0;
   double a[RPL], b[RPL], c[RPL];
 
@@ -618,6 +634,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     const double g0 = gq[i], g1 = gq[i + 1];
     const double delta = g1 - g0;
     double xlo, xhi;
+    double ulo = VAR_MIN, uhi = VAR_MAX;
     if constexpr (FUSED) {
       fused_row(g0, g1, true, delta, a[0], b[0], c[0]);
       xlo = xb_ahead.x;
@@ -628,6 +645,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       load_rows<RPL>(rec, R, nC, lane, a, b, c);
       xlo = rec[3 * R];
       xhi = rec[3 * R + 1];
+      if constexpr (UB) { ulo = rec[3 * R + 2]; uhi = rec[3 * R + 3]; }
       __syncwarp();
       if (i - AHEAD >= 0) issue(i - AHEAD);
     }
@@ -635,14 +653,14 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     // low/high: pyx:587-601 with x_min = x_max = NaN
     double uu, xx;
     // x_upper: g = (1e-9, -1) -> v = (-1e-9, 1), slot active_c_down (g[1] <= 0), reachability_algorithm.py:229-233
-    const bool ok_hi = lp2d_warp<RPL, true>(-1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
+    const bool ok_hi = lp2d_warp<RPL, true>(-1e-9, 1.0, a, b, c, nC, ulo, uhi, xlo, xhi, dn0, dn1, uu, xx, lane,
                                       n_resolve);
     const double x_upper = ok_hi ? xx : __longlong_as_double(0x7ff8000000000000LL);
     // x_lower: g = (-1e-9, 1) -> v = (1e-9, -1), slot active_c_up, reachability_algorithm.py:234-236
     bool ok_lo;
     double x_lower;
     double ufeas;
-    if (fast_lower && xlo <= xhi && lp1d_fixed_x_warp<RPL>(1.0, xlo, a, b, c, VAR_MIN, VAR_MAX, ufeas)) {
+    if (fast_lower && xlo <= xhi && lp1d_fixed_x_warp<RPL>(1.0, xlo, a, b, c, ulo, uhi, ufeas)) {
       // TB_SCAN_FAST_LOWER: some u is feasible at x = xlo, so min x IS xlo.  The reference reaches the same vertex
       // through ~4 projected re-solves and returns xlo plus rounding noise of its projection arithmetic
       // (|noise| <= ~1e-16, 5 % of the stages): this shortcut is exact for the LP, not bit-identical to that noise.
@@ -650,7 +668,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       x_lower = xlo;
       ++n_fast;
     } else {
-        ok_lo = lp2d_warp<RPL, true>(1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+        ok_lo = lp2d_warp<RPL, true>(1e-9, -1.0, a, b, c, nC, ulo, uhi, xlo, xhi, up0, up1, uu, xx, lane,
                                    n_resolve);
       x_lower = ok_lo ? xx : __longlong_as_double(0x7ff8000000000000LL);
     }
@@ -666,7 +684,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     kn0 = x_lower;
     kn1 = x_upper;
   }
-  if (counters && lane == 0 && !forward_only) {
+  if (COUNT && counters && lane == 0 && !forward_only) {
     // backward stages entered: N, or N - fstage when stage fstage failed; 2 LPs each (fast mode: n_fast of them 1-variable)
     const int nb = (st == TB_STATUS_OK) ? N : N - fstage;
     counters[path * 4 + 0] = 2 * nb - n_fast;
@@ -678,6 +696,10 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
 
   const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
   const double x_start = sds * sds;
+  if (Gp < G && !forward_only) {  // ragged batch: K entries past this path's grid are NaN
+    double *kq = Kp();
+    for (int j = 2 * Gp + lane; j < 2 * G; j += 32) kq[j] = nan_d;
+  }
   if (backward_only) {
     if (lane == 0) {
       status[path] = st;
@@ -690,7 +712,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     if (x_start + ALG_SMALL < kn0 || kn1 + ALG_SMALL < x_start) { st = TB_STATUS_FAIL_UNCONTROLLABLE; fstage = 0; }
   }
   if (st != TB_STATUS_OK) {
-    for (int j = lane; j < G; j += 32) sdp[j] = nan_d;
+    for (int j = lane; j < Gp; j += 32) sdp[j] = nan_d;
     for (int j = lane; j < N; j += 32) up[j] = nan_d;
   } else {
     // ---------------- forward pass, reachability_algorithm.py:303-364 ----------------
@@ -704,11 +726,13 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       const double *gq = gp();
       const double g0 = gq[i], g1 = gq[i + 1];
       const double delta = g1 - g0;
+      double f_ulo = VAR_MIN, f_uhi = VAR_MAX;
       if constexpr (FUSED) {
         fused_row(g0, g1, false, delta, a[0], b[0], c[0]);
       } else {
         const double *rec = acquire();
         load_rows<RPL>(rec, R, nC, lane, a, b, c);
+        if constexpr (UB) { f_ulo = rec[3 * R + 2]; f_uhi = rec[3 * R + 3]; }
         __syncwarp();
         if (i + AHEAD < N) issue(i + AHEAD);
       }
@@ -721,7 +745,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
       while (true) {
         // _forward_step: g = (-2 delta, -1), x_min = x_max = x -> 1-D branch, v0 = 2 delta (pyx:628-636);
         // TOPPRAsd's slowest pass uses g = (2 delta, 1) (desired_duration_algorithm.py:218-223)
-          ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, VAR_MIN, VAR_MAX, uopt);
+          ok = lp1d_fixed_x_warp<RPL>(sd_slow ? -(2 * delta) : -(-2 * delta), x, a, b, c, f_ulo, f_uhi, uopt);
         if (ok || sd_mode || tries >= MAX_TRIES) break;  // TOPPRAsd has no retry rule
         x = py_max(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
         ++tries;
@@ -733,7 +757,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
         st = TB_STATUS_ERR_UNKNOWN;
         fstage = i;
         if (lane == 0) sdp[i] = x;
-        for (int j = i + 1 + lane; j < G; j += 32) sdp[j] = nan_d;
+        for (int j = i + 1 + lane; j < Gp; j += 32) sdp[j] = nan_d;
         for (int j = i + lane; j < N; j += 32) up[j] = sd_mode ? nan_d : 0.0;
         break;
       }
@@ -754,12 +778,16 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
     while (n_waited < n_issued) (void)acquire();
     __syncwarp();
     if (!sd_mode)  // TOPPRAsd combines the squared velocities: its passes return x = sd^2
-      for (int j = lane; j < G; j += 32) sdp[j] = sqrt(sdp[j]);  // reachability_algorithm.py:365
+      for (int j = lane; j < Gp; j += 32) sdp[j] = sqrt(sdp[j]);  // reachability_algorithm.py:365
+  }
+  if (Gp < G) {  // ragged batch: entries past this path's grid are NaN
+    for (int j = Gp + lane; j < G; j += 32) sdp[j] = nan_d;
+    for (int j = max(Gp - 1, 0) + lane; j < G - 1; j += 32) up[j] = nan_d;
   }
   if (lane == 0) {
     status[path] = st;
     if (fail_stage) fail_stage[path] = fstage;
-    if (counters) {
+    if (COUNT && counters) {
       // forward: one 1-variable LP per stage entered (N, or fstage + 1 when stage fstage failed) + one per retry;
       // none when the path failed before the forward pass
       const int n_fwd_stages = (st == TB_STATUS_OK) ? N : ((st == TB_STATUS_ERR_UNKNOWN) ? fstage + 1 : -1);
@@ -776,7 +804,7 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
 template <int RPL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 feasible_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
-                const int grid_shared, const int B, const int G, double *__restrict__ Xout) {
+                const int grid_shared, const int B, const int G, const int ub, double *__restrict__ Xout) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long path = (long)blockIdx.x * WARPS + warp;
   if (path >= B) return;
@@ -791,21 +819,139 @@ feasible_kernel(const double *__restrict__ records, const int W, const int R, co
     const double *rec = rec_path + (size_t)i * W;
     load_rows<RPL>(rec, R, nC, lane, a, b, c);
     const double xlo = fmax(rec[3 * R], -CVXPY_MAXX), xhi = fmin(rec[3 * R + 1], CVXPY_MAXX);  // pyx:598-601
+    const double ulo = ub ? rec[3 * R + 2] : VAR_MIN, uhi = ub ? rec[3 * R + 3] : VAR_MAX;   // TB_SCAN_UBOUND records
     if (i < N) {
       const double delta = gp[i + 1] - gp[i];
       set_xnext_rows<RPL>(lane, delta, -CVXPY_MAXX, CVXPY_MAXX, a, b, c);
     }  // i == N: rows 0,1 stay (0,0,-1), pyx:621-625
     double uu, xx;
     // g_lower = (1e-9, 1): g[1] > 0 -> slot up; v = (-1e-9, -1)
-    const bool ok0 = lp2d_warp<RPL>(-1e-9, -1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu, xx, lane,
+    const bool ok0 = lp2d_warp<RPL>(-1e-9, -1.0, a, b, c, nC, ulo, uhi, xlo, xhi, up0, up1, uu, xx, lane,
                                     n_resolve);
     double x0 = ok0 ? xx : nan_d;
-    const bool ok1 = lp2d_warp<RPL>(1e-9, 1.0, a, b, c, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu, xx, lane,
+    const bool ok1 = lp2d_warp<RPL>(1e-9, 1.0, a, b, c, nC, ulo, uhi, xlo, xhi, dn0, dn1, uu, xx, lane,
                                     n_resolve);
     const double x1 = ok1 ? xx : nan_d;
     if (x0 < 0) x0 = 0;  // reachability_algorithm.py:160-162
     if (lane == 0) { Xp[2 * i] = x0; Xp[2 * i + 1] = x1; }
   }
+}
+
+// cy_solve_lp1d (pyx:93-144) over the rows a*u + (b*x + c) <= 0 of one stage, WITH the active index the reference stores
+// in active_c[0] of the chosen warm-start slot (pyx:645-650): the first row that set the final bound, -1 = low,
+// -2 = high.  (The scan's forward pass uses the leaner lp1d_fixed_x_warp: nothing reads that index there.)
+template <int RPL>
+__device__ __forceinline__ bool lp1d_fixed_x_active_warp(const double v0, const double x, const double (&a)[RPL],
+                                                         const double (&b)[RPL], const double (&c)[RPL], const int nC,
+                                                         const double low0, const double high0, const int lane,
+                                                         double &out_u, int &active) {
+  double my_hi = high0, my_lo = low0;
+  int hi_idx = INT_MAX, lo_idx = INT_MAX;
+#pragma unroll
+  for (int s = 0; s < RPL; ++s) {
+    const int r = lane + 32 * s;
+    if (r >= nC) continue;
+    const double bxc = b[s] * x + c[s];
+    if (a[s] > LP_TINY) {
+      const double t = -bxc / a[s];
+      if (t < my_hi) { my_hi = t; hi_idx = r; }
+    } else if (a[s] < -LP_TINY) {
+      const double t = -bxc / a[s];
+      if (t > my_lo) { my_lo = t; lo_idx = r; }
+    }
+  }
+  const double cur_max = warp_min(my_hi), cur_min = warp_max(my_lo);
+  int hk = (hi_idx != INT_MAX && my_hi == cur_max) ? hi_idx : INT_MAX;
+  int lk = (lo_idx != INT_MAX && my_lo == cur_min) ? lo_idx : INT_MAX;
+  hk = __reduce_min_sync(FULL, hk);
+  lk = __reduce_min_sync(FULL, lk);
+  if (cur_min > cur_max) return false;
+  if (fabs(v0) < LP_TINY || v0 < 0) { out_u = cur_min; active = (lk == INT_MAX) ? -1 : lk; }
+  else { out_u = cur_max; active = (hk == INT_MAX) ? -2 : hk; }
+  return true;
+}
+
+// compute_reachable_sets (reachability_algorithm.py:378-431), one warp per path, ONE launch: the feasible-set pass
+// (compute_feasible_sets, :131-164) followed by the forward recursion L[i+1] = _one_step_forward(i, L[i], X[i+1]).
+// Both passes run in the same kernel because the reference's seidelWrapper is stateful: the warm-start slots
+// active_c_up / active_c_down left behind by the feasible-set pass are the ones the reachable pass starts from.
+// Reference quirks kept: the objective and the x_next formula use deltas[i - 1] (deltas[N - 1] for i = 0, Python's
+// negative index, :389-404) while rows 0/1 of the stage use deltas[i]; a stage with L[i,0] == L[i,1] takes the 1-variable
+// branch of solve_stagewise_optim and stores its active index in slot [0] only; after a NaN the remaining L stay 0.
+template <int RPL, int WARPS, bool UB>
+__global__ void __launch_bounds__(WARPS * 32)
+reachable_kernel(const double *__restrict__ records, const int W, const int R, const double *__restrict__ grid,
+                 const int grid_shared, const int B, const int G, const double *__restrict__ sdmin,
+                 const double *__restrict__ sdmax, double *__restrict__ Xout, double *__restrict__ Lout,
+                 int *__restrict__ fail_stage) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long path = (long)blockIdx.x * WARPS + warp;
+  if (path >= B) return;
+  const int N = G - 1, nC = R + 2;
+  const double *rec_path = records + (size_t)path * G * W;
+  const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
+  double *Xp = Xout + (size_t)path * G * 2;
+  double *Lp = Lout + (size_t)path * G * 2;
+  double a[RPL], b[RPL], c[RPL];
+  int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0, n_resolve = 0;
+  const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  // ---- feasible sets (as feasible_kernel) ----
+  for (int i = 0; i <= N; ++i) {
+    const double *rec = rec_path + (size_t)i * W;
+    load_rows<RPL>(rec, R, nC, lane, a, b, c);
+    const double xlo = fmax(rec[3 * R], -CVXPY_MAXX), xhi = fmin(rec[3 * R + 1], CVXPY_MAXX);
+    const double ulo = UB ? rec[3 * R + 2] : VAR_MIN, uhi = UB ? rec[3 * R + 3] : VAR_MAX;
+    if (i < N) set_xnext_rows<RPL>(lane, gp[i + 1] - gp[i], -CVXPY_MAXX, CVXPY_MAXX, a, b, c);
+    double uu, xx;
+    const bool ok0 = lp2d_warp<RPL>(-1e-9, -1.0, a, b, c, nC, ulo, uhi, xlo, xhi, up0, up1, uu, xx, lane, n_resolve);
+    double x0 = ok0 ? xx : nan_d;
+    const bool ok1 = lp2d_warp<RPL>(1e-9, 1.0, a, b, c, nC, ulo, uhi, xlo, xhi, dn0, dn1, uu, xx, lane, n_resolve);
+    const double x1 = ok1 ? xx : nan_d;
+    if (x0 < 0) x0 = 0;
+    if (lane == 0) { Xp[2 * i] = x0; Xp[2 * i + 1] = x1; }
+  }
+  __syncwarp();
+  // ---- reachable sets ----
+  const double s0 = sdmin ? sdmin[path] : 0.0, s1 = sdmax ? sdmax[path] : s0;
+  double l0 = s0 * s0, l1 = s1 * s1;
+  for (int j = 2 * lane; j < 2 * G; j += 64) { Lp[j] = 0.0; Lp[j + 1] = 0.0; }   // np.zeros((N + 1, 2))
+  __syncwarp();
+  if (lane == 0) { Lp[0] = l0; Lp[1] = l1; }
+  int fs = -1;
+  for (int i = 0; i < N; ++i) {
+    const double *rec = rec_path + (size_t)i * W;
+    load_rows<RPL>(rec, R, nC, lane, a, b, c);
+    // low/high of solve_stagewise_optim (pyx:592-601): xbound of the stage intersected with [x_min, x_max] = L[i]
+    const double r_lo = rec[3 * R], r_hi = rec[3 * R + 1];
+    const double xlo = (r_lo > l0) ? r_lo : l0, xhi = (r_hi < l1) ? r_hi : l1;   // dbl_max / dbl_min (pyx:13-14)
+    const double ulo = UB ? rec[3 * R + 2] : VAR_MIN, uhi = UB ? rec[3 * R + 3] : VAR_MAX;
+    const double xn0 = Xp[2 * (i + 1)], xn1 = Xp[2 * (i + 1) + 1];
+    // rows 0/1: NaN bound = absent = (0, 0, -1) (pyx:604-620)
+    set_xnext_rows<RPL>(lane, gp[i + 1] - gp[i], xn0, xn1, a, b, c);
+    if ((lane == 0 && xn0 != xn0) || (lane == 1 && xn1 != xn1)) { a[0] = 0.0; b[0] = 0.0; c[0] = -1.0; }
+    const double dq = (i > 0) ? (gp[i] - gp[i - 1]) : (gp[N] - gp[N - 1]);   // deltas[i - 1]
+    double u1 = nan_d, x1v = nan_d, u0 = nan_d, x0v = nan_d;
+    bool ok_a, ok_b;
+    if (l0 == l1) {
+      // 1-variable branch (pyx:631-650): both objectives
+      int act = 0;
+      ok_a = lp1d_fixed_x_active_warp<RPL>(-(-2 * dq), l0, a, b, c, nC, ulo, uhi, lane, u1, act);
+      if (ok_a) { x1v = l0; dn0 = act; }                 // g[1] = -1: active_c_down[0]
+      ok_b = lp1d_fixed_x_active_warp<RPL>(-(2 * dq), l0, a, b, c, nC, ulo, uhi, lane, u0, act);
+      if (ok_b) { x0v = l0; up0 = act; }                 // g[1] = +1: active_c_up[0]
+    } else {
+      ok_a = lp2d_warp<RPL>(-(-2 * dq), 1.0, a, b, c, nC, ulo, uhi, xlo, xhi, dn0, dn1, u1, x1v, lane, n_resolve);
+      ok_b = lp2d_warp<RPL>(-(2 * dq), -1.0, a, b, c, nC, ulo, uhi, xlo, xhi, up0, up1, u0, x0v, lane, n_resolve);
+    }
+    double x_upper = ok_a ? (x1v + 2 * dq * u1) : nan_d;
+    double x_lower = ok_b ? (x0v + 2 * dq * u0) : nan_d;
+    if (x_lower < 0) x_lower = 0;
+    if (lane == 0) { Lp[2 * (i + 1)] = x_lower; Lp[2 * (i + 1) + 1] = x_upper; }
+    if (!(ok_a && ok_b)) { fs = i + 1; break; }   // "Path not parametrizable": return L (rest zeros)
+    l0 = x_lower;
+    l1 = x_upper;
+  }
+  if (lane == 0 && fail_stage) fail_stage[path] = fs;
 }
 
 // Batched stand-alone LPs (one warp per LP): the device counterparts of the reference's Python shims
@@ -893,13 +1039,14 @@ constexpr int SCAN_WARPS = TB_SCAN_WARPS;  // 1: a finished path frees its slot 
 #endif
 
 #ifndef TB_SCAN_FUSED_WARPS_PER_SM
-#define TB_SCAN_FUSED_WARPS_PER_SM 32
+#define TB_SCAN_FUSED_WARPS_PER_SM 28  // 72 registers: 28 x 148 = 4144 resident paths still cover the 4096-path batch in one wave (measured r02: 1.317 vs 1.339 ms at 32)
 #endif
 
 template <int RPL>
 int launch_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
                 const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
-                double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+                double *sd, double *u, int *status, int *fail_stage, int *counters, const int *glen,
+                cudaStream_t stream) {
   const size_t smem = (size_t)SCAN_WARPS * SCAN_NBUF * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t) +
                       SCAN_WARPS * 4 * sizeof(void *);
   // Two register budgets for the common nC <= 32 case: 64 registers (32 one-warp CTAs per SM: the 4096-path batch
@@ -910,7 +1057,7 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
   const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
   auto kern = (RPL == 1 && dense) ? (fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true> : scan_kernel<RPL, SCAN_WARPS, MINB, false>)
                                   : (fast ? scan_kernel<RPL, SCAN_WARPS, 1, true> : scan_kernel<RPL, SCAN_WARPS, 1, false>);
-  if (RPL == 1 && dense) {
+  if (RPL == 1 && dense && !counters) {
     // the three launch kinds of the batched solver get their own instantiation: full scan, backward only, forward only
     const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
     if (mode == 0)
@@ -922,13 +1069,15 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
       kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, TB_SCAN_FORWARD_ONLY>
                   : scan_kernel<RPL, SCAN_WARPS, MINB, false, TB_SCAN_FORWARD_ONLY>;
   }
+  if (flags & TB_SCAN_UBOUND)  // records with a u-bound pair: the generic build (exact mode only)
+    kern = scan_kernel<RPL, SCAN_WARPS, 1, false, -1, false, true>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tb_scan: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
   const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
   kern<<<blocks, SCAN_WARPS * 32, smem, stream>>>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi,
-                                                  flags, K, sd, u, status, fail_stage, counters, VelAccSrc{});
+                                                  flags, K, sd, u, status, fail_stage, counters, glen, VelAccSrc{});
   return check_launch("tb_scan");
 }
 
@@ -936,13 +1085,16 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
 template <int MINB>
 int launch_scan_velacc_occ(const VelAccSrc &src, int W, int R, const double *grid, int grid_shared, int B, int G,
                            const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
-                           double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+                           double *sd, double *u, int *status, int *fail_stage, int *counters, const int *glen,
+                           cudaStream_t stream) {
   const size_t smem = (size_t)SCAN_WARPS * W * sizeof(double) + SCAN_WARPS * SCAN_NBUF * sizeof(uint64_t) +
                       SCAN_WARPS * 4 * sizeof(void *);
   const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
   const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
   auto kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, -1, true> : scan_kernel<1, SCAN_WARPS, MINB, false, -1, true>;
-  if (mode == 0)
+  if (counters) {
+    // instrumented launch: the run-time-flag build
+  } else if (mode == 0)
     kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, 0, true> : scan_kernel<1, SCAN_WARPS, MINB, false, 0, true>;
   else if (mode == TB_SCAN_BACKWARD_ONLY)
     kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, TB_SCAN_BACKWARD_ONLY, true>
@@ -952,28 +1104,43 @@ int launch_scan_velacc_occ(const VelAccSrc &src, int W, int R, const double *gri
                 : scan_kernel<1, SCAN_WARPS, MINB, false, TB_SCAN_FORWARD_ONLY, true>;
   const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
   kern<<<blocks, SCAN_WARPS * 32, smem, stream>>>(nullptr, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi,
-                                                  flags, K, sd, u, status, fail_stage, counters, src);
+                                                  flags, K, sd, u, status, fail_stage, counters, glen, src);
   return check_launch("tb_scan_velacc");
 }
 
 int launch_scan_velacc(const VelAccSrc &src, int W, int R, const double *grid, int grid_shared, int B, int G,
                        const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
-                       double *sd, double *u, int *status, int *fail_stage, int *counters, cudaStream_t stream) {
+                       double *sd, double *u, int *status, int *fail_stage, int *counters, const int *glen,
+                       cudaStream_t stream) {
   static const char *occ_env = getenv("TB_SCAN_FUSED_OCC");  // tuning: resident warps per SM (32 -> 64 regs, 28 -> 72)
   const int occ = occ_env ? atoi(occ_env) : TB_SCAN_FUSED_WARPS_PER_SM;
   if (occ == 28)
     return launch_scan_velacc_occ<28>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
-                                      status, fail_stage, counters, stream);
+                                      status, fail_stage, counters, glen, stream);
   return launch_scan_velacc_occ<32>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
-                                    status, fail_stage, counters, stream);
+                                    status, fail_stage, counters, glen, stream);
 }
 
 template <int RPL>
 int launch_feasible(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
-                    double *X, cudaStream_t stream) {
+                    int ub, double *X, cudaStream_t stream) {
   const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
-  feasible_kernel<RPL, SCAN_WARPS><<<blocks, SCAN_WARPS * 32, 0, stream>>>(records, W, R, grid, grid_shared, B, G, X);
+  feasible_kernel<RPL, SCAN_WARPS><<<blocks, SCAN_WARPS * 32, 0, stream>>>(records, W, R, grid, grid_shared, B, G, ub, X);
   return check_launch("tb_feasible_sets");
+}
+
+template <int RPL>
+int launch_reachable(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                     const double *sdmin, const double *sdmax, int flags, double *X, double *L, int *fail_stage,
+                     cudaStream_t stream) {
+  const int blocks = (B + SCAN_WARPS - 1) / SCAN_WARPS;
+  if (flags & TB_SCAN_UBOUND)
+    reachable_kernel<RPL, SCAN_WARPS, true><<<blocks, SCAN_WARPS * 32, 0, stream>>>(records, W, R, grid, grid_shared, B, G,
+                                                                                   sdmin, sdmax, X, L, fail_stage);
+  else
+    reachable_kernel<RPL, SCAN_WARPS, false><<<blocks, SCAN_WARPS * 32, 0, stream>>>(records, W, R, grid, grid_shared, B, G,
+                                                                                    sdmin, sdmax, X, L, fail_stage);
+  return check_launch("tb_reachable_sets");
 }
 
 int check_scan_args(const char *fn, const void *records, int W, int R, const void *grid, int B, int G) {
@@ -987,28 +1154,41 @@ int check_scan_args(const char *fn, const void *records, int W, int R, const voi
 }  // namespace
 }  // namespace tb
 
-extern "C" int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
-                          const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
-                          double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream) {
+extern "C" int tb_scan_ragged(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                              const int *glen, const double *sd_start, const double *sd_end, const double *sd_end_hi,
+                              int flags, double *K, double *sd, double *u, int *status, int *fail_stage, int *counters,
+                              void *stream) {
   using namespace tb;
   int rc = check_scan_args("tb_scan", records, W, R, grid, B, G);
   if (rc) return rc;
+  if ((flags & TB_SCAN_UBOUND) && W < 3 * R + 4) { set_error("tb_scan: TB_SCAN_UBOUND needs records of W >= 3R+4 doubles"); return TB_ERR_ARG; }
+  if ((flags & TB_SCAN_UBOUND) && (flags & TB_SCAN_FAST_LOWER)) { set_error("tb_scan: TB_SCAN_UBOUND excludes TB_SCAN_FAST_LOWER"); return TB_ERR_UNSUPPORTED; }
+  if (glen && grid_shared) { set_error("tb_scan: ragged batches (glen) need per-path grids [B][G]"); return TB_ERR_ARG; }
   const bool backward_only = (flags & TB_SCAN_BACKWARD_ONLY) != 0;
   if (!K || !status || (!backward_only && (!sd || (G > 1 && !u)))) { set_error("tb_scan: null output"); return TB_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   const int nC = R + 2;
-  if (nC <= 32) return launch_scan<1>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
-  if (nC <= 64) return launch_scan<2>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
-  if (nC <= 96) return launch_scan<3>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
-  return launch_scan<4>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, s);
+  if (nC <= 32) return launch_scan<1>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, glen, s);
+  if (nC <= 64) return launch_scan<2>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, glen, s);
+  if (nC <= 96) return launch_scan<3>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, glen, s);
+  return launch_scan<4>(records, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status, fail_stage, counters, glen, s);
 }
 
-extern "C" int tb_scan_velacc(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof,
-                              const double *grid, int grid_shared, int B, int G, const double *alim, int lim_shared,
-                              int interp, const double *xbound, const double *sd_start, const double *sd_end,
-                              const double *sd_end_hi, int flags, double *K, double *sd, double *u, int *status,
-                              int *fail_stage, int *counters, void *stream) {
+extern "C" int tb_scan_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                          const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
+                          double *sd, double *u, int *status, int *fail_stage, int *counters, void *stream) {
+  return tb_scan_ragged(records, W, R, grid, grid_shared, B, G, nullptr, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
+                        status, fail_stage, counters, stream);
+}
+
+extern "C" int tb_scan_velacc_ragged(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof,
+                                     const double *grid, int grid_shared, int B, int G, const int *glen,
+                                     const double *alim, int lim_shared, int interp, const double *xbound,
+                                     const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags,
+                                     double *K, double *sd, double *u, int *status, int *fail_stage, int *counters,
+                                     void *stream) {
   using namespace tb;
+  if (glen && grid_shared) { set_error("tb_scan_velacc: ragged batches (glen) need per-path grids [B][G]"); return TB_ERR_ARG; }
   if (!ppoly || !breaks || !grid || !alim || !xbound || B <= 0 || G <= 0 || nseg <= 0 || dof <= 0) {
     set_error("tb_scan_velacc: bad argument");
     return TB_ERR_ARG;
@@ -1025,7 +1205,17 @@ extern "C" int tb_scan_velacc(const double *ppoly, const double *breaks, int bre
   }
   const VelAccSrc src{ppoly, breaks, alim, xbound, breaks_shared, nseg, dof, lim_shared};
   return launch_scan_velacc(src, Wc, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status,
-                            fail_stage, counters, (cudaStream_t)stream);
+                            fail_stage, counters, glen, (cudaStream_t)stream);
+}
+
+extern "C" int tb_scan_velacc(const double *ppoly, const double *breaks, int breaks_shared, int nseg, int dof,
+                              const double *grid, int grid_shared, int B, int G, const double *alim, int lim_shared,
+                              int interp, const double *xbound, const double *sd_start, const double *sd_end,
+                              const double *sd_end_hi, int flags, double *K, double *sd, double *u, int *status,
+                              int *fail_stage, int *counters, void *stream) {
+  return tb_scan_velacc_ragged(ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, B, G, nullptr, alim,
+                               lim_shared, interp, xbound, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status,
+                               fail_stage, counters, stream);
 }
 
 extern "C" int tb_scan(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
@@ -1035,18 +1225,41 @@ extern "C" int tb_scan(const double *records, int W, int R, const double *grid, 
                     nullptr, stream);
 }
 
-extern "C" int tb_feasible_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
-                                double *X, void *stream) {
+extern "C" int tb_feasible_sets_ex(const double *records, int W, int R, const double *grid, int grid_shared, int B,
+                                   int G, int flags, double *X, void *stream) {
   using namespace tb;
   int rc = check_scan_args("tb_feasible_sets", records, W, R, grid, B, G);
   if (rc) return rc;
   if (!X) { set_error("tb_feasible_sets: null output"); return TB_ERR_ARG; }
+  const int ub = (flags & TB_SCAN_UBOUND) ? 1 : 0;
+  if (ub && W < 3 * R + 4) { set_error("tb_feasible_sets: TB_SCAN_UBOUND needs W >= 3R+4"); return TB_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   const int nC = R + 2;
-  if (nC <= 32) return launch_feasible<1>(records, W, R, grid, grid_shared, B, G, X, s);
-  if (nC <= 64) return launch_feasible<2>(records, W, R, grid, grid_shared, B, G, X, s);
-  if (nC <= 96) return launch_feasible<3>(records, W, R, grid, grid_shared, B, G, X, s);
-  return launch_feasible<4>(records, W, R, grid, grid_shared, B, G, X, s);
+  if (nC <= 32) return launch_feasible<1>(records, W, R, grid, grid_shared, B, G, ub, X, s);
+  if (nC <= 64) return launch_feasible<2>(records, W, R, grid, grid_shared, B, G, ub, X, s);
+  if (nC <= 96) return launch_feasible<3>(records, W, R, grid, grid_shared, B, G, ub, X, s);
+  return launch_feasible<4>(records, W, R, grid, grid_shared, B, G, ub, X, s);
+}
+
+extern "C" int tb_feasible_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                                double *X, void *stream) {
+  return tb_feasible_sets_ex(records, W, R, grid, grid_shared, B, G, 0, X, stream);
+}
+
+extern "C" int tb_reachable_sets(const double *records, int W, int R, const double *grid, int grid_shared, int B, int G,
+                                 const double *sdmin, const double *sdmax, int flags, double *X, double *L,
+                                 int *fail_stage, void *stream) {
+  using namespace tb;
+  int rc = check_scan_args("tb_reachable_sets", records, W, R, grid, B, G);
+  if (rc) return rc;
+  if (!X || !L) { set_error("tb_reachable_sets: null output"); return TB_ERR_ARG; }
+  if ((flags & TB_SCAN_UBOUND) && W < 3 * R + 4) { set_error("tb_reachable_sets: TB_SCAN_UBOUND needs W >= 3R+4"); return TB_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nC = R + 2;
+  if (nC <= 32) return launch_reachable<1>(records, W, R, grid, grid_shared, B, G, sdmin, sdmax, flags, X, L, fail_stage, s);
+  if (nC <= 64) return launch_reachable<2>(records, W, R, grid, grid_shared, B, G, sdmin, sdmax, flags, X, L, fail_stage, s);
+  if (nC <= 96) return launch_reachable<3>(records, W, R, grid, grid_shared, B, G, sdmin, sdmax, flags, X, L, fail_stage, s);
+  return launch_reachable<4>(records, W, R, grid, grid_shared, B, G, sdmin, sdmax, flags, X, L, fail_stage, s);
 }
 
 extern "C" int tb_lp2d_batch(const double *v, const double *a, const double *b, const double *c, const double *low,

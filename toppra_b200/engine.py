@@ -60,6 +60,9 @@ def parse_bc(bc_type, B, dof, device):
             order, val = side
             if order not in (1, 2):
                 raise ValueError("The specified derivative order must be 1 or 2.")
+            if isinstance(val, torch_mod().Tensor):   # boundary values already on the device: [B, dof]
+                out.append((int(order), as_device(val.reshape(B, dof).contiguous(), device)))
+                continue
             val = np.asarray(val, dtype=np.float64)
             val = np.broadcast_to(val, (B, dof)) if val.ndim <= 1 else val.reshape(B, dof)
             out.append((int(order), as_device(np.ascontiguousarray(val), device)))
@@ -102,10 +105,18 @@ def record_doubles(R):
     return int(_lib.load().tb_record_doubles(int(R)))
 
 
-def alloc_records(B, G, R, device):
+def alloc_records(B, G, R, device, ubound=False):
+    """Stage records [B, G, W]: a[R] | b[R] | c[R] | xlo | xhi (W = 3R+2 rounded to even); with ubound=True the record
+    also carries ulo | uhi (W = 3R+4 rounded to even; the scans are told by TB_SCAN_UBOUND, inferred from W)."""
     torch = torch_mod()
     W = record_doubles(R)
+    if ubound:
+        W = (3 * R + 4 + 1) & ~1
     return torch.empty((B, G, W), dtype=torch.float64, device=device), W
+
+
+def has_ubound(records, R):
+    return records.shape[-1] >= 3 * int(R) + 4
 
 
 def init_bounds(records, R):
@@ -200,8 +211,9 @@ def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
 
 
 def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False, counters=False,
-         sd_forward=None, forward_from=None, fast_lower=False):
-    """K2.  Returns dict(K [B,G,2], sd [B,G], u [B,G-1], status [B] int32, fail_stage [B] int32[, counters [B,4]])."""
+         sd_forward=None, forward_from=None, fast_lower=False, glen=None):
+    """K2.  Returns dict(K [B,G,2], sd [B,G], u [B,G-1], status [B] int32, fail_stage [B] int32[, counters [B,4]]).
+    glen: optional int32 [B] gridpoints per path (ragged batch, grid [B, G] padded)."""
     torch = torch_mod()
     B, G, W = records.shape
     dev = records.device
@@ -219,11 +231,14 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     u = None if backward_only else torch.empty((B, max(G - 1, 0)), dtype=torch.float64, device=dev)
     cnt = torch.zeros((B, 4), dtype=torch.int32, device=dev) if counters else None
     u_arg = u if (u is None or u.numel() > 0) else torch.empty((1,), dtype=torch.float64, device=dev)
+    check_glen(glen, B, grid)
+    ub = has_ubound(records, R)
     with torch.cuda.device(dev):
-        rc = _lib.load().tb_scan_ex(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
-                                    _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi),
+        rc = _lib.load().tb_scan_ragged(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
+                                    _lib.ptr(glen), _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi),
                                     (1 if backward_only else 0) | ({None: 0, "fast": 4, "slow": 12}[sd_forward])
-                                    | (16 if forward_from is not None else 0) | (32 if fast_lower else 0),
+                                    | (16 if forward_from is not None else 0) | (32 if (fast_lower and not ub) else 0)
+                                    | (64 if ub else 0),
                                     _lib.ptr(K), _lib.ptr(sd),
                                     _lib.ptr(u_arg),
                                     _lib.ptr(status), _lib.ptr(fail_stage), _lib.ptr(cnt), _lib.stream_ptr())
@@ -234,7 +249,17 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     return out
 
 
-SCAN_FLAGS = dict(backward_only=1, sd_fast=4, sd_slow=12, forward_only=16, fast_lower=32)
+SCAN_FLAGS = dict(backward_only=1, sd_fast=4, sd_slow=12, forward_only=16, fast_lower=32, ubound=64)
+
+
+def check_glen(glen, B, grid):
+    if glen is None:
+        return
+    torch = torch_mod()
+    if glen.dtype != torch.int32 or tuple(glen.shape) != (B,):
+        raise ValueError("glen must be an int32 tensor of shape (%d,)" % B)
+    if grid.dim() != 2:
+        raise ValueError("ragged batches (glen) need per-path gridpoints of shape (B, G)")
 
 
 def velacc_fused_supported(nseg, dof, interp):
@@ -272,7 +297,7 @@ def xbound_constant(ppoly, breaks, grid, vlim, records, R_total, write_xbound):
 
 
 def scan_velacc(ppoly, breaks, grid, alim, interp, xbound, sd_start=None, sd_end=None, sd_end_hi=None,
-                backward_only=False, counters=False, sd_forward=None, forward_from=None, fast_lower=False):
+                backward_only=False, counters=False, sd_forward=None, forward_from=None, fast_lower=False, glen=None):
     """K2 fused with K1 for JointVelocity + JointAcceleration (tb_scan_velacc): rows are built inside the scan from
     the spline; `xbound` [B, G, 2] from xbound_velocity().  Same outputs as scan()."""
     torch = torch_mod()
@@ -298,9 +323,10 @@ def scan_velacc(ppoly, breaks, grid, alim, interp, xbound, sd_start=None, sd_end
     u_arg = u if (u is None or u.numel() > 0) else torch.empty((1,), dtype=torch.float64, device=dev)
     flags = ((1 if backward_only else 0) | ({None: 0, "fast": 4, "slow": 12}[sd_forward])
              | (16 if forward_from is not None else 0) | (32 if fast_lower else 0))
+    check_glen(glen, B, grid)
     with torch.cuda.device(dev):
-        rc = _lib.load().tb_scan_velacc(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, nseg, dof,
-                                        _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G, _lib.ptr(alim),
+        rc = _lib.load().tb_scan_velacc_ragged(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, nseg, dof,
+                                        _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G, _lib.ptr(glen), _lib.ptr(alim),
                                         1 if alim.dim() == 2 else 0, 1 if interp else 0, _lib.ptr(xbound),
                                         _lib.ptr(sd_start), _lib.ptr(sd_end), _lib.ptr(sd_end_hi), flags, _lib.ptr(K),
                                         _lib.ptr(sd), _lib.ptr(u_arg), _lib.ptr(status), _lib.ptr(fail_stage),
@@ -346,10 +372,86 @@ def feasible_sets(records, R, grid):
     B, G, W = records.shape
     X = torch.empty((B, G, 2), dtype=torch.float64, device=records.device)
     with torch.cuda.device(records.device):
-        rc = _lib.load().tb_feasible_sets(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
-                                          _lib.ptr(X), _lib.stream_ptr())
+        rc = _lib.load().tb_feasible_sets_ex(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B,
+                                             G, 64 if has_ubound(records, R) else 0, _lib.ptr(X), _lib.stream_ptr())
     _lib.check(rc, "tb_feasible_sets")
     return X
+
+
+def reachable_sets(records, R, grid, sdmin=None, sdmax=None):
+    """compute_reachable_sets for B paths in one launch (tb_reachable_sets).  sdmin / sdmax: [B] tensors or None.
+    Returns dict(X [B,G,2] feasible sets, L [B,G,2] reachable sets, fail_stage [B] int32)."""
+    torch = torch_mod()
+    B, G, W = records.shape
+    dev = records.device
+    for t, what in ((sdmin, "sdmin"), (sdmax, "sdmax")):
+        check_path_vector(t, B, what)
+    X = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+    L = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
+    fs = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_reachable_sets(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G,
+                                           _lib.ptr(sdmin), _lib.ptr(sdmax), 64 if has_ubound(records, R) else 0,
+                                           _lib.ptr(X), _lib.ptr(L), _lib.ptr(fs), _lib.stream_ptr())
+    _lib.check(rc, "tb_reachable_sets")
+    return dict(X=X, L=L, fail_stage=fs)
+
+
+def propose_gridpoints(ppoly, breaks, max_err_threshold=1e-4, max_iteration=100, max_seg_length=0.05, min_nb_points=100,
+                       max_points=2048):
+    """propose_gridpoints for B paths (tb_propose_gridpoints).  Returns (grid [B, max_points] padded with the path end,
+    glen [B] int32, status [B] int32: 0 ok, 1 = no good grid within max_iteration passes, < 0 = max_points exceeded)."""
+    torch = torch_mod()
+    B, _, nseg, dof = ppoly.shape
+    dev = ppoly.device
+    check_grid_shapes(B, breaks, nseg + 1, breaks, nseg + 1)
+    grid = torch.empty((B, int(max_points)), dtype=torch.float64, device=dev)
+    scratch = torch.empty_like(grid)
+    glen = torch.empty((B,), dtype=torch.int32, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_propose_gridpoints(_lib.ptr(ppoly), _lib.ptr(breaks), 1 if breaks.dim() == 1 else 0, B, nseg,
+                                               dof, float(max_err_threshold), int(max_iteration), float(max_seg_length),
+                                               int(min_nb_points), int(max_points), _lib.ptr(grid), _lib.ptr(scratch),
+                                               _lib.ptr(glen), _lib.ptr(status), _lib.stream_ptr())
+    _lib.check(rc, "tb_propose_gridpoints")
+    return grid, glen, status
+
+
+def sd_bisect(x_fast, u_fast, x_slow, u_slow, grid, desired, atol=1e-5, status_in=None, max_iter=200):
+    """TOPPRAsd blend (tb_sd_bisect).  Returns dict(sd [B,G], u [B,G-1], info [B,4] = (alpha, fastest, slowest duration,
+    bisection steps), status [B])."""
+    torch = torch_mod()
+    B, G = x_fast.shape
+    dev = x_fast.device
+    check_path_vector(desired, B, "desired_duration")
+    sd = torch.empty((B, G), dtype=torch.float64, device=dev)
+    u = torch.empty((B, G - 1), dtype=torch.float64, device=dev)
+    info = torch.empty((B, 4), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_sd_bisect(_lib.ptr(x_fast), _lib.ptr(u_fast), _lib.ptr(x_slow), _lib.ptr(u_slow),
+                                      _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B, G, _lib.ptr(desired), float(atol),
+                                      int(max_iter), _lib.ptr(status_in), _lib.ptr(sd), _lib.ptr(u), _lib.ptr(info),
+                                      _lib.ptr(status), _lib.stream_ptr())
+    _lib.check(rc, "tb_sd_bisect")
+    return dict(sd=sd, u=u, info=info, status=status)
+
+
+def spline_time_stamps(sd, grid, glen=None):
+    """ParametrizeSpline knots (tb_spline_time_stamps).  Returns (t [B,G], s [B,G] compacted + padded, nkeep [B] int32)."""
+    torch = torch_mod()
+    B, G = sd.shape
+    dev = sd.device
+    check_glen(glen, B, grid)
+    t = torch.empty((B, G), dtype=torch.float64, device=dev)
+    s = torch.empty((B, G), dtype=torch.float64, device=dev)
+    nkeep = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tb_spline_time_stamps(_lib.ptr(sd), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, _lib.ptr(glen), B,
+                                               G, _lib.ptr(t), _lib.ptr(s), _lib.ptr(nkeep), _lib.stream_ptr())
+    _lib.check(rc, "tb_spline_time_stamps")
+    return t, s, nkeep
 
 
 def solve_velacc_host(ss, wp, grid, vlim, alim, interp=True, sd_start=None, sd_end=None, device=0):

@@ -13,42 +13,19 @@ from . import engine
 logger = logging.getLogger(__name__)
 
 
-def propose_gridpoints(path, max_err_threshold=1e-4, max_iteration=100, max_seg_length=0.05, min_nb_points=100):
-    """Generate gridpoints that sufficiently cover the given path (reference interpolator.py:49-122).
-
-    Each pass bisects every segment that is longer than `max_seg_length` or whose estimated interpolation error
-    0.5 * max|q''(mid)| * d^2 exceeds `max_err_threshold`; afterwards all segments are bisected until there are at
-    least `min_nb_points` points.  All midpoints of a pass are evaluated with ONE device call."""
-    gridpoints_ept = [path.path_interval[0], path.path_interval[1]]
-    iteration = 0
-    for iteration in range(max_iteration):
-        add_new_points = False
-        pts = np.asarray(gridpoints_ept, dtype=np.float64)
-        mids = 0.5 * (pts[:-1] + pts[1:])
-        dist = pts[1:] - pts[:-1]
-        qss_mid = np.asarray(path(mids, 2)).reshape(len(mids), -1)
-        for idx in range(len(pts) - 1):
-            if dist[idx] > max_seg_length:
-                gridpoints_ept.append(mids[idx])
-                add_new_points = True
-                continue
-            max_err = np.max(np.abs(0.5 * qss_mid[idx] * dist[idx] ** 2))
-            if max_err > max_err_threshold:
-                add_new_points = True
-                gridpoints_ept.append(mids[idx])
-                continue
-        gridpoints_ept = sorted(gridpoints_ept)
-        if not add_new_points:
-            break
-    while len(gridpoints_ept) < min_nb_points:
-        new_pts = []
-        for idx in range(len(gridpoints_ept) - 1):
-            new_pts.append(0.5 * (gridpoints_ept[idx] + gridpoints_ept[idx + 1]))
-        gridpoints_ept.extend(new_pts)
-        gridpoints_ept = sorted(gridpoints_ept)
-    if iteration == max_iteration - 1:
-        raise ValueError("Unable to find a good gridpoint for this path.")
-    return gridpoints_ept
+def propose_gridpoints(path, max_err_threshold=1e-4, max_iteration=100, max_seg_length=0.05, min_nb_points=100,
+                       max_points=4096):
+    """Generate gridpoints that sufficiently cover the given path (reference interpolator.py:49-122): segments longer
+    than `max_seg_length`, or whose estimated interpolation error 0.5 * max|q''(mid)| * d^2 exceeds
+    `max_err_threshold`, are bisected pass after pass; then every segment is bisected until there are at least
+    `min_nb_points` points.  Runs on the GPU (csrc/tb_frows.cu: tb_propose_gridpoints); this is the B = 1 case of
+    `BatchSplineInterpolator.propose_gridpoints`.  Returns the list of gridpoints like the reference."""
+    if not hasattr(path, "as_batch"):
+        raise TypeError("toppra_b200.propose_gridpoints needs a path with a piecewise-cubic device form "
+                        "(SplineInterpolator, PPolyPath, SimplePath, PolynomialPath); got %s" % type(path).__name__)
+    grid, glen = path.as_batch().propose_gridpoints(max_err_threshold, max_iteration, max_seg_length, min_nb_points,
+                                                    max_points)
+    return grid[0, :int(glen[0])].cpu().numpy().tolist()
 
 
 class AbstractGeometricPath(object):
@@ -198,6 +175,23 @@ class BatchSplineInterpolator(object):
         s = np.atleast_1d(np.asarray(path_positions, dtype=np.float64))
         out = self.eval_device(engine.as_device(s, self.device), order)
         return out.cpu().numpy()
+
+    def propose_gridpoints(self, max_err_threshold=1e-4, max_iteration=100, max_seg_length=0.05, min_nb_points=100,
+                           max_points=4096):
+        """Adaptive gridpoints for every path of the batch (reference propose_gridpoints, interpolator.py:49-122; one
+        warp per path, tb_propose_gridpoints).  The grids are RAGGED: returns (grid [B, Gmax] CUDA tensor padded with
+        the path end, glen [B] int32 CUDA tensor); Gmax = longest grid of the batch.  Pass both to
+        `BatchTOPPRA(..., gridpoints=grid, glen=glen)`.  Raises ValueError like the reference when a path finds no
+        good grid within `max_iteration` passes (or needs more than `max_points` points)."""
+        grid, glen, status = engine.propose_gridpoints(self.d_ppoly, self.d_ss, max_err_threshold, max_iteration,
+                                                       max_seg_length, min_nb_points, max_points)
+        st = status.cpu().numpy()          # one small D2H: the error behaviour of the reference needs the host
+        if (st == 1).any():
+            raise ValueError("Unable to find a good gridpoint for this path.")
+        if (st != 0).any():
+            raise ValueError("propose_gridpoints: more than max_points=%d gridpoints needed" % max_points)
+        gmax = int(glen.max().item())
+        return grid[:, :gmax].contiguous(), glen
 
     def chunk(self, lo, hi):
         """View of paths [lo, hi) sharing this object's device buffers (used by chunked batch solves)."""

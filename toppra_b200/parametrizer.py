@@ -8,7 +8,6 @@ import logging
 import numpy as np
 
 from . import engine
-from .constants import TINY
 from .exceptions import ToppraError
 from .interpolator import AbstractGeometricPath, SplineInterpolator
 
@@ -79,26 +78,85 @@ class ParametrizeConstAccel(AbstractGeometricPath):
         return out[0] if scalar else out
 
 
+class BatchParametrizeSpline(object):
+    """ParametrizeSpline (reference parametrizer.py:161-196) for B paths on the GPU: the time-stamp recurrence with its
+    two data-dependent rules (tb_spline_time_stamps, csrc/tb_frows.cu), q at the kept gridpoints (tb_ppoly_eval) and the
+    clamped re-fit (tb_spline_fit with first-derivative boundary values q'(s) * sd).
+
+    path: BatchSplineInterpolator; gridpoints: [G] or [B, G]; velocities: sd [B, G]; glen: optional int32 [B] for ragged
+    grids.  The knot lists are ragged whenever the grids are, or an increment below 1e-8 is dropped: paths are then
+    grouped by knot count and each group is fitted with one launch (`self.groups`: list of (path indices,
+    BatchSplineInterpolator over time)).  `durations` is a CUDA tensor [B]."""
+
+    def __init__(self, path, gridpoints, velocities, glen=None):
+        torch = engine.torch_mod()
+        self._path = path
+        dev = path.device
+        d_grid = engine.as_device(gridpoints, dev)
+        d_sd = engine.as_device(velocities, dev)
+        B, G = d_sd.shape
+        if glen is not None and d_grid.dim() == 1:
+            d_grid = d_grid.expand(B, G).contiguous()
+        self.t_knots, self.s_knots, self.nkeep = engine.spline_time_stamps(d_sd, d_grid, glen)
+        q_knots = path.eval_device(self.s_knots, 0)                               # [B, G, dof]
+        s0 = d_grid[..., 0:1] if d_grid.dim() == 2 else d_grid[0:1]
+        if glen is None:
+            s1 = d_grid[..., -1:] if d_grid.dim() == 2 else d_grid[-1:]
+            v1 = d_sd[:, -1]
+        else:
+            last = (glen.to(torch.int64) - 1).unsqueeze(1)
+            s1 = torch.gather(d_grid, 1, last)
+            v1 = torch.gather(d_sd, 1, last)[:, 0]
+        # boundary conditions: first derivatives q'(path_interval) * sd at both ends (reference :189-196)
+        bc0 = path.eval_device(s0, 1)[:, 0, :] * d_sd[:, 0:1]
+        bc1 = path.eval_device(s1, 1)[:, 0, :] * v1.unsqueeze(1)
+        n_host = self.nkeep.cpu().numpy()       # grouping by knot count needs the counts on the host (B ints)
+        self.durations = torch.gather(self.t_knots, 1, (self.nkeep.to(torch.int64) - 1).unsqueeze(1))[:, 0]
+        self.groups = []
+        from .interpolator import BatchSplineInterpolator
+        for n in np.unique(n_host):
+            idx = np.nonzero(n_host == n)[0]
+            sel = engine.as_device(idx.astype(np.int64), dev, dtype=torch.int64)
+            full = len(idx) == B
+            t = self.t_knots[:, :n] if full else self.t_knots[sel, :n]
+            q = q_knots[:, :n] if full else q_knots[sel, :n]
+            b0, b1 = (bc0, bc1) if full else (bc0[sel], bc1[sel])
+            fit = BatchSplineInterpolator(t.contiguous(), q.contiguous(), ((1, b0.contiguous()), (1, b1.contiguous())),
+                                          device=dev, validate=False)
+            self.groups.append((idx, fit))
+
+    def __call__(self, ts, order=0):
+        """ts: [M] shared or [B, M] times -> CUDA tensor [B, M, dof]."""
+        torch = engine.torch_mod()
+        ts = engine.as_device(ts, self._path.device)
+        B = self.t_knots.shape[0]
+        out = None
+        for idx, fit in self.groups:
+            t = ts if ts.dim() == 1 else (ts if len(idx) == B else ts[engine.as_device(idx.astype(np.int64), ts.device, dtype=torch.int64)])
+            val = fit.eval_device(t.contiguous(), order)
+            if len(idx) == B:
+                return val
+            if out is None:
+                out = torch.empty((B,) + tuple(val.shape[1:]), dtype=val.dtype, device=val.device)
+            out[engine.as_device(idx.astype(np.int64), val.device, dtype=torch.int64)] = val
+        return out
+
+
 class ParametrizeSpline(SplineInterpolator):
     """Output trajectory by cubic-spline interpolation of q(s_i) at the gridpoint time stamps
     t_i = t_{i-1} + ds / mean(sd_{i-1}, sd_i) (5 s for a stalled segment; increments < 1e-8 dropped), with the
-    first derivatives at both ends clamped to q'(s) * sd."""
+    first derivatives at both ends clamped to q'(s) * sd (reference parametrizer.py:161-196).  The recurrence runs on
+    the GPU (tb_spline_time_stamps): this is the B = 1 case of `BatchParametrizeSpline`."""
 
     def __init__(self, path, gridpoints, velocities):
-        gridpoints = np.asarray(gridpoints, dtype=np.float64)
-        velocities = np.asarray(velocities, dtype=np.float64)
-        t_grid = np.zeros_like(gridpoints)
-        skip = []
-        for i in range(1, len(t_grid)):
-            sd_average = (velocities[i - 1] + velocities[i]) / 2
-            delta_s = gridpoints[i] - gridpoints[i - 1]
-            delta_t = delta_s / sd_average if sd_average > TINY else 5
-            t_grid[i] = t_grid[i - 1] + delta_t
-            if delta_t < TINY:
-                skip.append(i)
-        t_grid = np.delete(t_grid, skip)
-        gridpoints = np.delete(gridpoints, skip)
-        q_grid = path(gridpoints)
+        gridpoints = np.ascontiguousarray(gridpoints, dtype=np.float64)
+        velocities = np.ascontiguousarray(velocities, dtype=np.float64)
+        bpath = path.as_batch()
+        t, s, nkeep = engine.spline_time_stamps(engine.as_device(velocities[None], bpath.device),
+                                                engine.as_device(gridpoints, bpath.device))
+        n = int(nkeep[0].item())
+        t_grid = t[0, :n].cpu().numpy()
+        q_grid = path(s[0, :n].cpu().numpy())
         bc = ((1, path(path.path_interval[0], 1) * velocities[0]),
               (1, path(path.path_interval[1], 1) * velocities[-1]))
         super(ParametrizeSpline, self).__init__(t_grid, q_grid, bc)

@@ -99,8 +99,9 @@ class B200SolverWrapper(SolverWrapper):
             arr = np.zeros((G, self.nC))
             arr[:, 2:] = rec[:, idx * R:(idx + 1) * R]
             out[key] = arr
-        out["low"] = np.stack((np.full(G, -1e8), rec[:, 3 * R]), axis=1)
-        out["high"] = np.stack((np.full(G, 1e8), rec[:, 3 * R + 1]), axis=1)
+        ub = engine.has_ubound(self.records, R)   # u-bound pair behind the x-bound pair (pyx:512-515)
+        out["low"] = np.stack((rec[:, 3 * R + 2] if ub else np.full(G, -1e8), rec[:, 3 * R]), axis=1)
+        out["high"] = np.stack((rec[:, 3 * R + 3] if ub else np.full(G, 1e8), rec[:, 3 * R + 1]), axis=1)
         return out
 
     def solve_stagewise_optim(self, i, H, g, x_min, x_max, x_next_min, x_next_max):
@@ -159,11 +160,31 @@ class B200SolverWrapper(SolverWrapper):
             res["counters"] = out["counters"][0].cpu().numpy()
         return res
 
+    def parameterize_sd(self, sd_start, sd_end, desired_duration, atol=1e-5):
+        """TOPPRAsd on the device: two scans (fastest / slowest forward rules) + tb_sd_bisect; host arrays out."""
+        self._no_conic("TOPPRAsd")
+        s0, s1 = self._scalar(sd_start), self._scalar(sd_end)
+        fast = engine.scan(self.records, self.R, self.ctx.d_grid, s0, s1, sd_forward="fast")
+        slow = engine.scan(self.records, self.R, self.ctx.d_grid, s0, s1, sd_forward="slow")
+        out = engine.sd_bisect(fast["sd"], fast["u"], slow["sd"], slow["u"], self.ctx.d_grid,
+                               self._scalar(desired_duration), atol, status_in=fast["status"])
+        info = out["info"][0].cpu().numpy()
+        return dict(K=fast["K"][0].cpu().numpy(), status=int(fast["status"][0].item()),
+                    blend_status=int(out["status"][0].item()), sd=out["sd"][0].cpu().numpy(),
+                    u=out["u"][0].cpu().numpy(), alpha=float(info[0]), duration_fast=float(info[1]),
+                    duration_slow=float(info[2]))
+
     def controllable_sets(self, sdmin, sdmax):
         from ..batch import scan_any
         out = scan_any(self.records, self.R, self.ctx.d_grid, self.conic, None, self._scalar(sdmin),
                        None if sdmin == sdmax else self._scalar(sdmax), backward_only=True)
         return out["K"][0].cpu().numpy(), int(out["status"][0].item())
+
+    def reachable_sets(self, sdmin, sdmax):
+        """(X, L, fail_stage) of compute_reachable_sets: one launch (tb_reachable_sets)."""
+        self._no_conic("compute_reachable_sets")
+        out = engine.reachable_sets(self.records, self.R, self.ctx.d_grid, self._scalar(sdmin), self._scalar(sdmax))
+        return out["X"][0].cpu().numpy(), out["L"][0].cpu().numpy(), int(out["fail_stage"][0].item())
 
     def feasible_sets(self):
         if self.conic is not None:
