@@ -165,6 +165,24 @@ def test_split_backward_forward_and_host_copy(ta):
     assert (one["status"][::7] == 3).all() and (one["status"][1::7] == 0).all()
     for key in ("K", "sd", "sdd", "status"):
         assert np.array_equal(one[key], host[key].numpy(), equal_nan=True), key
+    # pipelined caller (sync=False): several solves in flight on two result buffers; every device-to-host copy runs on the
+    # package's copy stream; each buffer is valid when its own host_ready event has completed — no device-wide sync
+    sets = [inst._pinned_outputs(None), inst._pinned_outputs(None)]
+    starts = [s0, np.zeros(B), 0.5 * s0, s0]
+    refs = [inst.compute_parameterization(v, 0.0).to_host() for v in starts]
+    pending = []
+    for k, v in enumerate(starts):
+        if k >= 2:   # the buffer about to be reused: its previous solve must have landed and been checked
+            kk, evt, buf = pending.pop(0)
+            evt.synchronize()
+            for key in ("K", "sd", "sdd", "status"):
+                assert np.array_equal(refs[kk][key], buf[key].numpy(), equal_nan=True), (kk, key)
+        buf = inst.solve_to_host(v, 0.0, pinned=sets[k & 1], sync=False)
+        pending.append((k, inst.host_ready, buf))
+    for kk, evt, buf in pending:
+        evt.synchronize()
+        for key in ("K", "sd", "sdd", "status"):
+            assert np.array_equal(refs[kk][key], buf[key].numpy(), equal_nan=True), (kk, key)
 
 
 def test_fast_lower_bound_mode(ta):

@@ -71,6 +71,18 @@ def build_records(ctx, constraints, out=None):
     return records, R
 
 
+_COPY_STREAMS = {}
+
+
+def copy_stream(device):
+    """One device-to-host copy stream per device, shared by every solve: copies of consecutive solves stay ordered."""
+    torch = engine.torch_mod()
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
+
+
 class BatchResult(object):
     """Device-resident result of BatchTOPPRA.compute_parameterization.
 
@@ -283,8 +295,9 @@ class BatchTOPPRA(object):
         copy of K overlapped with the forward pass: the scan runs as a backward-only and a forward-only launch and K
         leaves on a second stream in between.  Returns the dict of pinned host TENSORS (same keys and types for every
         problem kind: chunked and robust problems take the plain path).  sync=True (default): the host waits for the
-        copies, the buffers are valid on return.  sync=False (pipelined callers): nothing is waited for; the buffers
-        are valid once `self.host_ready` (a CUDA event recorded after the last copy) has completed —
+        copies, the buffers are valid on return.  sync=False (pipelined callers): nothing is waited for and all copies
+        run on the package's copy stream (`batch.copy_stream(device)`), so the next solve's kernels overlap them; the
+        buffers are valid once `self.host_ready` (a CUDA event recorded after the last copy) has completed —
         `inst.host_ready.synchronize()`."""
         torch = engine.torch_mod()
         pinned = self._pinned_outputs(pinned)
@@ -300,26 +313,43 @@ class BatchTOPPRA(object):
                 self.host_ready.synchronize()
             return pinned
         s0, s1 = self._vel_tensor(sd_start), self._vel_tensor(sd_end)
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(self.device)
+        copy = copy_stream(self.device)
+        self._copy_stream = copy
         back = self._scan(s0, s1, backward_only=True)
         ev = torch.cuda.Event()
         ev.record(main)
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(ev)
+        with torch.cuda.stream(copy):
+            copy.wait_event(ev)
             pinned["K"].copy_(back["K"], non_blocking=True)
+        back["K"].record_stream(copy)
         fwd = self._scan(s0, s1, forward_from=back)
-        pinned["sd"].copy_(fwd["sd"], non_blocking=True)
-        pinned["sdd"].copy_(fwd["u"], non_blocking=True)
-        pinned["status"].copy_(fwd["status"], non_blocking=True)
-        pinned["fail_stage"].copy_(fwd["fail_stage"], non_blocking=True)
-        main.wait_stream(self._copy_stream)   # the step is complete (for events / callers) when K has landed too
-        back["K"].record_stream(self._copy_stream)
         self.last_result = BatchResult(fwd)
-        self.host_ready = torch.cuda.Event()
-        self.host_ready.record(main)
         if sync:
+            # the host waits for this solve: the small results follow the forward launch on the caller's stream
+            pinned["sd"].copy_(fwd["sd"], non_blocking=True)
+            pinned["sdd"].copy_(fwd["u"], non_blocking=True)
+            pinned["status"].copy_(fwd["status"], non_blocking=True)
+            pinned["fail_stage"].copy_(fwd["fail_stage"], non_blocking=True)
+            main.wait_stream(copy)            # the step is complete (for events / callers) when K has landed too
+            self.host_ready = torch.cuda.Event()
+            self.host_ready.record(main)
             self.host_ready.synchronize()     # host-visible: every copy above has landed
+            return pinned
+        # pipelined caller: EVERY device-to-host copy goes to the copy stream, so the caller's stream is free for the next
+        # solve at once (its kernels overlap these copies); the buffers are valid at `self.host_ready`.  Callers that keep
+        # more than one solve in flight alternate between two sets of pinned buffers.
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(copy):
+            copy.wait_event(done)
+            pinned["sd"].copy_(fwd["sd"], non_blocking=True)
+            pinned["sdd"].copy_(fwd["u"], non_blocking=True)
+            pinned["status"].copy_(fwd["status"], non_blocking=True)
+            pinned["fail_stage"].copy_(fwd["fail_stage"], non_blocking=True)
+            self.host_ready = torch.cuda.Event()
+            self.host_ready.record(copy)
+        for key in ("sd", "u", "status", "fail_stage"):
+            fwd[key].record_stream(copy)
         return pinned
 
     def chunk_size(self):

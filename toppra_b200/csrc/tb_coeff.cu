@@ -325,106 +325,114 @@ __global__ void xbound_varying_kernel(const double *__restrict__ ppoly, const do
 //     c = tau(q, 0, 0);  a = tau(q, 0, q') - c;  b = tau(q, q', q'') - c;  c += sign(q') * friction  (:138)
 // for the joint-torque factory (:114-140): F = [I; -I], g = [tau_max; -tau_min], Interpolation lift
 // (linear_constraint.py:134-163).  The reference calls a user Python inv_dyn 3 (N+1) times per path; here the inverse
-// dynamics is a DEVICE MODEL picked from a small registry (TB_INVDYN_*), evaluated by one thread per (path, gridpoint)
-// straight from the spline: no [B*G, dof] intermediates, no host round trip.  Each thread writes the first row block
-// of its own record and the lifted block of the PREVIOUS record (a+ = a_i + 2 delta_{i-1} b_i), so nothing is
-// evaluated twice; the last gridpoint duplicates itself (linear_constraint.py:141-153).
+// dynamics is a DEVICE MODEL picked from a small registry (TB_INVDYN_*), evaluated straight from the spline: no
+// [B*G, dof] intermediates, no host round trip.  The lifted block of record i (a+ = a_{i+1} + 2 delta_i b_{i+1}) reads the
+// values of gridpoint i+1 from shared memory; the last gridpoint duplicates itself (linear_constraint.py:141-153).
 //   TB_INVDYN_COUPLED_COSINE: tau_i = p0 qdd_i + p1 sum_j cos(q_i - q_j) qdd_j + p2 sin(q_i) |qd|^2 + p3 sin(q_i)
 //                             (SURVEY.md section 8d cfg 3: p = (2, 0.3, 0.1, 4.9));  cos(q_i - q_j) is expanded
 //                             into cos q_i cos q_j + sin q_i sin q_j: dof sincos instead of dof^2 cosines
 //   TB_INVDYN_PENDULUMS:      tau_i = p[2i] qdd_i + p[2i+1] sin(q_i)   (independent joints; params [dof][2])
 constexpr int SO_MAX_DOF = 16;
 
-template <int MODEL>
-__device__ __forceinline__ void inv_dyn_terms(const int dof, const double *__restrict__ prm, const double *q,
-                                              const double *qd, const double *qdd, double *a, double *b, double *c) {
-  double sq[SO_MAX_DOF], cq[SO_MAX_DOF];
-  for (int k = 0; k < dof; ++k) sincos(q[k], &sq[k], &cq[k]);
-  if (MODEL == TB_INVDYN_COUPLED_COSINE) {
-    const double m0 = prm[0], m1 = prm[1], h = prm[2], gr = prm[3];
-    double cs1 = 0.0, ss1 = 0.0, cs2 = 0.0, ss2 = 0.0, v2 = 0.0;
-    for (int k = 0; k < dof; ++k) {
-      cs1 += cq[k] * qd[k]; ss1 += sq[k] * qd[k];      // M(q) q'  (tau(q, 0, q') - c)
-      cs2 += cq[k] * qdd[k]; ss2 += sq[k] * qdd[k];    // M(q) q''
-      v2 += qd[k] * qd[k];
-    }
-    for (int k = 0; k < dof; ++k) {
-      c[k] = gr * sq[k];
-      a[k] = m0 * qd[k] + m1 * (cq[k] * cs1 + sq[k] * ss1);
-      b[k] = m0 * qdd[k] + m1 * (cq[k] * cs2 + sq[k] * ss2) + h * sq[k] * v2;
-    }
-  } else {
-    for (int k = 0; k < dof; ++k) {
-      c[k] = prm[2 * k + 1] * sq[k];
-      a[k] = prm[2 * k] * qd[k];
-      b[k] = prm[2 * k] * qdd[k];
-    }
-  }
-}
+// second_order_rows_tiled_kernel: one CTA per (path, 32 gridpoints).
+//   phase 1  thread per (gridpoint, joint): q, q', q'' from the spline and sincos(q) — the expensive part, spread over
+//            all threads instead of one thread per gridpoint;
+//   phase 2  thread per (gridpoint, joint): the model's coupling sums over the joints (same summation order as
+//            the first version of this kernel) -> a, b, c in shared memory (33 gridpoints: one more than the tile for the lifted block);
+//   phase 3  the CTA streams the 3 x (2 | 4) dof row entries of its 32 records out in record order: consecutive
+//            threads write consecutive doubles (runs of (2 | 4) dof doubles) instead of one thread striding through 72
+//            scattered 8-byte stores per gridpoint.
+constexpr int SO_TILE = 32;
+constexpr int SO_THREADS = 128;
 
 template <int MODEL>
-__global__ void __launch_bounds__(128)
-second_order_rows_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks, const int breaks_shared,
-                         const long B, const int nseg, const int dof, const double *__restrict__ grid,
-                         const int grid_shared, const int G, const double *__restrict__ prm,
-                         const double *__restrict__ taulim, const int lim_shared, const double *__restrict__ friction,
-                         const int interp, double *__restrict__ records, const int W, const int R_total,
-                         const int row0) {
-  const long total = B * G;
-  const int N = G - 1;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int gi = (int)(idx % G);
-    const long p = idx / G;
-    const double *x = breaks + (breaks_shared ? 0 : p * (nseg + 1));
-    const double *cpp = ppoly + p * 4 * nseg * dof;
-    const double *gp = grid + (grid_shared ? 0 : p * G);
-    const double *tl = taulim + (lim_shared ? 0 : p * dof * 2);
-    const double s = gp[gi];
+__global__ void __launch_bounds__(SO_THREADS)
+second_order_rows_tiled_kernel(const double *__restrict__ ppoly, const double *__restrict__ breaks,
+                               const int breaks_shared, const int nseg, const int dof, const double *__restrict__ grid,
+                               const int grid_shared, const int G, const double *__restrict__ prm,
+                               const double *__restrict__ taulim, const int lim_shared,
+                               const double *__restrict__ friction, const int interp, double *__restrict__ records,
+                               const int W, const int R_total, const int row0) {
+  extern __shared__ double so_sm[];
+  const int tiles = (G + SO_TILE - 1) / SO_TILE;
+  const long p = blockIdx.x / tiles;
+  const int gi0 = (int)(blockIdx.x % tiles) * SO_TILE;
+  const int npts = min(SO_TILE, G - gi0);                  // records of this tile
+  const int nev = min(npts + 1, G - gi0);                  // gridpoints evaluated (one more for the lift)
+  const int tid = threadIdx.x, N = G - 1;
+  const double *x = breaks + (breaks_shared ? 0 : p * (nseg + 1));
+  const double *cpp = ppoly + p * 4 * nseg * dof;
+  const double *gp = grid + (grid_shared ? 0 : p * G);
+  const double *tl = taulim + (lim_shared ? 0 : p * dof * 2);
+  // shared: per evaluated gridpoint and joint: qd, qdd, sin q, cos q, then a, b, c; the gridpoints themselves
+  const int ne = (SO_TILE + 1) * dof;
+  double *s_qd = so_sm, *s_qdd = so_sm + ne, *s_sq = so_sm + 2 * ne, *s_cq = so_sm + 3 * ne;
+  double *s_a = so_sm + 4 * ne, *s_b = so_sm + 5 * ne, *s_c = so_sm + 6 * ne, *s_g = so_sm + 7 * ne;
+  const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  for (int t = tid; t < nev; t += SO_THREADS) s_g[t] = gp[gi0 + t];
+  for (int e = tid; e < nev * dof; e += SO_THREADS) {
+    const int t = e / dof, k = e - t * dof;
+    const double s = gp[gi0 + t];
     const int seg = find_interval(x, nseg, s);
-    double q[SO_MAX_DOF], qd[SO_MAX_DOF], qdd[SO_MAX_DOF], a[SO_MAX_DOF], b[SO_MAX_DOF], c[SO_MAX_DOF];
-    const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
-    for (int k = 0; k < dof; ++k) {
-      q[k] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 0);
-      qd[k] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 1);
-      qdd[k] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 2);
-    }
-    inv_dyn_terms<MODEL>(dof, prm, q, qd, qdd, a, b, c);
-    if (friction)
-      for (int k = 0; k < dof; ++k) {  // np.sign(q') * joint_friction, linear_second_order.py:138
-        const double sg = (qd[k] > 0) ? 1.0 : ((qd[k] < 0) ? -1.0 : 0.0);
-        c[k] = c[k] + sg * friction[k];
+    const double q = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 0);
+    s_qd[e] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 1);
+    s_qdd[e] = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 2);
+    double sv, cv;
+    sincos(q, &sv, &cv);
+    s_sq[e] = sv;
+    s_cq[e] = cv;
+  }
+  __syncthreads();
+  for (int e = tid; e < nev * dof; e += SO_THREADS) {
+    const int t = e / dof, k = e - t * dof;
+    const double *qd = s_qd + t * dof, *qdd = s_qdd + t * dof, *sq = s_sq + t * dof, *cq = s_cq + t * dof;
+    double av, bv, cv;
+    if (MODEL == TB_INVDYN_COUPLED_COSINE) {
+      const double m0 = prm[0], m1 = prm[1], h = prm[2], gr = prm[3];
+      double cs1 = 0.0, ss1 = 0.0, cs2 = 0.0, ss2 = 0.0, v2 = 0.0;
+      for (int j = 0; j < dof; ++j) {
+        cs1 += cq[j] * qd[j]; ss1 += sq[j] * qd[j];
+        cs2 += cq[j] * qdd[j]; ss2 += sq[j] * qdd[j];
+        v2 += qd[j] * qd[j];
       }
-    double *rec = records + idx * (long)W;
-    const int m = dof, k2 = 2 * dof;
-    // first block of this record: rows [0, m) = +(a, b, c) - tau_max, rows [m, 2m) = -(a, b, c) + tau_min
-    for (int k = 0; k < m; ++k) {
-      const double gmax = tl[k * 2 + 1], gmin = -tl[k * 2 + 0];  // g = [tau_max; -tau_min]
-      rec[row0 + k] = a[k];
-      rec[R_total + row0 + k] = b[k];
-      rec[2 * R_total + row0 + k] = c[k] - gmax;
-      rec[row0 + m + k] = -a[k];
-      rec[R_total + row0 + m + k] = -b[k];
-      rec[2 * R_total + row0 + m + k] = -c[k] - gmin;
+      cv = gr * sq[k];
+      av = m0 * qd[k] + m1 * (cq[k] * cs1 + sq[k] * ss1);
+      bv = m0 * qdd[k] + m1 * (cq[k] * cs2 + sq[k] * ss2) + h * sq[k] * v2;
+    } else {
+      cv = prm[2 * k + 1] * sq[k];
+      av = prm[2 * k] * qd[k];
+      bv = prm[2 * k] * qdd[k];
     }
-    if (interp) {
-      // lifted block of the previous record (and of this one at the last gridpoint, which duplicates itself)
-      for (int tgt = (gi > 0 ? gi - 1 : gi); tgt <= gi; ++tgt) {
-        if (tgt == gi && gi != N) continue;
-        const bool lift = tgt < gi;
-        const double two_delta = lift ? 2 * (gp[gi] - gp[tgt]) : 0.0;
-        double *rt = records + (p * G + tgt) * (long)W;
-        for (int k = 0; k < m; ++k) {
-          const double gmax = tl[k * 2 + 1], gmin = -tl[k * 2 + 0];
-          const double av = lift ? a[k] + two_delta * b[k] : a[k];
-          rt[row0 + k2 + k] = av;
-          rt[R_total + row0 + k2 + k] = b[k];
-          rt[2 * R_total + row0 + k2 + k] = c[k] - gmax;
-          rt[row0 + k2 + m + k] = -av;
-          rt[R_total + row0 + k2 + m + k] = -b[k];
-          rt[2 * R_total + row0 + k2 + m + k] = -c[k] - gmin;
-        }
-      }
+    if (friction) {  // np.sign(q') * joint_friction, linear_second_order.py:138
+      const double sg = (qd[k] > 0) ? 1.0 : ((qd[k] < 0) ? -1.0 : 0.0);
+      cv = cv + sg * friction[k];
     }
+    s_a[e] = av; s_b[e] = bv; s_c[e] = cv;
+  }
+  __syncthreads();
+  // phase 3: record entries in record order.  Row j of the constraint: blk = j / dof (bit 0: negated copy, bit 1: the
+  // block evaluated at s_{i+1} and lifted), k = j % dof.
+  const int nrows = (interp ? 4 : 2) * dof;
+  const int per_rec = 3 * nrows;
+  double *rec0 = records + (p * G + gi0) * (long)W;
+  for (int e = tid; e < npts * per_rec; e += SO_THREADS) {
+    const int gl = e / per_rec, r = e - gl * per_rec;
+    const int part = r / nrows, j = r - part * nrows;
+    const int blk = j / dof, k = j - blk * dof;
+    const bool neg = (blk & 1) != 0, second = (blk >> 1) != 0;
+    const int gi = gi0 + gl;
+    const bool lift = second && gi < N;                   // the last gridpoint duplicates itself (linear_constraint.py:141-153)
+    const int src = (lift ? gl + 1 : gl) * dof + k;
+    double v;
+    if (part == 0) {
+      v = lift ? s_a[src] + (2 * (s_g[gl + 1] - s_g[gl])) * s_b[src] : s_a[src];
+      v = neg ? -v : v;
+    } else if (part == 1) {
+      v = neg ? -s_b[src] : s_b[src];
+    } else {
+      v = neg ? (-s_c[src] - (-tl[k * 2 + 0])) : (s_c[src] - tl[k * 2 + 1]);   // F c - g, g = [tau_max; -tau_min]
+    }
+    rec0[(long)gl * W + part * R_total + row0 + j] = v;
   }
 }
 
@@ -561,18 +569,18 @@ extern "C" int tb_coeff_second_order(int model, const double *params, int nparam
     set_error("tb_coeff_second_order: rows [%d,%d) do not fit R_total=%d / W=%d", row0, row0 + nrows, R_total, W);
     return TB_ERR_ARG;
   }
-  const long total = (long)B * G;
-  const int threads = 128;
-  long blocks = (total + threads - 1) / threads;
-  if (blocks > 148L * 64) blocks = 148L * 64;
   cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = (G + SO_TILE - 1) / SO_TILE;
+  const long blocks = (long)B * tiles;
+  if (blocks > 0x7fffffffL) { set_error("tb_coeff_second_order: B * ceil(G / 32) = %ld CTAs exceed the grid limit", blocks); return TB_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)(7 * (SO_TILE + 1) * dof + SO_TILE + 1) * sizeof(double);
   if (model == TB_INVDYN_COUPLED_COSINE)
-    second_order_rows_kernel<TB_INVDYN_COUPLED_COSINE><<<(unsigned)blocks, threads, 0, st>>>(
-        ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
+    second_order_rows_tiled_kernel<TB_INVDYN_COUPLED_COSINE><<<(unsigned)blocks, SO_THREADS, smem, st>>>(
+        ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
         records, W, R_total, row0);
   else
-    second_order_rows_kernel<TB_INVDYN_PENDULUMS><<<(unsigned)blocks, threads, 0, st>>>(
-        ppoly, breaks, breaks_shared, B, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
+    second_order_rows_tiled_kernel<TB_INVDYN_PENDULUMS><<<(unsigned)blocks, SO_THREADS, smem, st>>>(
+        ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
         records, W, R_total, row0);
   return check_launch("tb_coeff_second_order");
 }

@@ -1112,8 +1112,11 @@ int launch_scan_velacc(const VelAccSrc &src, int W, int R, const double *grid, i
                        const double *sd_start, const double *sd_end, const double *sd_end_hi, int flags, double *K,
                        double *sd, double *u, int *status, int *fail_stage, int *counters, const int *glen,
                        cudaStream_t stream) {
-  static const char *occ_env = getenv("TB_SCAN_FUSED_OCC");  // tuning: resident warps per SM (32 -> 64 regs, 28 -> 72)
-  const int occ = occ_env ? atoi(occ_env) : TB_SCAN_FUSED_WARPS_PER_SM;
+  // Register budget by batch size (measured r02, B200): up to 28 x 148 = 4144 paths the 72-register build holds the
+  // whole batch in one wave and wins (1.317 vs 1.339 ms at 4096 paths); larger batches are issue-bound and want the 32
+  // resident warps per SM of the 64-register build (2^20 paths: 290.7 vs 308.8 ms).  TB_SCAN_FUSED_OCC=28|32 overrides.
+  static const char *occ_env = getenv("TB_SCAN_FUSED_OCC");
+  const int occ = occ_env ? atoi(occ_env) : ((long)B <= 148L * TB_SCAN_FUSED_WARPS_PER_SM ? TB_SCAN_FUSED_WARPS_PER_SM : 32);
   if (occ == 28)
     return launch_scan_velacc_occ<28>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
                                       status, fail_stage, counters, glen, stream);
