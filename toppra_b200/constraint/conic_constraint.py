@@ -60,7 +60,9 @@ class RobustLinearConstraint(ConicConstraint):
         N = len(gridpoints) - 1
         P = np.zeros((N + 1, d + 2, 3, 3))
         P[:] = np.diag(self.ellipsoid_axes_lengths)
-        _, _, _, _, _, u_, x_ = (None,) * 7
+        # the base constraint's own ubound / xbound pass through (reference :97-99, :124); the in-scope bases
+        # (JointAcceleration, SecondOrder, JointTorque) return None for both, user-defined ones may not
+        u_, x_ = self.base_constraint.compute_constraint_params(path, gridpoints)[5:7]
         return a, b, c, P, u_, x_
 
     # device protocol (see LinearConstraint): the rows are those of the base constraint; the solver gets the

@@ -493,7 +493,8 @@ scan_kernel(const double *__restrict__ records, const int W, const int R, const 
   // of the path's PPoly dco [nseg][dof][5] + breakpoints [nseg+1] (in W doubles; W = that size rounded up to even)
   double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (FUSED ? 1 : SCAN_NBUF) * W;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * (FUSED ? 1 : SCAN_NBUF) * W * sizeof(double)) + warp * SCAN_NBUF;
-  const int Gp = glen ? min(max(glen[path], 1), G) : G;  // this path's gridpoints
+  // ragged batches run on the run-time-flag build (CFLAGS < 0); the specialised builds keep G as the loop bound
+  const int Gp = (CFLAGS < 0 && glen) ? min(max(glen[path], 1), G) : G;  // this path's gridpoints
   const int N = Gp - 1, nC = R + 2;
   const unsigned rec_bytes = (unsigned)(W * sizeof(double));
   // Per-path base pointers live in shared memory: under the 64-register cap the compiler otherwise rebuilds them
@@ -1057,7 +1058,7 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
   const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
   auto kern = (RPL == 1 && dense) ? (fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true> : scan_kernel<RPL, SCAN_WARPS, MINB, false>)
                                   : (fast ? scan_kernel<RPL, SCAN_WARPS, 1, true> : scan_kernel<RPL, SCAN_WARPS, 1, false>);
-  if (RPL == 1 && dense && !counters) {
+  if (RPL == 1 && dense && !counters && !glen) {
     // the three launch kinds of the batched solver get their own instantiation: full scan, backward only, forward only
     const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
     if (mode == 0)
@@ -1092,8 +1093,8 @@ int launch_scan_velacc_occ(const VelAccSrc &src, int W, int R, const double *gri
   const bool fast = (flags & TB_SCAN_FAST_LOWER) != 0;
   const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
   auto kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, -1, true> : scan_kernel<1, SCAN_WARPS, MINB, false, -1, true>;
-  if (counters) {
-    // instrumented launch: the run-time-flag build
+  if (counters || glen) {
+    // instrumented or ragged launch: the run-time-flag build
   } else if (mode == 0)
     kern = fast ? scan_kernel<1, SCAN_WARPS, MINB, true, 0, true> : scan_kernel<1, SCAN_WARPS, MINB, false, 0, true>;
   else if (mode == TB_SCAN_BACKWARD_ONLY)
