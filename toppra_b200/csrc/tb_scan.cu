@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "tb_common.cuh"
+#include "tb_scan_common.cuh"
 
 namespace tb {
 namespace {
@@ -78,40 +79,6 @@ __device__ __forceinline__ double warp_max(double v) {
   return __hiloint2double((int)(mh ^ (unsigned)(m2 | (int)0x80000000)), (int)(ml ^ (unsigned)m2));
 }
 
-// Position of LP row r in Seidel's processing order, cy_seidel_solverwrapper.pyx:252-264:
-// a valid warm-start pair puts active_c[1] first, active_c[0] second, then the remaining rows ascending.
-__device__ __forceinline__ int row_pos(int r, bool valid, int ac0, int ac1) {
-  if (!valid) return r;
-  if (r == ac1) return 0;
-  if (r == ac0) return 1;
-  return 2 + r - (r > ac0 ? 1 : 0) - (r > ac1 ? 1 : 0);
-}
-__device__ __forceinline__ int pos_row(int p, bool valid, int ac0, int ac1) {
-  if (!valid) return p;
-  if (p == 0) return ac1;
-  if (p == 1) return ac0;
-  const int lo = min(ac0, ac1), hi = max(ac0, ac1);
-  int r = p - 2;
-  if (r >= lo) ++r;
-  if (r >= hi) ++r;
-  return r;
-}
-
-// Identity the optimiser cannot see through: keeps a sanitised division operand from being folded back into the
-// original one when the quotient is later replaced by a select (the compiler would divide the raw value again).
-__device__ __forceinline__ double opaque(double v) {
-  asm volatile("" : "+d"(v));
-  return v;
-}
-
-// Python's builtin max(a, b) / min(a, b) on floats (reachability_algorithm.py:324-354): a unless b compares beyond it
-__device__ __forceinline__ double py_max(const double a, const double b) { return (b > a) ? b : a; }
-__device__ __forceinline__ double py_min(const double a, const double b) { return (b < a) ? b : a; }
-
-constexpr int BOXBASE = 1 << 20;
-constexpr double SKIP_GAP = 1e-7;   // shortcuts A/B: required violation, relative to the terms' magnitudes (TINY = 1e-10)
-constexpr double SKIP_BIG = 1e300;
-constexpr double SKIP_TMAX = 90.0;  // shortcut A: largest line parameter of a skipped visit (see lp2d_impl)
 #ifndef TB_SCAN_NBUF
 #define TB_SCAN_NBUF 4
 #endif
@@ -456,14 +423,6 @@ __device__ __forceinline__ void set_xnext_rows(const int lane, const double delt
 // (tb_coeff.cu: PPoly derivative evaluation like scipy, interpolation lift a+ = q'(s_{i+1}) + 2 delta q''(s_{i+1}),
 // c = -amax / +amin), so the rows are bit-identical to the materialised records; only the velocity bound
 // (xbound [B][G][2], 16 B per gridpoint instead of 8 (3R+2)) still comes from memory.
-struct VelAccSrc {
-  const double *ppoly;   // [B][4][nseg][dof]
-  const double *breaks;  // [nseg+1] or [B][nseg+1]
-  const double *alim;    // [dof][2] or [B][dof][2]
-  const double *xbound;  // [B][G][2]
-  int breaks_shared, nseg, dof, lim_shared;
-};
-
 // UB: the stage records carry a u-bound pair (ulo, uhi) behind the x-bound pair (TB_SCAN_UBOUND: `ubound` of a
 // constraint, intersected into low/high[:, 0] by seidelWrapper.__init__, pyx:512-515); otherwise u in [-1e8, 1e8].
 // glen (optional): ragged batches, path p has glen[p] <= G gridpoints (strides stay G; outputs past glen[p] are NaN).
@@ -1208,6 +1167,11 @@ extern "C" int tb_scan_velacc_ragged(const double *ppoly, const double *breaks, 
     return TB_ERR_UNSUPPORTED;
   }
   const VelAccSrc src{ppoly, breaks, alim, xbound, breaks_shared, nseg, dof, lim_shared};
+  // the two-paths-per-warp build (tb_scan_pair.cu) takes every dense launch it supports; ragged, instrumented and TOPPRAsd
+  // launches stay on the one-warp-per-path kernel
+  if (!glen && !counters && scan_velacc_pair_supported(dof, interp, nseg, flags))
+    return launch_scan_velacc_pair(src, interp, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
+                                   status, fail_stage, (cudaStream_t)stream);
   return launch_scan_velacc(src, Wc, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u, status,
                             fail_stage, counters, glen, (cudaStream_t)stream);
 }
