@@ -1,4 +1,8 @@
-// tb_scan_pair.cu — K2 for JointVelocity + JointAcceleration problems, TWO PATHS PER WARP (tb_scan_velacc's fast build).
+// tb_scan_pair.cu — K2 for JointVelocity + JointAcceleration problems, TWO PATHS PER WARP.  EXPERIMENT, opt-in
+// (TB_SCAN_PAIR=1: divergent half-warps, TB_SCAN_PAIR=2: lockstep): both forms are bit-identical to the one-warp-per-path
+// kernel on the whole GPU test suite and both are SLOWER on a B200 (4096 paths: 1.68 / 1.71 ms vs 1.32 ms; 2^20 paths:
+// 2.5 / 2.75 M paths/s vs 3.6 M) — see profiles/r02_pair_*_experiment_ncu.txt and DESIGN.md section 10.  The default
+// launch path does not use this file.
 //
 // Replaces the same reference functions as tb_scan.cu (reachability_algorithm.py:166-376, time_optimal_algorithm.py:55-92,
 // cy_seidel_solverwrapper.pyx:93-144, 149-390, 549-697); results are bit-identical to it and to the one-warp-per-path
@@ -486,6 +490,439 @@ scan_pair_kernel(const VelAccSrc src, const int interp, const int Wc, const doub
   }
 }
 
+// ======================================================================================================================
+// LOCKSTEP form.  redux.sync and vote.sync deliver ONE result per warp, so with half-warp masks every collective of the
+// kernel above is executed once per half plus a convergence branch (measured: branch_resolving 26 % of the stall
+// samples, 1.67 ms).  Here both half-warps run ONE instruction stream: reductions are xor-butterflies of full-mask
+// shuffles (offsets 8, 4, 2, 1 stay inside a half), votes are one full-mask ballot from which each half reads its 16 bits,
+// and what differs between the two paths — number of re-solves, shortcut taken or not, failure — is predication on
+// per-half flags instead of branches.  Same arithmetic, same results.
+// ======================================================================================================================
+__device__ __forceinline__ double half_min(double v) {
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {
+    const double o = __shfl_xor_sync(FULL, v, off);
+    v = (o < v) ? o : v;
+  }
+  return v;
+}
+__device__ __forceinline__ int half_min_int(int v) {
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(FULL, v, off));
+  return v;
+}
+__device__ __forceinline__ bool half_any(const bool pred, const int gbase) {
+  return ((__ballot_sync(FULL, pred) >> gbase) & 0xffffu) != 0u;
+}
+
+// lp2d for both halves at once.  `en`: this half has a problem to solve.  Returns feasibility per half; outputs (ac0, ac1,
+// out_u, out_x) are written only for a feasible, enabled half.
+template <bool SKIP>
+__device__ __forceinline__ bool lp2d_lock(const double v0, const double v1, const double a, const double b, const double cP,
+                                          const double cN, const int rP, const int rN, const int nC, const double low0,
+                                          const double high0, const double low1, const double high1, int &ac0, int &ac1,
+                                          double &out_u, double &out_x, const int l, const int gbase, const bool en) {
+  bool act = en && !(low0 > high0 || low1 > high1);  // pyx:233-235
+  bool ok = act;
+  const bool valid = ac0 >= 0 && ac0 < nC && ac1 >= 0 && ac1 < nC && ac0 != ac1;  // uniform over the half-warp
+  double p0 = (v0 > LP_TINY) ? high0 : low0;       // pyx:236-247
+  double p1 = (v1 > LP_TINY) ? high1 : low1;
+  int nac0 = (v0 > LP_TINY) ? -2 : -1;
+  int nac1 = (v1 > LP_TINY) ? -4 : -3;
+  const int posP = (rP >= 0) ? row_pos(rP, valid, ac0, ac1) : INT_MAX;
+  const int posN = (rN >= 0) ? row_pos(rN, valid, ac0, ac1) : INT_MAX;
+  const unsigned lt_mask = (1u << l) - 1u;
+  int kpos = -1;
+  const bool skip_ok = SKIP && (((v0 > LP_TINY) && (v1 < 0)) || ((v0 < -LP_TINY) && (v1 > 0)));
+  while (true) {
+    int knew = INT_MAX;
+    // ---- shortcut A (natural order), for the halves that are at their first visit without a valid warm-start pair
+    const bool needA = SKIP && act && kpos < 0 && !valid && skip_ok;
+    if (SKIP && __any_sync(FULL, needA)) {
+      const double sg = (v0 > 0) ? 1.0 : -1.0;
+      const double x = p1, u0m = sg * p0;
+      const double sa = sg * a;
+      const bool aup = sa > LP_TINY, adn = sa < -LP_TINY, any = aup || adn;
+      const bool realP = posP != INT_MAX, realN = posN != INT_MAX;
+      const bool uprP = realP && aup, uprN = realN && adn, lorP = realP && adn, lorN = realN && aup;
+      const double bx = b * x;
+      const double bxcP = bx + cP, bxcN = -bx + cN;
+      const double den = any ? a : 1.0;
+      const bool znP = (bxcP == 0.0), znN = (bxcN == 0.0);
+      const double qdP = -opaque(znP ? 1.0 : bxcP) / den;
+      const double qdN = opaque(znN ? 1.0 : bxcN) / den;
+      const double uoP = znP ? 0.0 : sg * qdP, uoN = znN ? 0.0 : sg * qdN;
+      const bool hasU = uprP || uprN;
+      const double uoU = uprP ? uoP : uoN;
+      const int posU = uprP ? posP : posN;
+      const double v1dP = (-b) * v0 + a * v1;
+      const double v1dU = uprP ? v1dP : -v1dP;
+      bool bad = hasU && !((fabs(v1dU) < LP_TINY) || (v1dU < 0));
+      const double aU = uprP ? a : -a, bU = uprP ? b : -b;
+      bad = bad || (hasU && !(fabs(x * aU - (sg * uoU) * bU) < SKIP_TMAX * (aU * aU + bU * bU)));
+      const double um = half_min(hasU ? uoU : SKIP_BIG);
+      const int m = half_min_int((hasU && uoU == um) ? posU : INT_MAX);
+      double second = half_min((hasU && posU != m) ? uoU : SKIP_BIG);
+      second = (u0m < second) ? u0m : second;
+      if (hasU && posU == m) {
+        const double cU = uprP ? cP : cN, bxcU = uprP ? bxcP : bxcN;
+        const double au = aU * (sg * second);
+        const double val = au + bxcU;
+        bad = bad || !(val >= SKIP_GAP * (1.0 + fabs(au) + fabs(bU * x) + fabs(cU)));
+      }
+      if (posP < m)
+        bad = bad || (lorP && (uoP > um - 1e-9 * (1.0 + fabs(um)))) || (!uprP && !lorP && ((bxcP > -1e-9) || (a != 0.0)));
+      if (posN < m)
+        bad = bad || (lorN && (uoN > um - 1e-9 * (1.0 + fabs(um)))) || (!uprN && !lorN && ((bxcN > -1e-9) || (a != 0.0)));
+      const double ur = sg * um;
+      bad = bad || (ur < low0 + 1.0) || (ur > high0 - 1.0);
+      const bool anybad = half_any(bad, gbase);
+      if (needA && m != INT_MAX && !anybad) knew = m;
+    }
+    // ---- first row (in order) violated at the current point, pyx:269-275 (NaN counts as violated)
+    const bool searched = (knew == INT_MAX);
+    {
+      const double s = a * p0 + b * p1;
+      const double valP = s + cP, valN = -s + cN;
+      const bool candP = !(valP < LP_TINY) && (posP > kpos) && (posP != INT_MAX);
+      const bool candN = !(valN < LP_TINY) && (posN > kpos) && (posN != INT_MAX);
+      const int found = half_min_int(min(candP ? posP : INT_MAX, candN ? posN : INT_MAX));
+      if (searched) knew = found;
+    }
+    // ---- shortcut B (valid warm-start pair, row p = ac1 violated at the start vertex)
+    const bool needB = SKIP && act && searched && kpos < 0 && valid && skip_ok && knew == 0;
+    if (SKIP && __any_sync(FULL, needB)) {
+      const bool mineN = (rN == ac1);
+      const unsigned holder = (__ballot_sync(FULL, (rP == ac1) || mineN) >> gbase) & 0xffffu;
+      const int src = gbase + __ffs(holder) - 1;
+      const double ap = __shfl_sync(FULL, mineN ? -a : a, src);
+      const double bp = __shfl_sync(FULL, mineN ? -b : b, src);
+      const double cp = __shfl_sync(FULL, mineN ? cN : cP, src);
+      bool okb = fabs(ap) > 1e-6;
+      const double ia = 1.0 / (okb ? ap : 1.0);
+      okb = okb && (low1 <= high1 - 1e-7 * (1.0 + fabs(low1) + fabs(high1)));
+      const double slp = v1 - v0 * bp * ia;
+      okb = okb && !(fabs(slp) < 1e-6);
+      const double sx = (slp > 0) ? high1 : low1;
+      const double su = -(bp * sx + cp) * ia;
+      okb = okb && (su >= low0 + 1.0) && (su <= high0 - 1.0);
+      okb = okb && (fabs(sx * ap - su * bp) < 1e9 * (ap * ap + bp * bp));
+      const double t1P = a * su, t2P = b * sx;
+      const double vP = t1P + t2P + cP, vN = -t1P + -t2P + cN;
+      const double mag = fabs(t1P) + fabs(t2P);
+      const bool kviol = ((posP == 1) && (vP >= SKIP_GAP * (1.0 + mag + fabs(cP)))) ||
+                         ((posN == 1) && (vN >= SKIP_GAP * (1.0 + mag + fabs(cN))));
+      const bool anyk = half_any(kviol, gbase);
+      if (needB && anyk && okb) knew = 1;
+    }
+    if (act && knew == INT_MAX) act = false;           // no violated row left: this half holds its optimum
+    if (!__any_sync(FULL, act)) break;
+    // ---- projected re-solve on row `knew` (halves that are done run along; their results are discarded)
+    const int kp = knew;
+    const int krow = pos_row(kp, valid, ac0, ac1);
+    const bool kN = (rN == krow);
+    const unsigned holder = (__ballot_sync(FULL, (rP == krow) || kN) >> gbase) & 0xffffu;
+    const int src = gbase + __ffs(holder) - 1;
+    const double ak = __shfl_sync(FULL, kN ? -a : a, src);
+    const double bk = __shfl_sync(FULL, kN ? -b : b, src);
+    const double ck = __shfl_sync(FULL, kN ? cN : cP, src);
+    const double nrm = ak * ak + bk * bk;
+    const double zq = ((l & 1) ? (-bk * ck) : (-ak * ck)) / (act ? nrm : 1.0);
+    const double z0 = __shfl_sync(FULL, zq, gbase);
+    const double z1 = __shfl_sync(FULL, zq, gbase + 1);
+    const double dt0 = -bk, dt1 = ak;
+    const double v1d = dt0 * v0 + dt1 * v1;
+    const bool partP = posP < kp, partN = posN < kp;
+    const bool idle = !(partP || partN);
+    const unsigned idleb = (__ballot_sync(FULL, idle) >> gbase) & 0xffffu;
+    const int inl = min(__popc(idleb), 2);
+    const int rank = __popc(idleb & lt_mask);
+    const bool isbox = idle && rank < inl;
+    double thi, tlo;
+    int khi, klo;
+    bool bad = false;
+    {
+      const bool bu = rank == 0;
+      const double ba = isbox ? (bu ? 1.0 : 0.0) : a, bb = isbox ? (bu ? 0.0 : 1.0) : b;
+      const double bcP = isbox ? (bu ? -high0 : -high1) : cP, bcN = isbox ? (bu ? low0 : low1) : cN;
+      const int kP = isbox ? BOXBASE + (bu ? 1 : 3) : posP, kN2 = isbox ? BOXBASE + (bu ? 0 : 2) : posN;
+      project_slab(isbox || partP, isbox || partN, ba, bb, bcP, bcN, kP, kN2, dt0, dt1, z0, z1, thi, tlo, khi, klo, bad);
+    }
+    double my_hi = thi, my_lo = tlo;
+    double fhi = LP_INF, flo = -LP_INF;
+    int fkhi = INT_MAX, fklo = INT_MAX;
+    if (__any_sync(FULL, act && inl < 2)) {  // some half has fewer than two idle lanes: extra box item on its lanes 0..
+      const int slab = inl + l;
+      const bool bu = slab == 0, on = (inl < 2) && (slab < 2);
+      project_slab(on, on, bu ? 1.0 : 0.0, bu ? 0.0 : 1.0, bu ? -high0 : -high1, bu ? low0 : low1,
+                   BOXBASE + (bu ? 1 : 3), BOXBASE + (bu ? 0 : 2), dt0, dt1, z0, z1, fhi, flo, fkhi, fklo, bad);
+      my_hi = (fhi < my_hi) ? fhi : my_hi;
+      my_lo = (flo > my_lo) ? flo : my_lo;
+    }
+    const bool pick_min = (fabs(v1d) < LP_TINY) || (v1d < 0);
+    const double red = half_min(pick_min ? -my_lo : my_hi);
+    const double tstar = pick_min ? -red : red;
+    const bool cross = pick_min ? (my_hi < tstar) : (my_lo > tstar);
+    const bool infeas = half_any(bad || cross, gbase) || (tstar == (pick_min ? -LP_INF : LP_INF));  // pyx:376-383
+    int mykey = ((pick_min ? tlo : thi) == tstar) ? (pick_min ? klo : khi) : INT_MAX;
+    mykey = ((pick_min ? flo : fhi) == tstar) ? min(mykey, pick_min ? fklo : fkhi) : mykey;
+    const int akey = half_min_int(mykey);
+    if (act) {
+      if (infeas) {
+        ok = false;
+        act = false;
+      } else {
+        kpos = kp;
+        nac0 = krow;
+        nac1 = (akey >= BOXBASE) ? (-1 - (akey - BOXBASE)) : pos_row(akey, valid, ac0, ac1);
+        p0 = z0 + tstar * dt0;  // pyx:362-363
+        p1 = z1 + tstar * dt1;
+      }
+    }
+  }
+  if (ok) {
+    ac0 = nac0;
+    ac1 = nac1;
+    out_u = p0;
+    out_x = p1;
+  }
+  return ok;
+}
+
+__device__ __forceinline__ bool lp1d_lock(const double v0, const double x, const double a, const double b, const double cP,
+                                          const double cN, const double low0, const double high0, double &out_u,
+                                          const int gbase) {
+  const double bx = b * x;
+  const double bxcP = bx + cP, bxcN = -bx + cN;
+  const bool ap = a > LP_TINY, an = a < -LP_TINY;
+  const double den = (ap || an) ? a : 1.0;
+  const bool znP = (bxcP == 0.0), znN = (bxcN == 0.0);
+  const double qP0 = -opaque(znP ? 1.0 : bxcP) / den;
+  const double qN0 = opaque(znN ? 1.0 : bxcN) / den;
+  const double tP = znP ? (-bxcP) * den : qP0;
+  const double tN = znN ? (-bxcN) * (-den) : qN0;
+  const double tu = ap ? tP : tN, tl = ap ? tN : tP;
+  double my_hi = high0, my_lo = low0;
+  my_hi = ((ap || an) && tu < my_hi) ? tu : my_hi;
+  my_lo = ((ap || an) && tl > my_lo) ? tl : my_lo;
+  const bool pick_min = (fabs(v0) < LP_TINY) || (v0 < 0);
+  const double red = half_min(pick_min ? -my_lo : my_hi);
+  const double ustar = pick_min ? -red : red;
+  const bool infeas = half_any(pick_min ? (my_hi < ustar) : (my_lo > ustar), gbase);
+  out_u = ustar;
+  return !infeas;
+}
+
+template <bool FAST, int CFLAGS, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+scan_lock_kernel(const VelAccSrc src, const int interp, const int Wc, const double *__restrict__ grid, const int grid_shared,
+                 const int B, const int G, const double *__restrict__ sd_start, const double *__restrict__ sd_end,
+                 const double *__restrict__ sd_end_hi, double *__restrict__ Kout, double *__restrict__ sdout,
+                 double *__restrict__ uout, int *__restrict__ status, int *__restrict__ fail_stage) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = (int)threadIdx.x;
+  const int grp = lane >> 4, l = lane & 15, gbase = grp * GL;
+  const long path_raw = (long)blockIdx.x * 2 + grp;
+  const bool en = path_raw < B;                     // an odd batch: the last half-warp runs along on the last path, muted
+  const long path = en ? path_raw : (long)B - 1;
+  constexpr bool backward_only = (CFLAGS & TB_SCAN_BACKWARD_ONLY) != 0;
+  constexpr bool forward_only = (CFLAGS & TB_SCAN_FORWARD_ONLY) != 0;
+  const int N = G - 1, nseg = src.nseg, dof = src.dof;
+  const int nblk = interp ? 2 : 1;
+  const int nC = 2 * nblk * dof + 2;
+  double *bufs = reinterpret_cast<double *>(smem_raw) + (size_t)grp * Wc;
+  const double *dco = bufs, *sx = bufs + nseg * dof * 6;
+  {
+    const double *cpp = src.ppoly + (size_t)path * 4 * nseg * dof;
+    const double *xb = src.breaks + (src.breaks_shared ? 0 : (size_t)path * (nseg + 1));
+    double *dco_w = bufs, *sx_w = bufs + nseg * dof * 6;
+    for (int q = l; q < nseg * dof; q += GL) {
+      const double c0 = cpp[q], c1 = cpp[nseg * dof + q], c2 = cpp[2 * nseg * dof + q];
+      const double d0 = c0 * 3.0, d1 = c1 * 2.0, d2 = c2 * 1.0;
+      double *o = dco_w + q * 6;
+      o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d0 * 2.0; o[4] = d1 * 1.0; o[5] = 0.0;
+    }
+    for (int q = l; q <= nseg; q += GL) sx_w[q] = xb[q];
+  }
+  const bool isj = (l >= 1) && (l - 1 < nblk * dof);
+  const int f_second = isj ? (l - 1) / dof : 0;
+  const int f_k = isj ? (l - 1) - f_second * dof : 0;
+  const int rP = (l == 0) ? 1 : (isj ? 2 + 2 * f_second * dof + f_k : -1);
+  const int rN = (l == 0) ? 0 : (isj ? rP + dof : -1);
+  double cP = -1.0, cN = -1.0;
+  if (isj) {
+    const double *al = src.alim + (src.lim_shared ? 0 : (size_t)path * dof * 2);
+    cP = 0.0 - al[f_k * 2 + 1];
+    cN = 0.0 - (-al[f_k * 2 + 0]);
+  }
+  int f_seg = 0;
+  __syncwarp();
+  const double *gp = grid + (grid_shared ? 0 : (size_t)path * G);
+  const double *xbp = src.xbound + (size_t)path * G * 2;
+  double *Kp = Kout + (size_t)path * G * 2;
+  double *sdp = backward_only ? nullptr : sdout + (size_t)path * G;
+  double *up = backward_only ? nullptr : uout + (size_t)path * (G > 1 ? G - 1 : 0);
+  auto slab_ab = [&](const double s0, const double s1, const bool down, const double delta, double &ra, double &rb) {
+    const double s = f_second ? s1 : s0;
+    if (down) { while (f_seg > 0 && s < sx[f_seg]) --f_seg; }
+    else { while (f_seg < nseg - 1 && s >= sx[f_seg + 1]) ++f_seg; }
+    const double ds = s - sx[f_seg];
+    const double2 *o = reinterpret_cast<const double2 *>(dco + (f_seg * dof + f_k) * 6);
+    const double2 o01 = o[0], o23 = o[1], o45 = o[2];
+    double z = ds;
+    double v1 = 0.0 + o23.x;
+    v1 = v1 + o01.y * z;
+    z = z * ds;
+    v1 = v1 + o01.x * z;
+    double v2 = 0.0 + o45.x;
+    v2 = v2 + o23.y * ds;
+    const double va = f_second ? (v1 + (2 * delta) * v2) : v1;
+    ra = isj ? va : 0.0;
+    rb = isj ? v2 : 0.0;
+  };
+  const bool lead = en && (l == 0);               // the lane that writes this path's scalars
+
+  // ---------------- backward pass ----------------
+  const double sde = sd_end ? sd_end[path] : 0.0;
+  const double sds = sd_start ? sd_start[path] : 0.0;
+  const double sdeh = sd_end_hi ? sd_end_hi[path] : sde;
+  double kn0 = sde * sde, kn1 = sdeh * sdeh;
+  if (lead && !forward_only) { Kp[2 * N] = kn0; Kp[2 * N + 1] = kn1; }
+  int st = TB_STATUS_OK, fstage = -1;
+  int up0 = 0, up1 = 0, dn0 = 0, dn1 = 0;
+  if (forward_only) {
+    st = status[path];
+    fstage = fail_stage ? fail_stage[path] : -1;
+    kn0 = Kp[0];
+    kn1 = Kp[1];
+  }
+  double2 xb_ahead = make_double2(0.0, 0.0);
+  f_seg = nseg - 1;
+  if (!forward_only && N > 0) xb_ahead = reinterpret_cast<const double2 *>(xbp)[N - 1];
+  const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  double a, b;
+  bool alive = en;                                 // this half is still scanning
+  for (int i = forward_only ? -1 : N - 1; i >= 0; --i) {
+    if (!__any_sync(FULL, alive)) break;
+    const double g0 = gp[i], g1 = gp[i + 1];
+    const double delta = g1 - g0;
+    slab_ab(g0, g1, true, delta, a, b);
+    const double xlo = xb_ahead.x, xhi = xb_ahead.y;
+    if (i > 0) xb_ahead = reinterpret_cast<const double2 *>(xbp)[i - 1];
+    const double sa = (l == 0) ? 2 * delta : a, sb = (l == 0) ? 1.0 : b;
+    const double scP = (l == 0) ? -kn1 : cP, scN = (l == 0) ? kn0 : cN;
+    double uu = 0.0, xx = 0.0;
+    const bool ok_hi = lp2d_lock<true>(-1e-9, 1.0, sa, sb, scP, scN, rP, rN, nC, VAR_MIN, VAR_MAX, xlo, xhi, dn0, dn1, uu,
+                                       xx, l, gbase, alive);
+    const double x_upper = ok_hi ? xx : nan_d;
+    bool ok_lo;
+    double x_lower, ufeas;
+    bool fastok = false;
+    if (FAST) fastok = (xlo <= xhi) && lp1d_lock(1.0, xlo, sa, sb, scP, scN, VAR_MIN, VAR_MAX, ufeas, gbase);
+    {
+      // TB_SCAN_FAST_LOWER: a half with some feasible u at x = xlo takes min x = xlo and sits the exact LP out
+      const bool ok2 = lp2d_lock<true>(1e-9, -1.0, sa, sb, scP, scN, rP, rN, nC, VAR_MIN, VAR_MAX, xlo, xhi, up0, up1, uu,
+                                       xx, l, gbase, alive && !fastok);
+      ok_lo = fastok || ok2;
+      x_lower = fastok ? xlo : (ok2 ? xx : nan_d);
+    }
+    if (x_lower < 0) x_lower = 0;
+    if (alive && l == 0) { Kp[2 * i] = x_lower; Kp[2 * i + 1] = x_upper; }
+    const bool failnow = alive && !(ok_hi && ok_lo);
+    if (__any_sync(FULL, failnow)) {
+      for (int j = l; j < 2 * i; j += GL)
+        if (failnow) Kp[j] = 0.0;
+    }
+    if (failnow) {
+      st = TB_STATUS_FAIL_UNCONTROLLABLE;
+      fstage = i;
+      alive = false;
+    }
+    if (alive) {
+      kn0 = x_lower;
+      kn1 = x_upper;
+    }
+  }
+  __syncwarp();
+  const double x_start = sds * sds;
+  if (backward_only) {
+    if (lead) {
+      status[path] = st;
+      if (fail_stage) fail_stage[path] = fstage;
+    }
+    return;
+  }
+  if (st == TB_STATUS_OK) {
+    if (x_start + ALG_SMALL < kn0 || kn1 + ALG_SMALL < x_start) { st = TB_STATUS_FAIL_UNCONTROLLABLE; fstage = 0; }
+  }
+  alive = en && (st == TB_STATUS_OK);
+  if (en && !alive) {
+    for (int j = l; j < G; j += GL) sdp[j] = nan_d;
+    for (int j = l; j < N; j += GL) up[j] = nan_d;
+  }
+  // ---------------- forward pass ----------------
+  double x = x_start;
+  if (alive && l == 0) sdp[0] = x;
+  f_seg = 0;
+  for (int i = 0; i < N; ++i) {
+    if (!__any_sync(FULL, alive)) break;
+    const double g0 = gp[i], g1 = gp[i + 1];
+    const double delta = g1 - g0;
+    slab_ab(g0, g1, false, delta, a, b);
+    const double k0 = Kp[2 * (i + 1)], k1 = Kp[2 * (i + 1) + 1];
+    const double sa = (l == 0) ? 2 * delta : a, sb = (l == 0) ? 1.0 : b;
+    const double scP = (l == 0) ? -k1 : cP, scN = (l == 0) ? k0 : cN;
+    int tries = 0;
+    bool ok = false, pending = alive;
+    double uopt = 0.0;
+    while (true) {
+      double ucand;
+      const bool okc = lp1d_lock(-(-2 * delta), x, sa, sb, scP, scN, VAR_MIN, VAR_MAX, ucand, gbase);
+      if (pending) {
+        ok = okc;
+        uopt = ucand;
+        if (ok || tries >= MAX_TRIES) {
+          pending = false;
+        } else {
+          x = py_max(x - ALG_TINY, 0.999 * x);  // reachability_algorithm.py:324-327
+          ++tries;
+        }
+      }
+      if (!__any_sync(FULL, pending)) break;
+    }
+    const bool failnow = alive && !ok;
+    if (__any_sync(FULL, failnow)) {
+      if (failnow && l == 0) sdp[i] = x;
+      for (int j = i + 1 + l; j < G; j += GL)
+        if (failnow) sdp[j] = nan_d;
+      for (int j = i + l; j < N; j += GL)
+        if (failnow) up[j] = 0.0;
+    }
+    if (failnow) {
+      st = TB_STATUS_ERR_UNKNOWN;
+      fstage = i;
+      alive = false;
+    }
+    double x_next = x + 2 * delta * uopt;
+    x_next = py_max(x_next - ALG_TINY, 0.9999 * x_next);
+    x_next = py_min(k1, py_max(k0, x_next));
+    if (alive && l == 0) {
+      up[i] = uopt;
+      if (tries) sdp[i] = x;
+      sdp[i + 1] = x_next;
+    }
+    if (alive) x = x_next;
+  }
+  __syncwarp();
+  // sd = sqrt(x) for the paths that ran the forward pass (to the end or until ErrUnknown: sqrt(NaN) = NaN)
+  if (en && (st == TB_STATUS_OK || st == TB_STATUS_ERR_UNKNOWN))
+    for (int j = l; j < G; j += GL) sdp[j] = sqrt(sdp[j]);
+  if (lead) {
+    status[path] = st;
+    if (fail_stage) fail_stage[path] = fstage;
+  }
+}
+
 #ifndef TB_SCAN_PAIR_MINB
 #define TB_SCAN_PAIR_MINB 16  // resident warps per SM the register budget is sized for (128 registers)
 #endif
@@ -496,20 +933,24 @@ int launch_pair(const VelAccSrc &src, int interp, int Wc, const double *grid, in
                 int *status, int *fail_stage, cudaStream_t stream) {
   const size_t smem = (size_t)2 * Wc * sizeof(double);
   const int blocks = (B + 1) / 2;
-  scan_pair_kernel<FAST, CFLAGS, TB_SCAN_PAIR_MINB><<<blocks, 32, smem, stream>>>(src, interp, Wc, grid, grid_shared, B, G,
-                                                                                 sd_start, sd_end, sd_end_hi, K, sd, u,
-                                                                                 status, fail_stage);
+  static const char *env = getenv("TB_SCAN_PAIR");
+  if (env && env[0] == '1')   // the divergent half-warp experiment (slower; kept for A/B)
+    scan_pair_kernel<FAST, CFLAGS, TB_SCAN_PAIR_MINB><<<blocks, 32, smem, stream>>>(src, interp, Wc, grid, grid_shared, B, G,
+                                                                                   sd_start, sd_end, sd_end_hi, K, sd, u,
+                                                                                   status, fail_stage);
+  else
+    scan_lock_kernel<FAST, CFLAGS, TB_SCAN_PAIR_MINB><<<blocks, 32, smem, stream>>>(src, interp, Wc, grid, grid_shared, B, G,
+                                                                                   sd_start, sd_end, sd_end_hi, K, sd, u,
+                                                                                   status, fail_stage);
   return check_launch("tb_scan_velacc");
 }
 
 }  // namespace
 
 bool scan_velacc_pair_supported(int dof, int interp, int nseg, int flags) {
-  // Measured (profiles/r02_pair_divergent_experiment_ncu.txt): 1.67 ms vs 1.32 ms of the one-warp-per-path kernel at 4096
-  // paths — redux.sync / vote.sync deliver ONE result per warp, so half-warp masks serialise every collective (plus a
-  // convergence branch each: `branch_resolving` 26 % of the stall samples).  Opt-in for A/B: TB_SCAN_PAIR=1.
-  static const char *env = getenv("TB_SCAN_PAIR");
-  if (!(env && env[0] == '1')) return false;
+  // Measured: both forms are slower than the one-warp-per-path kernel (file header); opt-in for A/B only.
+  static const char *env = getenv("TB_SCAN_PAIR");   // 2: lockstep build, 1: divergent half-warp build, else off
+  if (!(env && (env[0] == '1' || env[0] == '2'))) return false;
   const int mode = flags & ~TB_SCAN_FAST_LOWER;
   if (mode != 0 && mode != TB_SCAN_BACKWARD_ONLY && mode != TB_SCAN_FORWARD_ONLY) return false;  // TOPPRAsd rules etc.
   const int Wc = (nseg * dof * 6 + nseg + 1 + 1) & ~1;
