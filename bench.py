@@ -486,7 +486,17 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's copy kernels share the SMs with the scan (whose resident one-warp CTAs hold the whole register file): a
+        # high-priority NCCL stream lets their CTAs in as scan CTAs retire, so the gathers progress under the compute
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        if opts is not None:
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     # pinned host buffers (e2e) and device-resident inputs (value)
     h_way = torch.as_tensor(way).pin_memory()
     h_vlim = torch.as_tensor(vlim).pin_memory()

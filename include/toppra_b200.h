@@ -75,6 +75,7 @@ extern "C" {
 #define TB_BC_NOT_A_KNOT 0
 #define TB_BC_FIRST_DERIV 1   /* 'clamped' = first derivative 0 */
 #define TB_BC_SECOND_DERIV 2  /* 'natural' = second derivative 0 */
+#define TB_BC_PERIODIC 3      /* both ends; the caller guarantees wp[.][0] == wp[.][n-1] (scipy checks allclose 1e-15) */
 
 int tb_version(void);
 const char *tb_last_error(void);
@@ -85,7 +86,7 @@ int tb_limits(int *max_rows, int *max_knots);
 /* Record stride in doubles for R static rows: 3R+2 rounded up to even. */
 int tb_record_doubles(int R);
 
-/* K0 — not-a-knot / clamped / natural cubic spline through wp[B][n][dof] at ss.
+/* K0 — not-a-knot / clamped / natural / periodic cubic spline through wp[B][n][dof] at ss.
  *   ss: [n] (ss_shared=1) or [B][n]; bc0/bc1: boundary values [B][dof] or NULL (= zeros);
  *   ppoly out: [B][4][n-1][dof] (scipy PPoly.c layout per path, highest power first);
  *   workspace: device scratch of tb_spline_fit_workspace_doubles(B, n, dof) doubles (0 for short splines:

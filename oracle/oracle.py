@@ -83,7 +83,7 @@ def cubic_spline_fit(x, y, bc_type="not-a-knot"):
         y = y[:, None]
     y, yp = _d(y)
     n, dof = y.shape
-    kinds = {"not-a-knot": 0, "clamped": 1, "natural": 2}
+    kinds = {"not-a-knot": 0, "clamped": 1, "natural": 2, "periodic": 3}
     if isinstance(bc_type, str):
         k0 = k1 = kinds[bc_type]
         v0 = v1 = np.zeros(dof)

@@ -439,6 +439,36 @@ def other_paths_case():
     print("other paths: statuses", [int(data[t + "_status"]) for t in ("sp_auto", "sp_yd", "poly")])
 
 
+def periodic_case():
+    """scipy CubicSpline(bc_type='periodic') (reference SplineInterpolator passes bc_type through, interpolator.py:419):
+    closed curves, y[0] == y[-1]; n = 2, 3 (special cases), 4, 5, 9, 20 (the workspace path of the fit kernel)."""
+    rng = np.random.RandomState(11)
+    fits = {}
+    for n in (2, 3, 4, 5, 9, 20):
+        x = np.sort(rng.rand(n)) * 3.0
+        x[0] = 0.0
+        y = rng.randn(n, 3)
+        y[-1] = y[0]
+        cs = CubicSpline(x, y, bc_type="periodic")
+        se = np.linspace(x[0], x[-1], 41)
+        csd = cs.derivative()          # the reference evaluates derivatives like this (interpolator.py:419-430)
+        fits.update({"x_%d" % n: x, "y_%d" % n: y, "c_%d" % n: cs.c, "s_%d" % n: se, "q_%d" % n: cs(se),
+                     "qd_%d" % n: csd(se), "qdd_%d" % n: csd.derivative()(se)})
+    # a closed 7-DOF path through the reference's TOPPRA (the solver evaluates q', q'' at the gridpoints through scipy's
+    # periodic extrapolation: the last gridpoint wraps to the first)
+    way = rng.randn(6, 7)
+    way[-1] = way[0]
+    ssp = np.linspace(0, 1, 6)
+    vl, al = 10 + rng.rand(7) * 20, 10 + rng.rand(7) * 2
+    vlim, alim = np.vstack((-vl, vl)).T, np.vstack((-al, al)).T
+    grid = np.linspace(0, 1, 100)
+    o, _ = solve_ref(ssp, way, vlim, alim, grid, bc_type="periodic")
+    fits.update(solve_ss=ssp, solve_way=way, solve_vlim=vlim, solve_alim=alim, solve_grid=grid, solve_K=o["K"],
+                solve_sd=o["sd"], solve_sdd=o["sdd"], solve_status=np.int32(o["status"]))
+    np.savez_compressed(os.path.join(HERE, "spline_periodic.npz"), **fits)
+    print("spline_periodic: written")
+
+
 def frows_batch_case():
     """Rows f1-f3 + ubound for BATCHES (VERDICT r1 "next" #8, #9): 16 paths each through the reference's own
     propose_gridpoints (ragged grids), compute_reachable_sets, TOPPRAsd, ParametrizeSpline, and a user-defined
@@ -569,8 +599,11 @@ if __name__ == "__main__":
         other_paths_case()
     elif len(sys.argv) > 1 and sys.argv[1] == "frows_batch":
         frows_batch_case()
+    elif len(sys.argv) > 1 and sys.argv[1] == "periodic":
+        periodic_case()
     else:
         main()
         joint_torque_case()
         other_paths_case()
         frows_batch_case()
+        periodic_case()

@@ -182,3 +182,37 @@ def test_ubound_from_a_constraint_bit_exact(ta, golden):
         rows = w.rows()
         assert np.array_equal(rows["low"][:, 0], np.maximum(-1e8, -g["ub_ulim"][b] * (1.0 + grid)))
     assert tight > 50       # the u-bound is active on many stages: the test exercises it
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 9, 20])
+def test_periodic_spline_bit_exact(ta, golden, n):
+    """bc_type='periodic' (scipy CubicSpline; reference SplineInterpolator forwards bc_type, interpolator.py:419): the
+    condensed cyclic system of scipy _cubic.py restated in K0; coefficients and evaluations equal scipy's bit for bit."""
+    g = golden("spline_periodic")
+    x, y = g["x_%d" % n], g["y_%d" % n]
+    path = ta.SplineInterpolator(x, y, bc_type="periodic")
+    assert np.array_equal(path.cspl.c, g["c_%d" % n])
+    for order, key in ((0, "q"), (1, "qd"), (2, "qdd")):
+        assert np.array_equal(path(g["s_%d" % n], order), g["%s_%d" % (key, n)]), (n, order)
+    if n > 2:
+        bad = y.copy()
+        bad[-1, 0] += 1e-3
+        with pytest.raises(ValueError, match="identical"):
+            ta.SplineInterpolator(x, bad, bc_type="periodic")
+    with pytest.raises(ValueError, match="both"):
+        ta.SplineInterpolator(x, y, bc_type=("periodic", "natural"))
+
+
+def test_periodic_path_solve(ta, golden):
+    """TOPPRA on a closed path.  The kernels evaluate the LAST gridpoint on the last spline segment, the reference (through
+    scipy's periodic extrapolation) on the first one at ds = 0: the same number up to rounding, so the parameterisation
+    agrees to 1e-9 instead of bit for bit (documented in DESIGN.md)."""
+    g = golden("spline_periodic")
+    path = ta.SplineInterpolator(g["solve_ss"], g["solve_way"], bc_type="periodic")
+    cons = [ta.constraint.JointVelocityConstraint(g["solve_vlim"]), ta.constraint.JointAccelerationConstraint(g["solve_alim"])]
+    inst = ta.algorithm.TOPPRA(cons, path, gridpoints=g["solve_grid"], solver_wrapper="seidel")
+    sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+    assert g["solve_status"] == 0
+    np.testing.assert_allclose(K, g["solve_K"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sd, g["solve_sd"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sdd, g["solve_sdd"], rtol=1e-8, atol=1e-8)

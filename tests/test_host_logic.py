@@ -75,8 +75,9 @@ def test_parse_bc_errors():
     from toppra_b200 import engine
     import torch
     if not torch.cuda.is_available():
-        with pytest.raises(NotImplementedError):
-            engine.parse_bc("periodic", 1, 2, "cpu")
+        assert engine.parse_bc("periodic", 1, 2, "cpu") == ((3, None), (3, None))
+        with pytest.raises(ValueError, match="both"):      # scipy: 'periodic' is defined for both curve ends
+            engine.parse_bc(("periodic", "natural"), 1, 2, "cpu")
         with pytest.raises(ValueError):
             engine.parse_bc("bogus", 1, 2, "cpu")
 

@@ -80,13 +80,14 @@ __global__ void spline_fit_kernel(const double *__restrict__ ss, const int ss_sh
   const double *y = wp + p * n * dof;
   double *c = ppoly + p * 4 * (n - 1) * dof;
   const int nseg = n - 1;
-  // scratch: thread-local arrays for short splines, caller workspace [B*dof][6][n] for long ones
+  // scratch: thread-local arrays for short splines, caller workspace [B*dof][7][n] for long ones
   double l_dx[LOCAL_KNOTS], l_slope[LOCAL_KNOTS], l_s[LOCAL_KNOTS], l_dl[LOCAL_KNOTS], l_dd[LOCAL_KNOTS],
-      l_du[LOCAL_KNOTS];
-  double *dx = l_dx, *slope = l_slope, *s = l_s, *dl = l_dl, *dd = l_dd, *du = l_du;
+      l_du[LOCAL_KNOTS], l_t2[LOCAL_KNOTS];
+  double *dx = l_dx, *slope = l_slope, *s = l_s, *dl = l_dl, *dd = l_dd, *du = l_du, *t2 = l_t2;
   if (n > LOCAL_KNOTS) {
-    double *w = workspace + idx * 6 * (long)n;
+    double *w = workspace + idx * 7 * (long)n;
     dx = w; slope = w + n; s = w + 2 * (long)n; dl = w + 3 * (long)n; dd = w + 4 * (long)n; du = w + 5 * (long)n;
+    t2 = w + 6 * (long)n;
   }
   for (int i = 0; i < nseg; ++i) {
     dx[i] = x[i + 1] - x[i];
@@ -94,11 +95,43 @@ __global__ void spline_fit_kernel(const double *__restrict__ ss, const int ss_sh
   }
   int k0 = bc0_kind, k1 = bc1_kind;
   double v0 = bc0 ? bc0[p * dof + k] : 0.0, v1 = bc1 ? bc1[p * dof + k] : 0.0;
-  if (n == 2) {  // _cubic.py: not-a-knot on 2 points -> straight line
-    if (k0 == TB_BC_NOT_A_KNOT) { k0 = TB_BC_FIRST_DERIV; v0 = slope[0]; }
-    if (k1 == TB_BC_NOT_A_KNOT) { k1 = TB_BC_FIRST_DERIV; v1 = slope[0]; }
+  if (n == 2) {  // _cubic.py: not-a-knot / periodic on 2 points -> first derivative = slope (0 for periodic data)
+    if (k0 == TB_BC_NOT_A_KNOT || k0 == TB_BC_PERIODIC) { k0 = TB_BC_FIRST_DERIV; v0 = slope[0]; }
+    if (k1 == TB_BC_NOT_A_KNOT || k1 == TB_BC_PERIODIC) { k1 = TB_BC_FIRST_DERIV; v1 = slope[0]; }
   }
-  if (n == 3 && k0 == TB_BC_NOT_A_KNOT && k1 == TB_BC_NOT_A_KNOT) {
+  if (k0 == TB_BC_PERIODIC && n == 3) {
+    // _cubic.py: t = (slope / dx).sum(0) / (1 / dx).sum(0); every knot gets this derivative
+    const double t = (slope[0] / dx[0] + slope[1] / dx[1]) / (1.0 / dx[0] + 1.0 / dx[1]);
+    s[0] = t; s[1] = t; s[2] = t;
+  } else if (k0 == TB_BC_PERIODIC) {
+    // _cubic.py, periodic branch: s[n-1] = s[0]; the cyclic (n-1) x (n-1) system is condensed to a tridiagonal
+    // (n-2) x (n-2) matrix Ac solved for two right-hand sides (b1, and b2 = minus the removed column), then
+    // s[n-2] = (b[-1] - a_m1_0 s1[0] - a_m1_m2 s1[-1]) / (a_m1_m1 + a_m1_0 s2[0] + a_m1_m2 s2[-1]), s[:n-2] = s1 + s[n-2] s2
+    const int m = n - 2;
+    const double a_m1_0 = dx[n - 3], a_m1_m2 = dx[n - 2], a_m1_m1 = 2 * (dx[n - 2] + dx[n - 3]);
+    const double b_last = 3 * (dx[n - 2] * slope[n - 3] + dx[n - 3] * slope[n - 2]);
+    for (int pass = 0; pass < 2; ++pass) {   // dgtsv overwrites the matrix: it is built once per right-hand side
+      dd[0] = 2 * (dx[n - 2] + dx[0]);
+      for (int j = 1; j < m; ++j) dd[j] = 2 * (dx[j - 1] + dx[j]);
+      du[0] = dx[n - 2];
+      for (int j = 1; j < m - 1; ++j) du[j] = dx[j - 1];
+      for (int j = 0; j < m - 1; ++j) dl[j] = dx[j + 1];
+      if (pass == 0) {
+        s[0] = 3 * (dx[0] * slope[n - 2] + dx[n - 2] * slope[0]);
+        for (int i = 1; i < m; ++i) s[i] = 3 * (dx[i] * slope[i - 1] + dx[i - 1] * slope[i]);
+        dgtsv_like(m, dl, dd, du, s);
+      } else {
+        for (int i = 0; i < m; ++i) t2[i] = 0.0;
+        t2[0] = -dx[0];
+        t2[m - 1] = -dx[n - 4];
+        dgtsv_like(m, dl, dd, du, t2);
+      }
+    }
+    const double s_m1 = ((b_last - a_m1_0 * s[0]) - a_m1_m2 * s[m - 1]) / ((a_m1_m1 + a_m1_0 * t2[0]) + a_m1_m2 * t2[m - 1]);
+    for (int i = 0; i < m; ++i) s[i] = s[i] + s_m1 * t2[i];
+    s[n - 2] = s_m1;
+    s[n - 1] = s[0];
+  } else if (n == 3 && k0 == TB_BC_NOT_A_KNOT && k1 == TB_BC_NOT_A_KNOT) {
     // parabola through the 3 points: dense 3x3 system, LU with partial pivoting (scipy.linalg.solve)
     double A[3][3] = {{1, 1, 0}, {dx[1], 2 * (dx[0] + dx[1]), dx[0]}, {0, 1, 1}};
     double b[3] = {2 * slope[0], 3 * (dx[0] * slope[1] + dx[1] * slope[0]), 2 * slope[1]};
@@ -164,7 +197,7 @@ __global__ void spline_fit_kernel(const double *__restrict__ ss, const int ss_sh
 extern "C" int tb_spline_fit_workspace_doubles(int B, int n, int dof) {
   if (B <= 0 || n < 2 || dof <= 0) return TB_ERR_ARG;
   if (n <= tb::LOCAL_KNOTS) return 0;
-  const long need = (long)B * dof * 6 * n;
+  const long need = (long)B * dof * 7 * n;
   return need > 0x7fffffffL ? TB_ERR_UNSUPPORTED : (int)need;
 }
 
@@ -178,7 +211,11 @@ extern "C" int tb_spline_fit(const double *ss, int ss_shared, const double *wp, 
     set_error("tb_spline_fit: n=%d > %d needs a workspace of tb_spline_fit_workspace_doubles() doubles", n, LOCAL_KNOTS);
     return TB_ERR_ARG;
   }
-  if (bc0_kind < 0 || bc0_kind > 2 || bc1_kind < 0 || bc1_kind > 2) { set_error("tb_spline_fit: bad bc kind"); return TB_ERR_ARG; }
+  if (bc0_kind < 0 || bc0_kind > 3 || bc1_kind < 0 || bc1_kind > 3) { set_error("tb_spline_fit: bad bc kind"); return TB_ERR_ARG; }
+  if ((bc0_kind == TB_BC_PERIODIC) != (bc1_kind == TB_BC_PERIODIC)) {
+    set_error("tb_spline_fit: 'periodic' is defined for both ends of the curve");   // scipy _validate_bc
+    return TB_ERR_ARG;
+  }
   const long total = (long)B * dof;
   const int threads = 128;
   const long blocks = (total + threads - 1) / threads;

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 
-BC_KINDS = {"not-a-knot": 0, "clamped": 1, "natural": 2}
+BC_KINDS = {"not-a-knot": 0, "clamped": 1, "natural": 2, "periodic": 3}
 
 
 def torch_mod():
@@ -45,15 +45,16 @@ def default_device(device=None):
 def parse_bc(bc_type, B, dof, device):
     """scipy CubicSpline bc_type -> ((kind0, val0), (kind1, val1)) with device value tensors [B, dof] or None."""
     if isinstance(bc_type, str):
-        if bc_type == "periodic":
-            raise NotImplementedError("toppra_b200: bc_type='periodic' is not supported on device")
         if bc_type not in BC_KINDS:
             raise ValueError("bc_type=%r not understood" % (bc_type,))
         return (BC_KINDS[bc_type], None), (BC_KINDS[bc_type], None)
     out = []
     for side in bc_type:
         if isinstance(side, str):
-            if side not in BC_KINDS or side == "periodic":
+            if side == "periodic":   # scipy _validate_bc
+                raise ValueError("'periodic' `bc_type` is defined for both curve ends and cannot be used with other "
+                                 "boundary conditions.")
+            if side not in BC_KINDS:
                 raise ValueError("bc_type=%r not understood" % (side,))
             out.append((BC_KINDS[side], None))
         else:

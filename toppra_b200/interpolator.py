@@ -91,7 +91,7 @@ class BatchSplineInterpolator(object):
     ss_waypoints: (n,) shared by all paths, or (B, n)
     waypoints: (B, n, dof)
     bc_type: as scipy.interpolate.CubicSpline ('not-a-knot', 'clamped', 'natural', or a pair of
-        (order, value) tuples with order in {1, 2}); 'periodic' is not supported.
+        (order, value) tuples with order in {1, 2}), or 'periodic' (closed curves: waypoints[:, 0] == waypoints[:, -1]).
     device: torch device (default: current CUDA device)
 
     `ss_waypoints` / `waypoints` may be numpy arrays (copied H2D here) or CUDA tensors (used in place)."""
@@ -122,6 +122,17 @@ class BatchSplineInterpolator(object):
                 raise ValueError("`ss_waypoints` must be a strictly increasing sequence.")
         self.bc_type = bc_type
         bc = engine.parse_bc(bc_type, self.B, self._dof, self.device)
+        if validate and isinstance(bc_type, str) and bc_type == "periodic":
+            # scipy _validate_bc: np.allclose(y[0], y[-1], rtol=1e-15, atol=1e-15)
+            wp_host = engine.host_view(waypoints)
+            if wp_host is not None:
+                closed = bool(np.allclose(wp_host[:, 0], wp_host[:, -1], rtol=1e-15, atol=1e-15))
+            else:
+                first, last = self.d_wp[:, 0], self.d_wp[:, -1]
+                closed = bool(((first - last).abs() <= 1e-15 + 1e-15 * last.abs()).all())
+            if not closed:
+                raise ValueError("The first and last `y` point along axis 0 must be identical (within machine precision) "
+                                 "when bc_type='periodic'.")
         self.d_ppoly = engine.spline_fit(self.d_ss, self.d_wp, bc)
 
     @classmethod
@@ -169,6 +180,12 @@ class BatchSplineInterpolator(object):
         """s: CUDA tensor [G] (shared) or [B, G] -> CUDA tensor [B, G, dof]."""
         if order not in (0, 1, 2):
             raise ValueError("Invalid order %s" % order)
+        if isinstance(self.bc_type, str) and self.bc_type == "periodic":
+            # scipy sets extrapolate='periodic' for these splines: PPoly.__call__ first maps
+            # x -> xmin + (x - xmin) % (xmax - xmin), so the end of the interval evaluates at its start
+            torch = engine.torch_mod()
+            x0, x1 = self.d_ss[..., :1], self.d_ss[..., -1:]
+            s = (x0 + torch.remainder(s - x0, x1 - x0)).contiguous()
         return engine.ppoly_eval(self.d_ppoly, self.d_ss, s, order)
 
     def __call__(self, path_positions, order=0):
