@@ -52,21 +52,29 @@ def build_records(ctx, constraints, out=None):
     else:
         records, _ = engine.alloc_records(ctx.B, ctx.G, R, ctx.device, ubound=ubound)
     kinds = [type(c) for c in constraints]
-    if (len(constraints) == 2 and JointVelocityConstraint in kinds and JointAccelerationConstraint in kinds):
-        # headline case: one fused K1 launch writes the velocity bound and the acceleration rows
-        vel = constraints[kinds.index(JointVelocityConstraint)]
-        acc = constraints[kinds.index(JointAccelerationConstraint)]
+    fused_pair = ()
+    if kinds.count(JointVelocityConstraint) == 1 and kinds.count(JointAccelerationConstraint) == 1:
+        # one K1 launch writes the velocity bound AND the acceleration rows (wherever the two sit in the list); it also
+        # initialises the bound slots and the padding, so no separate init pass is needed
+        iv, ia = kinds.index(JointVelocityConstraint), kinds.index(JointAccelerationConstraint)
+        vel, acc = constraints[iv], constraints[ia]
         for c in (vel, acc):
             if ctx.bpath.dof != c.get_dof():
                 raise ValueError("Wrong dimension: constraint dof ({:d}) not equal to path dof ({:d})".format(
                     c.get_dof(), ctx.bpath.dof))
+        if ubound:
+            engine.init_bounds(records, R)     # the u-bound pair is not written by K1
         engine.coeff_velacc(ctx.bpath.d_ppoly, ctx.bpath.d_ss, ctx.d_grid, ctx.limits(vel.device_limits(ctx.device)),
-                            ctx.limits(acc.device_limits(ctx.device)), acc.interpolation, records, R, 0, 1)
-        return records, R
-    engine.init_bounds(records, R)
+                            ctx.limits(acc.device_limits(ctx.device)), acc.interpolation, records, R, int(sum(rows[:ia])), 1)
+        fused_pair = (iv, ia)
+        if len(constraints) == 2:
+            return records, R
+    else:
+        engine.init_bounds(records, R)
     row0 = 0
-    for c, n in zip(constraints, rows):
-        c.append_records(ctx, records, R, row0)
+    for i, (c, n) in enumerate(zip(constraints, rows)):
+        if i not in fused_pair:
+            c.append_records(ctx, records, R, row0)
         row0 += n
     return records, R
 

@@ -364,14 +364,27 @@ second_order_rows_tiled_kernel(const double *__restrict__ ppoly, const double *_
   const double *cpp = ppoly + p * 4 * nseg * dof;
   const double *gp = grid + (grid_shared ? 0 : p * G);
   const double *tl = taulim + (lim_shared ? 0 : p * dof * 2);
-  // shared: per evaluated gridpoint and joint: qd, qdd, sin q, cos q, then a, b, c; the gridpoints themselves
+  // shared: per evaluated gridpoint and joint: qd, qdd, sin q, cos q, then a, b, c; the gridpoints; the row decode table
   const int ne = (SO_TILE + 1) * dof;
   double *s_qd = so_sm, *s_qdd = so_sm + ne, *s_sq = so_sm + 2 * ne, *s_cq = so_sm + 3 * ne;
   double *s_a = so_sm + 4 * ne, *s_b = so_sm + 5 * ne, *s_c = so_sm + 6 * ne, *s_g = so_sm + 7 * ne;
+  const int nrows = (interp ? 4 : 2) * dof;
+  const int per_rec = 3 * nrows;
+  unsigned *s_tab = reinterpret_cast<unsigned *>(s_g + SO_TILE + 2);
   const double nan_d = __longlong_as_double(0x7ff8000000000000LL);
+  // row decode table, once per CTA (the only integer divisions of the kernel): entry r of a record's 3 * nrows values ->
+  // part (a | b | c), row j, joint k, negated copy, lifted block
+  for (int r = tid; r < per_rec; r += SO_THREADS) {
+    const int part = r / nrows, j = r - part * nrows;
+    const int blk = j / dof, k = j - blk * dof;
+    s_tab[r] = (unsigned)part | ((unsigned)k << 2) | ((unsigned)(blk & 1) << 8) | ((unsigned)(blk >> 1) << 9) | ((unsigned)j << 10);
+  }
   for (int t = tid; t < nev; t += SO_THREADS) s_g[t] = gp[gi0 + t];
+  // e -> (gridpoint t, joint k) without a division: t = floor(e / dof) by a multiply-high with ceil(2^32 / dof) (exact
+  // for e < 2^16)
+  const unsigned inv_dof = (unsigned)((0x100000000ULL + (unsigned)dof - 1u) / (unsigned)dof);
   for (int e = tid; e < nev * dof; e += SO_THREADS) {
-    const int t = e / dof, k = e - t * dof;
+    const int t = (int)__umulhi((unsigned)e, inv_dof), k = e - t * dof;
     const double s = gp[gi0 + t];
     const int seg = find_interval(x, nseg, s);
     const double q = seg < 0 ? nan_d : ppoly_eval1(cpp, nseg, dof, seg, k, s - x[seg], 0);
@@ -384,7 +397,7 @@ second_order_rows_tiled_kernel(const double *__restrict__ ppoly, const double *_
   }
   __syncthreads();
   for (int e = tid; e < nev * dof; e += SO_THREADS) {
-    const int t = e / dof, k = e - t * dof;
+    const int t = (int)__umulhi((unsigned)e, inv_dof), k = e - t * dof;
     const double *qd = s_qd + t * dof, *qdd = s_qdd + t * dof, *sq = s_sq + t * dof, *cq = s_cq + t * dof;
     double av, bv, cv;
     if (MODEL == TB_INVDYN_COUPLED_COSINE) {
@@ -410,29 +423,32 @@ second_order_rows_tiled_kernel(const double *__restrict__ ppoly, const double *_
     s_a[e] = av; s_b[e] = bv; s_c[e] = cv;
   }
   __syncthreads();
-  // phase 3: record entries in record order.  Row j of the constraint: blk = j / dof (bit 0: negated copy, bit 1: the
-  // block evaluated at s_{i+1} and lifted), k = j % dof.
-  const int nrows = (interp ? 4 : 2) * dof;
-  const int per_rec = 3 * nrows;
+  // phase 3: a warp takes one record at a time, its lanes the record's 3 * nrows values in record order (runs of nrows
+  // consecutive doubles per part).  Row j of the constraint: bit 0 of blk = negated copy, bit 1 = the block evaluated at
+  // s_{i+1} and lifted.
   double *rec0 = records + (p * G + gi0) * (long)W;
-  for (int e = tid; e < npts * per_rec; e += SO_THREADS) {
-    const int gl = e / per_rec, r = e - gl * per_rec;
-    const int part = r / nrows, j = r - part * nrows;
-    const int blk = j / dof, k = j - blk * dof;
-    const bool neg = (blk & 1) != 0, second = (blk >> 1) != 0;
-    const int gi = gi0 + gl;
-    const bool lift = second && gi < N;                   // the last gridpoint duplicates itself (linear_constraint.py:141-153)
-    const int src = (lift ? gl + 1 : gl) * dof + k;
-    double v;
-    if (part == 0) {
-      v = lift ? s_a[src] + (2 * (s_g[gl + 1] - s_g[gl])) * s_b[src] : s_a[src];
-      v = neg ? -v : v;
-    } else if (part == 1) {
-      v = neg ? -s_b[src] : s_b[src];
-    } else {
-      v = neg ? (-s_c[src] - (-tl[k * 2 + 0])) : (s_c[src] - tl[k * 2 + 1]);   // F c - g, g = [tau_max; -tau_min]
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int gl = warp; gl < npts; gl += SO_THREADS / 32) {
+    const bool last = (gi0 + gl) >= N;                  // the last gridpoint duplicates itself (linear_constraint.py:141-153)
+    const double two_delta = last ? 0.0 : 2 * (s_g[gl + 1] - s_g[gl]);
+    double *rec = rec0 + (long)gl * W;
+    for (int r = lane; r < per_rec; r += 32) {
+      const unsigned code = s_tab[r];
+      const int part = code & 3, k = (code >> 2) & 63, j = code >> 10;
+      const bool neg = (code >> 8) & 1, second = (code >> 9) & 1;
+      const bool lift = second && !last;
+      const int src = (lift ? gl + 1 : gl) * dof + k;
+      double v;
+      if (part == 0) {
+        v = lift ? s_a[src] + two_delta * s_b[src] : s_a[src];
+        v = neg ? -v : v;
+      } else if (part == 1) {
+        v = neg ? -s_b[src] : s_b[src];
+      } else {
+        v = neg ? (-s_c[src] - (-tl[k * 2 + 0])) : (s_c[src] - tl[k * 2 + 1]);   // F c - g, g = [tau_max; -tau_min]
+      }
+      rec[part * R_total + row0 + j] = v;
     }
-    rec0[(long)gl * W + part * R_total + row0 + j] = v;
   }
 }
 
@@ -573,7 +589,7 @@ extern "C" int tb_coeff_second_order(int model, const double *params, int nparam
   const int tiles = (G + SO_TILE - 1) / SO_TILE;
   const long blocks = (long)B * tiles;
   if (blocks > 0x7fffffffL) { set_error("tb_coeff_second_order: B * ceil(G / 32) = %ld CTAs exceed the grid limit", blocks); return TB_ERR_UNSUPPORTED; }
-  const size_t smem = (size_t)(7 * (SO_TILE + 1) * dof + SO_TILE + 1) * sizeof(double);
+  const size_t smem = (size_t)(7 * (SO_TILE + 1) * dof + SO_TILE + 2) * sizeof(double) + (size_t)3 * nrows * sizeof(unsigned);
   if (model == TB_INVDYN_COUPLED_COSINE)
     second_order_rows_tiled_kernel<TB_INVDYN_COUPLED_COSINE><<<(unsigned)blocks, SO_THREADS, smem, st>>>(
         ppoly, breaks, breaks_shared, nseg, dof, grid, grid_shared, G, params, taulim, lim_shared, friction, interp,
