@@ -998,6 +998,10 @@ constexpr int SCAN_WARPS = TB_SCAN_WARPS;  // 1: a finished path frees its slot 
 #define TB_SCAN_WARPS_PER_SM 32  // register budget of the dense build: 65536 / (32 * 32) -> 64 registers/thread (measured: 32 > 28 > 24)
 #endif
 
+#ifndef TB_SCAN_RPL2_WARPS_PER_SM
+#define TB_SCAN_RPL2_WARPS_PER_SM 20  // measured on cfg 3 (16384 x 500, nC = 50): free choice (150 regs) 19.0 ms, 16: 16.2, 20 (96 regs): 15.5, 24 (80 regs): 15.7
+#endif
+
 #ifndef TB_SCAN_FUSED_WARPS_PER_SM
 #define TB_SCAN_FUSED_WARPS_PER_SM 28  // 72 registers: 28 x 148 = 4144 resident paths still cover the 4096-path batch in one wave (measured r02: 1.317 vs 1.339 ms at 32)
 #endif
@@ -1028,6 +1032,17 @@ int launch_scan(const double *records, int W, int R, const double *grid, int gri
     else if (mode == TB_SCAN_FORWARD_ONLY)
       kern = fast ? scan_kernel<RPL, SCAN_WARPS, MINB, true, TB_SCAN_FORWARD_ONLY>
                   : scan_kernel<RPL, SCAN_WARPS, MINB, false, TB_SCAN_FORWARD_ONLY>;
+  }
+  if constexpr (RPL == 2) {
+    // nC in (32, 64] (BASELINE cfg 3: 50 rows).  Left alone the compiler takes 150 registers: 13 resident warps per SM
+    // and issue slots 54 % busy (profiles/r02_ncu_cfg3.txt).  Capped builds trade a few spills for residency.
+    static const char *rpl2_env = getenv("TB_SCAN_RPL2_OCC");
+    const int occ2 = rpl2_env ? atoi(rpl2_env) : TB_SCAN_RPL2_WARPS_PER_SM;
+    if (!fast && !counters) {
+      if (occ2 == 16) kern = scan_kernel<RPL, SCAN_WARPS, 16, false>;
+      else if (occ2 == 20) kern = scan_kernel<RPL, SCAN_WARPS, 20, false>;
+      else if (occ2 == 24) kern = scan_kernel<RPL, SCAN_WARPS, 24, false>;
+    }
   }
   if (flags & TB_SCAN_UBOUND)  // records with a u-bound pair: the generic build (exact mode only)
     kern = scan_kernel<RPL, SCAN_WARPS, 1, false, -1, false, true>;
