@@ -77,19 +77,20 @@ class SecondOrderConstraint(LinearConstraint):
 
     # ---- reference-style host evaluation (user callbacks) ------------------------------------------------
     def _colloc_host(self, path, gridpoints):
-        v_zero = np.zeros(path.dof)
-        p_vec = path(gridpoints)
-        ps_vec = path(gridpoints, 1)
-        pss_vec = path(gridpoints, 2)
-        F_vec = np.array(list(map(self.constraint_F, p_vec)))
-        g_vec = np.array(list(map(self.constraint_g, p_vec)))
-        c_vec = np.array([self.inv_dyn(_p, v_zero, v_zero) for _p in p_vec])
-        a_vec = np.array([self.inv_dyn(_p, v_zero, _ps) for _p, _ps in zip(p_vec, ps_vec)]) - c_vec
-        b_vec = np.array([self.inv_dyn(_p, _ps, pss_) for _p, _ps, pss_ in zip(p_vec, ps_vec, pss_vec)]) - c_vec
+        """Host evaluation with the user's numpy callbacks, gridpoint by gridpoint: w(q, 0, 0), w(q, 0, q'), w(q, q', q'')
+        and F(q), g(q) — what the reference does 3 (N + 1) times per path (linear_second_order.py:142-165)."""
+        q, qs, qss = (np.atleast_2d(path(gridpoints, order)) for order in (0, 1, 2))
+        still = np.zeros(path.dof)
+        n = len(gridpoints)
+        rest = [np.asarray(self.inv_dyn(q[i], still, still), dtype=np.float64) for i in range(n)]
+        a = np.stack([np.asarray(self.inv_dyn(q[i], still, qs[i]), dtype=np.float64) - rest[i] for i in range(n)])
+        b = np.stack([np.asarray(self.inv_dyn(q[i], qs[i], qss[i]), dtype=np.float64) - rest[i] for i in range(n)])
+        c = np.stack(rest)
         if self.custom_term is not None:
-            for i, _ in enumerate(gridpoints):
-                c_vec[i] = c_vec[i] + self.custom_term(path, gridpoints[i])
-        return a_vec, b_vec, c_vec, F_vec, g_vec
+            c = c + np.stack([np.asarray(self.custom_term(path, s), dtype=np.float64) for s in gridpoints])
+        F = np.stack([np.asarray(self.constraint_F(qi)) for qi in q])
+        g = np.stack([np.asarray(self.constraint_g(qi)) for qi in q])
+        return a, b, c, F, g
 
     def compute_constraint_params(self, path, gridpoints):
         if path.dof != self.dof:
