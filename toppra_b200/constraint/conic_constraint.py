@@ -15,15 +15,14 @@ from .. import engine
 class ConicConstraint(Constraint):
     """Base class for all canonical conic constraints (reference conic_constraint.py:6-44)."""
 
-    def __init__(self):
-        self.constraint_type = ConstraintType.CanonicalConic
-        self.discretization_type = DiscretizationType.Collocation
-        self.n_extra_vars = 0
-        self.dof = -1
-        self._format_string = ""
+    constraint_type = ConstraintType.CanonicalConic      # class-level defaults; instances override dof / scheme
+    discretization_type = DiscretizationType.Collocation
+    n_extra_vars = 0
+    dof = -1
+    _format_string = ""
 
     def compute_constraint_params(self, path, gridpoints):
-        raise NotImplementedError
+        raise NotImplementedError("%s does not say how its rows and ellipsoids are computed" % type(self).__name__)
 
 
 class RobustLinearConstraint(ConicConstraint):
@@ -36,15 +35,17 @@ class RobustLinearConstraint(ConicConstraint):
     discretization_scheme: Collocation (default, as in the reference) or Interpolation"""
 
     def __init__(self, cnst, ellipsoid_axes_lengths, discretization_scheme=DiscretizationType.Collocation):
-        super(RobustLinearConstraint, self).__init__()
-        self.dof = cnst.get_dof()
-        assert cnst.get_constraint_type() == ConstraintType.CanonicalLinear
-        self.set_discretization_type(discretization_scheme)
-        if np.any(np.r_[ellipsoid_axes_lengths] < 0):
+        axes = np.asarray(ellipsoid_axes_lengths, dtype=np.float64).reshape(-1)
+        if axes.shape != (3,):
+            raise ValueError("ellipsoid_axes_lengths must hold the three axes (ru, rx, rc); got {:}".format(
+                ellipsoid_axes_lengths))
+        if (axes < 0).any():
             raise ValueError("Perturbation must be non-negative. Input {:}".format(ellipsoid_axes_lengths))
-        self.base_constraint = cnst
-        self.ellipsoid_axes_lengths = ellipsoid_axes_lengths
-        self._format_string += "    Robust constraint generated from a canonical linear constraint\n"
+        assert cnst.get_constraint_type() == ConstraintType.CanonicalLinear, "only linear constraints can be robustified"
+        self.base_constraint, self.ellipsoid_axes_lengths = cnst, ellipsoid_axes_lengths
+        self.dof = cnst.get_dof()
+        self.set_discretization_type(discretization_scheme)
+        self._format_string = "    Robust constraint generated from a canonical linear constraint\n"
 
     def compute_constraint_params(self, path, gridpoints):
         """(a, b, c, P, ubound, xbound): rows a = F a0, b = F b0, c = F c0 - g of the base constraint
