@@ -431,7 +431,8 @@ def extra_configs(args, torch, dist, ta, dev, world, rank, peak):
         d_way, d_ss = torch.as_tensor(way).to(dev), torch.as_tensor(ss).to(dev)
         d_vlim, d_alim = torch.as_tensor(vlim).to(dev), torch.as_tensor(alim).to(dev)
         d_grid = torch.as_tensor(np.linspace(0, 1, G)).to(dev)
-        solver = ShardedSolver(Btot, G, dev, nchunks=8, gather=True)
+        # chunks of >= 32768 paths where the shard allows it (the scan's large-batch forward pass starts at 24576 paths)
+        solver = ShardedSolver(Btot, G, dev, nchunks=max(2, min(8, shard // 32768)), gather=True)
 
         ms, full = timed(lambda: solver.solve(d_ss, d_way, d_grid, d_vlim, d_alim), 3, 2)
         ms = allmax(ms)

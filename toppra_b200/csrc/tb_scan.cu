@@ -1092,6 +1092,21 @@ int launch_scan_velacc(const VelAccSrc &src, int W, int R, const double *grid, i
   // resident warps per SM of the 64-register build (2^20 paths: 290.7 vs 308.8 ms).  TB_SCAN_FUSED_OCC=28|32 overrides.
   static const char *occ_env = getenv("TB_SCAN_FUSED_OCC");
   const int occ = occ_env ? atoi(occ_env) : ((long)B <= 148L * TB_SCAN_FUSED_WARPS_PER_SM ? TB_SCAN_FUSED_WARPS_PER_SM : 32);
+  const int mode = flags & (TB_SCAN_BACKWARD_ONLY | TB_SCAN_SD_FORWARD | TB_SCAN_SD_SLOW | TB_SCAN_FORWARD_ONLY);
+  if ((mode == 0 || mode == TB_SCAN_FORWARD_ONLY) && !counters && !glen && forward_threads_supported(src.dof, B)) {
+    // large batches (issue-bound): the forward pass runs with one thread per path (tb_scan_fwd.cu) after a backward-only
+    // launch of this kernel
+    if (mode == 0) {
+      const int bflags = (flags & TB_SCAN_FAST_LOWER) | TB_SCAN_BACKWARD_ONLY;
+      const int rc = (occ == 28)
+          ? launch_scan_velacc_occ<28>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, bflags, K, nullptr,
+                                       nullptr, status, fail_stage, nullptr, nullptr, stream)
+          : launch_scan_velacc_occ<32>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, bflags, K, nullptr,
+                                       nullptr, status, fail_stage, nullptr, nullptr, stream);
+      if (rc) return rc;
+    }
+    return launch_forward_threads(src, R == 4 * src.dof, grid, grid_shared, B, G, sd_start, K, sd, u, status, fail_stage, stream);
+  }
   if (occ == 28)
     return launch_scan_velacc_occ<28>(src, W, R, grid, grid_shared, B, G, sd_start, sd_end, sd_end_hi, flags, K, sd, u,
                                       status, fail_stage, counters, glen, stream);

@@ -58,4 +58,14 @@ int launch_scan_velacc_pair(const VelAccSrc &src, int interp, const double *grid
                             double *sd, double *u, int *status, int *fail_stage, cudaStream_t stream);
 bool scan_velacc_pair_supported(int dof, int interp, int nseg, int flags);
 
+// forward pass with one thread per path (tb_scan_fwd.cu), for large batches: reads K / status / fail_stage of a
+// TB_SCAN_BACKWARD_ONLY launch
+#ifndef TB_SCAN_FWD_THREADS_MIN_DEFAULT
+#define TB_SCAN_FWD_THREADS_MIN_DEFAULT 24576  // measured (B200, 7-DOF, 200 gridpoints): 16384 paths 4.78 vs 4.65 ms (warp form wins), 32768: 8.19 vs 8.98 ms, 65536: 16.1 vs 17.7, 2^20 in 131072-path chunks: 263 vs 289 ms
+#endif
+bool forward_threads_supported(int dof, int B);
+int launch_forward_threads(const VelAccSrc &src, int interp, const double *grid, int grid_shared, int B, int G,
+                           const double *sd_start, const double *K, double *sd, double *u, int *status, int *fail_stage,
+                           cudaStream_t stream);
+
 }  // namespace tb
