@@ -558,7 +558,7 @@ def run_b200(args):
         return out
 
     # the e2e step builds constraint objects from host limit arrays each step (their H2D copy is part of the step)
-    e2e_mode = {"sync": False, "k": 0}
+    e2e_mode = {"sync": False, "k": 0, "ready": {}}
     from toppra_b200.batch import copy_stream
     d2h_stream = copy_stream(dev)
     nccl_side = torch.cuda.Stream(dev) if world > 1 else None
@@ -575,7 +575,16 @@ def run_b200(args):
         # K leaves on a copy stream while the forward pass runs; sync=False: pipelined caller, the pinned buffers are
         # valid at inst.host_ready (all copies are still inside the timed region); sync=True: host waits every step
         e2e_mode["k"] += 1
-        inst.solve_to_host(0.0, 0.0, pinned=h_sets[e2e_mode["k"] & 1], sync=e2e_mode["sync"])
+        k = e2e_mode["k"]
+        if not e2e_mode["sync"]:
+            # double buffering as a real pipelined caller does it: result buffer k & 1 is reused only after the solve that
+            # filled it last (step k - 2) has landed on the host — at most two steps are in flight
+            prev = e2e_mode["ready"].get(k & 1)
+            if prev is not None:
+                prev.synchronize()
+        inst.solve_to_host(0.0, 0.0, pinned=h_sets[k & 1], sync=e2e_mode["sync"])
+        if not e2e_mode["sync"]:
+            e2e_mode["ready"][k & 1] = inst.host_ready
         if world > 1:
             # NCCL: gather the result velocities; on a side stream, so the next step's kernels overlap the collective
             sd = inst.last_result.sd
@@ -749,7 +758,8 @@ def run_b200(args):
                 "host_sync_every_step": {"value": total_paths * args.steps / (ms_e2e_sync * 1e-3), "unit": UNIT,
                                          "ms_per_step": ms_e2e_sync / args.steps},
                 "api": "BatchSplineInterpolator + BatchTOPPRA.solve_to_host(sync=False) with pinned HOST inputs and "
-                       "outputs: a pipelined caller (two result buffers); all D2H copies run on the package's copy "
+                       "outputs: a pipelined caller with two result buffers (at most two steps in flight: a buffer is "
+                       "reused once its previous solve has landed); all D2H copies run on the package's copy "
                        "stream and overlap the next step's kernels; ONE event pair around the K steps, every copy of "
                        "every step (and the L2 flushes) inside it; host_sync_every_step = the same call with sync=True "
                        "(host waits for each step's results; per-step event pairs)"

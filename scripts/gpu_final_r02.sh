@@ -15,6 +15,10 @@ echo "== ncu full: fused scan (full kernel), then the split kernels of the e2e a
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'scan_kernel' -s 3 -c 1 \
    -o gpurun_out/prof_r02_scan -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --configs none > gpurun_out/ncu_full_scan.log 2>&1
 tail -1 gpurun_out/ncu_full_scan.log
+echo "== ncu full: large-batch forward pass (one thread per path) and the backward-only warp kernel at 32768 paths"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'forward_threads|scan_kernel' -s 4 -c 2 \
+   -o gpurun_out/prof_r02_fwd -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --batch 32768 > gpurun_out/ncu_full_fwd.log 2>&1
+tail -1 gpurun_out/ncu_full_fwd.log
 echo "== ncu full: cfg 3 kernels"
 B=4096 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'second_order|coeff_velacc|scan_kernel' -s 3 -c 3 \
    -o gpurun_out/prof_r02_cfg3 -f python scripts/cfg3_probe.py > gpurun_out/ncu_full_cfg3.log 2>&1

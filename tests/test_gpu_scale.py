@@ -225,6 +225,33 @@ def test_skip_ahead_is_bit_identical_on_many_paths(ta):
     assert cnt[:, 2].mean() < 2.5 * (G - 1)
 
 
+@pytest.mark.parametrize("interp", [True, False])
+def test_large_batch_forward_threads_bit_identical(ta, interp):
+    """Batches of >= 24576 paths run the forward pass with one thread per path (csrc/tb_scan_fwd.cu) after a backward-only
+    launch of the warp kernel: same bits as the sequential oracle.  An odd batch size, velocity-limited paths (the retry
+    rule), inadmissible and non-zero boundary speeds, both discretisation schemes; the split launch of solve_to_host too."""
+    from oracle import oracle as orc
+    B, G = 24576 + 37, 48
+    ss, way, vlim, alim = make_batch_fast(B, seed=9090)
+    vlim[:3000] *= 0.03
+    s0 = np.where(np.arange(B) % 13 == 0, 30.0, np.where(np.arange(B) % 5 == 0, 0.05, 0.0))
+    s1 = np.where(np.arange(B) % 7 == 0, 0.04, 0.0)
+    grid = np.linspace(0, 1, G)
+    path = ta.BatchSplineInterpolator(ss, way)
+    inst = ta.BatchTOPPRA([ta.constraint.JointVelocityConstraint(vlim),
+                           ta.constraint.JointAccelerationConstraint(alim, discretization_scheme=1 if interp else 0)], path, grid)
+    assert inst.fused
+    h = inst.compute_parameterization(s0, s1).to_host()
+    o = orc.solve_velacc_batch(path.d_ppoly.cpu().numpy(), np.tile(ss, (B, 1)), grid, vlim, alim, interp, sd_start=s0,
+                               sd_end=s1, nthreads=min(16, os.cpu_count() or 1))
+    assert np.array_equal(h["status"], o["status"]) and (h["status"] == 3).sum() >= B // 13 and (h["status"] == 0).sum() > B // 2
+    assert np.array_equal(h["K"], o["K"], equal_nan=True) and np.array_equal(h["sd"], o["sd"], equal_nan=True)
+    assert np.array_equal(h["sdd"], o["u"], equal_nan=True)
+    host = inst.solve_to_host(s0, s1)                 # backward-only launch, then the forward pass alone
+    for key, ref in (("K", o["K"]), ("sd", o["sd"]), ("sdd", o["u"]), ("status", o["status"])):
+        assert np.array_equal(host[key].numpy(), ref, equal_nan=True), key
+
+
 @pytest.mark.parametrize("name", ["deg6", "deg20", "scaled14"])
 def test_seidel_shortcuts_on_stress_rows_vs_reference_golden(ta, golden, name):
     """The K2 shortcuts (csrc/tb_scan.cu, A: jump to the last visited row, B: skip the first warm-start re-solve) must
