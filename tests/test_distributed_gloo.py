@@ -108,3 +108,38 @@ def test_solve_sharded_more_ranks_than_paths():
     ret = mp.get_context("spawn").Manager().dict()
     mp.spawn(_solve_worker_tiny, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _sharded_solver_worker(rank, world, port, ret):
+    """distributed.ShardedSolver (BASELINE cfg 5's entry point: equal shards, chunked solve, per-chunk all-gather into global
+    path order) on the CPU engine double over gloo: every rank must hold the reference's golden batch in path order."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_engine
+    cpu_engine.install_plain()
+    from toppra_b200.distributed import ShardedSolver, shard_range
+    g = np.load(os.path.join(here, "golden", "cfg2_seeds1000.npz"))
+    B, G = 8, len(g["grid"])
+    lo, hi = shard_range(B, rank, world)
+    solver = ShardedSolver(B, G, "cpu", nchunks=3, gather=True)          # 4 paths per rank in chunks of 1, 1, 2
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a))              # noqa: E731
+    full = solver.solve(t(g["ss"]), t(g["way"][lo:hi]), t(g["grid"]), t(g["vlim"][lo:hi]), t(g["alim"][lo:hi]))
+    ok = all(np.array_equal(full[k].numpy(), g[k][:B]) for k in ("K", "sd", "sdd"))
+    ok = ok and np.array_equal(full["status"].numpy(), g["status"][:B]) and solver.nchunks == 3
+    local = ShardedSolver(B, G, "cpu", nchunks=2, gather=False).solve(t(g["ss"]), t(g["way"][lo:hi]), t(g["grid"]),
+                                                                        t(g["vlim"][lo:hi]), t(g["alim"][lo:hi]))
+    ok = ok and np.array_equal(local["sd"].numpy(), g["sd"][lo:hi])
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_solver_world2_gloo_on_cpu_double():
+    world = 2
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_sharded_solver_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -96,7 +96,9 @@ class ShardedSolver(object):
         self.out = dict(K=torch.empty((n_out, G, 2), **f64), sd=torch.empty((n_out, G), **f64),
                         sdd=torch.empty((n_out, G - 1), **f64),
                         status=torch.empty((n_out,), dtype=torch.int32, device=device))
-        self.side = torch.cuda.Stream(device) if self.gather else None
+        # the overlap needs CUDA streams; on a CPU device (the gloo tests of the host logic) the gathers run inline
+        self.cuda = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device) if (self.gather and self.cuda) else None
         cmax = max(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))
         # NCCL writes [world][chunk] blocks; two scratch sets so that chunk c+1's gather never waits for chunk c's unpack
         self.scratch = [dict((k, torch.empty((self.world * cmax,) + tuple(v.shape[1:]), dtype=v.dtype, device=device))
@@ -111,7 +113,8 @@ class ShardedSolver(object):
         from .batch import BatchTOPPRA
         from .constraint import JointAccelerationConstraint, JointVelocityConstraint
         from .interpolator import BatchSplineInterpolator
-        main = torch.cuda.current_stream(self.dev)
+        main = torch.cuda.current_stream(self.dev) if self.cuda else None
+        record_events = record_events and self.cuda
         for c in range(self.nchunks):
             lo, hi = self.bounds[c], self.bounds[c + 1]
             n = hi - lo
@@ -131,18 +134,27 @@ class ShardedSolver(object):
                 for k, t in local.items():
                     self.out[k][lo:hi].copy_(t, non_blocking=True)
                 continue
-            done = torch.cuda.Event()
-            done.record(main)
             scr = self.scratch[c & 1]
-            with torch.cuda.stream(self.side):
-                self.side.wait_event(done)
-                for k, t in local.items():
-                    t.record_stream(self.side)
-                    buf = scr[k][: self.world * n]
-                    dist.all_gather_into_tensor(buf, t, group=self.group)
-                    # [world][n] blocks -> global path order: rank r's chunk sits at r * shard + lo
-                    view = self.out[k].view((self.world, self.shard) + tuple(self.out[k].shape[1:]))
-                    view[:, lo:hi].copy_(buf.view((self.world, n) + tuple(t.shape[1:])), non_blocking=True)
-        if self.gather:
+            if self.cuda:
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(done)
+                    for t in local.values():
+                        t.record_stream(self.side)
+                    self._gather_chunk(local, scr, lo, hi)
+            else:
+                self._gather_chunk(local, scr, lo, hi)
+        if self.gather and self.cuda:
             main.wait_stream(self.side)
         return self.out
+
+    def _gather_chunk(self, local, scr, lo, hi):
+        """All-gather one chunk of every result tensor and unpack the [world][n] blocks into global path order (rank r's
+        chunk sits at r * shard + lo)."""
+        n = hi - lo
+        for k, t in local.items():
+            buf = scr[k][: self.world * n]
+            self.dist.all_gather_into_tensor(buf, t.contiguous(), group=self.group)
+            view = self.out[k].view((self.world, self.shard) + tuple(self.out[k].shape[1:]))
+            view[:, lo:hi].copy_(buf.view((self.world, n) + tuple(t.shape[1:])), non_blocking=True)
