@@ -61,3 +61,138 @@ def test_lp_shims_random(ref):
         assert r0 == r1
         if r0:
             assert val0 == val1 and np.array_equal(np.asarray(var0), var1) and np.array_equal(np.asarray(act0), act1)
+
+
+def test_periodic_splines_random_vs_scipy():
+    """bc_type='periodic': the restated condensed cyclic system against scipy on random closed curves (n = 2..40,
+    non-uniform knots); the reference's SplineInterpolator is a thin wrapper over exactly this scipy call."""
+    from scipy.interpolate import CubicSpline
+    rng = np.random.RandomState(5)
+    for trial in range(60):
+        n = [2, 3, 4, 5][trial] if trial < 4 else rng.randint(4, 41)
+        x = np.cumsum(0.05 + rng.rand(n))
+        y = rng.randn(n, 1 + trial % 4)
+        y[-1] = y[0]
+        assert np.array_equal(orc.cubic_spline_fit(x, y, "periodic"), CubicSpline(x, y, bc_type="periodic").c), (trial, n)
+
+
+def test_ubound_random_vs_reference(ref):
+    """`ubound` of a constraint (seidelWrapper.__init__, pyx:512-515): random u-intervals and x-bounds through the reference's
+    own TOPPRA (parameterisation, feasible and reachable sets) against the oracle's stateful wrapper with the same rows."""
+    ta, algo, constraint = ref
+    ss = np.linspace(0, 1, 5)
+    rng = np.random.RandomState(17)
+
+    class UB(constraint.LinearConstraint):
+        def __init__(self, acc, ub, xb):
+            super(UB, self).__init__()
+            self.acc, self.ub, self.xb = acc, ub, xb
+            self.discretization_type = acc.discretization_type
+            self.identical = True
+
+        def get_dof(self):
+            return self.acc.get_dof()
+
+        def compute_constraint_params(self, path, gridpoints, *a):
+            pa, pb, pc, F, g, _, _ = self.acc.compute_constraint_params(path, gridpoints)
+            return pa, pb, pc, F, g, self.ub, self.xb
+
+    for seed in range(6000, 6012):
+        G = 40 + (seed % 4) * 25
+        grid = np.linspace(0, 1, G)
+        way, vlim, alim = make_path(seed)
+        width = 0.05 + 1.5 * rng.rand()
+        ub = np.stack((-width * (0.5 + rng.rand(G)), width * (0.5 + rng.rand(G))), axis=1)
+        xb = np.stack((np.zeros(G), 20.0 + 80 * rng.rand(G)), axis=1)
+        path = ta.SplineInterpolator(ss, way)
+        mk = lambda: [constraint.JointVelocityConstraint(vlim),  # noqa: E731
+                      UB(constraint.JointAccelerationConstraint(alim), ub, xb)]
+        inst = algo.TOPPRA(mk(), path, gridpoints=grid, solver_wrapper="seidel")
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        X = algo.TOPPRA(mk(), path, gridpoints=grid, solver_wrapper="seidel").compute_feasible_sets()
+        L = algo.TOPPRA(mk(), path, gridpoints=grid, solver_wrapper="seidel").compute_reachable_sets(0.0, 0.2)
+        # the same rows for the oracle: acceleration rows from its own K1 restatement, velocity bound intersected with xb
+        c = orc.cubic_spline_fit(ss, way)
+        lin = orc.solve_velacc(c, ss, grid, vlim, alim, True, 0, 0, want_rows=True)
+        xbo = np.stack((np.maximum(lin["xbound"][:, 0], xb[:, 0]), np.minimum(lin["xbound"][:, 1], xb[:, 1])), axis=1)
+        o = orc.solve_rows(lin["rows"], xbo, grid, 0.0, 0.0, ubound=ub)
+        assert np.array_equal(o["K"], K, equal_nan=True), seed
+        if sd is None:
+            assert o["status"] == 3
+        else:
+            assert np.array_equal(o["sd"], sd, equal_nan=True) and np.array_equal(o["u"], sdd, equal_nan=True), seed
+        w = orc.Wrapper(grid, lin["rows"], xbo, ub)
+        assert np.array_equal(w.compute_feasible_sets(), X, equal_nan=True), seed
+        # reachable sets: the reference runs the feasible-set pass first on the SAME wrapper object (stateful warm start)
+        Lo = np.zeros((G, 2))
+        Lo[0] = [0.0, 0.2 ** 2]
+        deltas = np.diff(grid)
+        for i in range(G - 1):
+            dq = deltas[i - 1]
+            obj = np.array([-2 * dq, -1.0])
+            o1 = w.solve_stagewise_optim(i, None, obj, Lo[i, 0], Lo[i, 1], X[i + 1, 0], X[i + 1, 1])
+            o0 = w.solve_stagewise_optim(i, None, -obj, Lo[i, 0], Lo[i, 1], X[i + 1, 0], X[i + 1, 1])
+            Lo[i + 1] = [o0[1] + 2 * dq * o0[0], o1[1] + 2 * dq * o1[0]]
+            if Lo[i + 1, 0] < 0:
+                Lo[i + 1, 0] = 0
+            if np.isnan(Lo[i + 1]).any():
+                break
+        assert np.array_equal(Lo, L, equal_nan=True), seed
+
+
+def test_propose_gridpoints_and_spline_time_stamps_random_vs_reference(ref, monkeypatch):
+    """The engine double's restatements (tests/cpu_engine.py) of propose_gridpoints and of ParametrizeSpline's time-stamp
+    recurrence against the reference on random paths / velocity profiles with stalls and dropped knots."""
+    ta, algo, constraint = ref
+    import torch
+    import toppra.interpolator as interp
+    from toppra.parametrizer import ParametrizeSpline
+    import cpu_engine
+    ss = np.linspace(0, 1, 5)
+    rng = np.random.RandomState(23)
+    for seed in range(7000, 7008):
+        way, _, _ = make_path(seed, dof=3 + seed % 4)
+        path = ta.SplineInterpolator(ss, way)
+        kw = dict(max_err_threshold=10 ** rng.uniform(-4, -1.5), max_seg_length=rng.uniform(0.04, 0.4),
+                  min_nb_points=int(rng.randint(5, 150)))
+        want = np.asarray(interp.propose_gridpoints(path, **kw))
+        c = orc.cubic_spline_fit(ss, way)
+        grid, glen, st = cpu_engine.propose_gridpoints(torch.from_numpy(c[None]), torch.from_numpy(ss), max_points=4096, **kw)
+        assert int(st[0]) == 0 and int(glen[0]) == len(want) and np.array_equal(grid[0, :len(want)].numpy(), want), seed
+        G = 80
+        g = np.linspace(0, 1, G)
+        vel = np.abs(rng.randn(G)) + 0.05
+        vel[rng.randint(1, G - 1, size=3)] = 0.0              # stalled gridpoints: the 5 s rule
+        vel[10:12] = 1e9                                      # increments below 1e-8: dropped knots
+        traj = ParametrizeSpline(path, g, vel)
+        t, s, nk = cpu_engine.spline_time_stamps(torch.from_numpy(vel[None]), torch.from_numpy(g))
+        n = int(nk[0])
+        assert n == len(traj.ss_waypoints) and np.array_equal(t[0, :n].numpy(), traj.ss_waypoints), seed
+
+
+def test_toppra_sd_random_vs_reference(ref, monkeypatch):
+    """TOPPRAsd (desired_duration_algorithm.py:42-191) through the package's host code on the engine double (two
+    TOPPRAsd-rule scans + the duration bisection) against the reference class on random paths and desired durations."""
+    ta_ref, algo, constraint = ref
+    import cpu_engine
+    ta = cpu_engine.install(monkeypatch)
+    ss = np.linspace(0, 1, 5)
+    rng = np.random.RandomState(31)
+    for seed in range(8000, 8010):
+        G = 50 + (seed % 3) * 30
+        grid = np.linspace(0, 1, G)
+        way, vlim, alim = make_path(seed, vel_active=(seed % 4 == 0))
+        inst = algo.TOPPRAsd([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
+                             ta_ref.SplineInterpolator(ss, way), gridpoints=grid, solver_wrapper="seidel")
+        fast = algo.TOPPRA([constraint.JointVelocityConstraint(vlim), constraint.JointAccelerationConstraint(alim)],
+                           ta_ref.SplineInterpolator(ss, way), gridpoints=grid, solver_wrapper="seidel")
+        _, sd_f, _ = fast.compute_parameterization(0, 0)
+        t_fast = np.sum(2 * np.diff(grid) / (sd_f[1:] + sd_f[:-1]))
+        want_t = t_fast * rng.choice([0.6, 1.3, 2.2, 5.0])
+        inst.set_desired_duration(want_t)
+        sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+        mine = ta.algorithm.TOPPRAsd([ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)],
+                                     ta.SplineInterpolator(ss, way), gridpoints=grid, solver_wrapper="seidel")
+        mine.set_desired_duration(want_t)
+        sdd2, sd2, _, K2 = mine.compute_parameterization(0, 0, return_data=True)
+        assert np.array_equal(K2, K) and np.array_equal(sd2, sd) and np.array_equal(sdd2, sdd), seed
