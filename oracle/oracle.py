@@ -310,3 +310,20 @@ def solve_rows_robust(rows, xbound, grid, conic_row0, conic_rows, ellipsoid, sd_
                                      ctypes.c_double(sd_end), K.ctypes.data_as(_dp), sd.ctypes.data_as(_dp),
                                      u.ctypes.data_as(_dp), ctypes.byref(nev))
     return dict(K=K, sd=sd, u=u, status=int(st), n_eval=nev.value)
+
+
+def feasible_rows_robust(rows, xbound, grid, conic_row0, conic_rows, ellipsoid):
+    """Feasible sets X [G, 2] of the robust problem (every stage on its own, x_next boxed to +-1e4) —
+    oracle/toppra_robust_oracle.c orc_feasible_rows_robust; NaN marks an infeasible stage."""
+    rows, rp = _d(rows)
+    grid, gp = _d(grid)
+    G, _, R = rows.shape
+    xp = None
+    if xbound is not None:
+        xbound, xp = _d(xbound)
+    ell, ep = _d(ellipsoid)
+    X = np.zeros((G, 2))
+    fn = lib().orc_feasible_rows_robust
+    fn.restype = None
+    fn(rp, xp, gp, G, R, int(conic_row0), int(conic_rows), ep, X.ctypes.data_as(_dp))
+    return X

@@ -215,3 +215,38 @@ int orc_solve_rows_robust(const double *rows, const double *xbound, const double
   free(a); free(b); free(c); free(conic);
   return status;
 }
+
+/* Feasible sets of the robust problem: every stage on its own, x and x_next boxed to [-1e4, 1e4] (the reference's
+ * compute_feasible_sets, reachability_algorithm.py:131-164, passes x_next bounds of +-CVXPY_MAXX = 1e4, constants.py:40).
+ * rows: [G][3][R], xbound [G][2], X out [G][2] (NaN = stage infeasible).  No hint: both searches start from the box. */
+#define CVXPY_MAXX 10000.0
+void orc_feasible_rows_robust(const double *rows, const double *xbound, const double *grid, int G, int R, int conic0,
+                              int conicn, const double *ell, double *X) {
+  int N = G - 1, nC = R + 2;
+  double *a = (double *)malloc(sizeof(double) * nC), *b = (double *)malloc(sizeof(double) * nC);
+  double *c = (double *)malloc(sizeof(double) * nC);
+  unsigned char *conic = (unsigned char *)calloc(nC, 1);
+  for (int r = 0; r < R; ++r) conic[2 + r] = (r >= conic0 && r < conic0 + conicn);
+  stage_t st = {nC, a, b, c, conic, ell[0], ell[1], ell[2], 0};
+  for (int i = 0; i <= N; ++i) {
+    for (int r = 0; r < R; ++r) {
+      a[2 + r] = rows[((size_t)i * 3 + 0) * R + r]; b[2 + r] = rows[((size_t)i * 3 + 1) * R + r];
+      c[2 + r] = rows[((size_t)i * 3 + 2) * R + r];
+    }
+    double xlo_b = xbound ? xbound[i * 2] : VAR_MIN, xhi_b = xbound ? xbound[i * 2 + 1] : VAR_MAX;
+    double xl = fmax(-CVXPY_MAXX, xlo_b), xh = fmin(CVXPY_MAXX, fmin(ECOS_MAXX, xhi_b));
+    a[0] = 0.0; b[0] = 0.0; c[0] = -1.0;
+    a[1] = 0.0; b[1] = 0.0; c[1] = -1.0;
+    if (i < N) {
+      double delta = grid[i + 1] - grid[i];
+      a[0] = -2 * delta; b[0] = -1.0; c[0] = -CVXPY_MAXX;
+      a[1] = 2 * delta; b[1] = 1.0; c[1] = -CVXPY_MAXX;
+    }
+    double x0 = NAN, x1 = NAN;
+    if (!extreme_x(&st, -1, xl, xh, &x0, NAN)) x0 = NAN;
+    if (!extreme_x(&st, +1, xl, xh, &x1, NAN)) x1 = NAN;
+    if (x0 < 0) x0 = 0;
+    X[2 * i] = x0; X[2 * i + 1] = x1;
+  }
+  free(a); free(b); free(c); free(conic);
+}

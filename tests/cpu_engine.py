@@ -332,10 +332,15 @@ def _scan_sd(records, R, grid, sd_start, sd_end, slow):
 
 def scan_robust(records, R, conic_row0, conic_rows, ellipsoid, grid, sd_start=None, sd_end=None, backward_only=False,
                 counters=False, feasible_sets=False):
-    if backward_only or feasible_sets:
-        raise NotImplementedError("cpu_engine test double: robust controllable / feasible sets are gpu-only here")
     B, G, W = records.shape
     gr = _np(grid)
+    if feasible_sets:
+        X = np.empty((B, G, 2))
+        for b in range(B):
+            rows, xb = _rows_of(records, R, b)
+            X[b] = orc.feasible_rows_robust(rows, xb, _per_path(gr, b), conic_row0, conic_rows, ellipsoid)
+        return dict(K=torch.from_numpy(X), status=torch.zeros(B, dtype=torch.int32),
+                    fail_stage=torch.full((B,), -1, dtype=torch.int32))
     K, sd, u = np.zeros((B, G, 2)), np.full((B, G), np.nan), np.full((B, max(G - 1, 1)), np.nan)
     status = np.zeros(B, dtype=np.int32)
     for b in range(B):
@@ -343,8 +348,13 @@ def scan_robust(records, R, conic_row0, conic_rows, ellipsoid, grid, sd_start=No
         o = orc.solve_rows_robust(rows, xb, _per_path(gr, b), conic_row0, conic_rows, ellipsoid, _scalar(sd_start, b),
                                   _scalar(sd_end, b))
         K[b], status[b] = o["K"], o["status"]
-        if o["status"] == 0:
+        if backward_only:     # no start-velocity check: uncontrollable iff a stage of the backward pass was infeasible
+            status[b] = 3 if np.isnan(o["K"]).any() else 0
+        elif o["status"] == 0:
             sd[b], u[b, :G - 1] = o["sd"], o["u"]
+    if backward_only:
+        return dict(K=torch.from_numpy(K), status=torch.from_numpy(status),
+                    fail_stage=torch.full((B,), -1, dtype=torch.int32))
     out = dict(K=torch.from_numpy(K), sd=torch.from_numpy(sd), u=torch.from_numpy(u[:, :max(G - 1, 0)]),
                status=torch.from_numpy(status), fail_stage=torch.full((B,), -1, dtype=torch.int32))
     if counters:

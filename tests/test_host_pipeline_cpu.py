@@ -44,8 +44,8 @@ def _expand(fn):
 
 CASES = [(T, name, ident, kw) for name in REPLAYED for ident, kw in _expand(getattr(T, name))]
 CASES += [(P, name, "", {}) for name in ("test_ppoly_path_single", "test_scalar_and_low_degree_pieces", "test_batch_from_ppoly",
-                                             "test_simple_path_and_polynomial_path")]
-for _name in ("test_gpu_zero_ellipsoid_equals_lp_path", "test_gpu_robust_coefficients"):  # full robust solves only
+                                             "test_simple_path_and_polynomial_path", "test_univariate_spline_interpolator")]
+for _name in ("test_gpu_zero_ellipsoid_equals_lp_path", "test_gpu_robust_coefficients", "test_gpu_toppra_conic_api"):
     CASES += [(Rb, _name, ident, kw) for ident, kw in _expand(getattr(Rb, _name))]
 CASES += [(S, "test_shapes_rows_per_lane_and_tiny_grids", ident, kw)
           for ident, kw in _expand(S.test_shapes_rows_per_lane_and_tiny_grids)]

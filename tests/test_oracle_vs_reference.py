@@ -196,3 +196,34 @@ def test_toppra_sd_random_vs_reference(ref, monkeypatch):
         mine.set_desired_duration(want_t)
         sdd2, sd2, _, K2 = mine.compute_parameterization(0, 0, return_data=True)
         assert np.array_equal(K2, K) and np.array_equal(sd2, sd) and np.array_equal(sdd2, sdd), seed
+
+
+def test_univariate_spline_interpolator_vs_reference(ref, monkeypatch):
+    """UnivariateSplineInterpolator (interpolator.py:508-581): the package's PPoly conversion of the FITPACK fits against
+    the reference class — evaluations to rounding, the retimed solution to 1e-9 (the reference evaluates B-splines, this
+    package local cubics, so the LP rows differ in the last bits)."""
+    ta_ref, algo, constraint = ref
+    import cpu_engine
+    ta = cpu_engine.install(monkeypatch)
+    for seed in range(4):
+        rng = np.random.RandomState(900 + seed)
+        n = 25 + 10 * seed
+        ss = np.sort(np.r_[0.0, rng.uniform(0.05, 2.95, n - 2), 3.0])
+        way = np.stack([np.sin(ss), np.cos(1.7 * ss), 0.2 * ss ** 2 - ss, np.sin(0.5 * ss) * ss], axis=1)
+        way += 0.03 * rng.randn(n, 4)
+        theirs, mine = ta_ref.UnivariateSplineInterpolator(ss, way), ta.UnivariateSplineInterpolator(ss, way)
+        s = np.linspace(0, 3.0, 301)
+        for order in (0, 1, 2):
+            np.testing.assert_allclose(mine(s, order), theirs(s, order), rtol=1e-10, atol=1e-10)
+        assert mine.dof == theirs.dof == 4 and list(mine.path_interval) == list(theirs.path_interval)
+        vlim, alim = np.array([[-2.0, 2.0]] * 4), np.array([[-6.0, 5.0]] * 4)
+        grid = np.linspace(0, 3.0, 151)
+        out = []
+        for pkg, cons, path in ((algo, constraint, theirs), (ta.algorithm, ta.constraint, mine)):
+            inst = pkg.TOPPRA([cons.JointVelocityConstraint(vlim), cons.JointAccelerationConstraint(alim)], path,
+                              gridpoints=grid, solver_wrapper="seidel")
+            out.append(inst.compute_parameterization(0, 0, return_data=True))
+        (sdd, sd, _, K), (sdd2, sd2, _, K2) = out
+        np.testing.assert_allclose(K2, K, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(sd2, sd, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(sdd2, sdd, rtol=1e-6, atol=1e-7)

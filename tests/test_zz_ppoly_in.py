@@ -124,3 +124,38 @@ def test_simple_path_and_polynomial_path(ta, golden):
     np.testing.assert_allclose(p2.evaldd([0, 0.5, 1]), [[6, 8], [6, 23], [6, 38]])
     with pytest.raises(NotImplementedError):
         ta.PolynomialPath([1, 0, 0, 0, 1])
+
+
+def test_univariate_spline_interpolator(ta):
+    """Smoothing-spline path (reference interpolator.py:508-581) through "PPoly in": values against scipy's own evaluation
+    of the fitted splines (what the reference's __call__ returns) to rounding, the solve against the oracle fed with the
+    converted coefficients bit for bit."""
+    from scipy.interpolate import UnivariateSpline
+    from oracle import oracle as orc
+    rng = np.random.RandomState(5)
+    ss = np.linspace(0, 2.0, 40)
+    way = np.stack([np.sin(2 * ss), np.cos(ss) * ss, 0.3 * ss ** 2], axis=1) + 0.02 * rng.randn(40, 3)
+    path = ta.UnivariateSplineInterpolator(ss, way)
+    assert path.dof == 3 and list(path.path_interval) == [0.0, 2.0] and path.duration == 2.0
+    assert np.array_equal(path.waypoints[1], way)
+    s = np.linspace(0, 2.0, 257)
+    for k in range(3):
+        spl = UnivariateSpline(ss, way[:, k])
+        for order in (0, 1, 2):
+            expect = spl(s) if order == 0 else spl.derivative(order)(s)
+            np.testing.assert_allclose(path(s, order)[:, k], expect, rtol=1e-10, atol=1e-10)
+    assert path(0.7).shape == (3,) and path([0.1, 0.2], 1).shape == (2, 3)
+    vlim = np.array([[-3.0, 3.0]] * 3)
+    alim = np.array([[-8.0, 8.0]] * 3)
+    grid = np.linspace(0, 2.0, 201)
+    inst = ta.algorithm.TOPPRA([ta.constraint.JointVelocityConstraint(vlim), ta.constraint.JointAccelerationConstraint(alim)],
+                               path, gridpoints=grid, solver_wrapper="seidel")
+    sdd, sd, _, K = inst.compute_parameterization(0, 0, return_data=True)
+    bp = path.as_batch()
+    o = orc.solve_velacc(bp.d_ppoly[0].cpu().numpy(), bp.d_ss.cpu().numpy().reshape(-1), grid, vlim, alim, True, 0, 0)
+    assert o["status"] == 0 and inst.problem_data.return_code == ta.algorithm.ParameterizationReturnCode.Ok
+    assert np.array_equal(K, o["K"]) and np.array_equal(sd, o["sd"])
+    scalar = ta.UnivariateSplineInterpolator(ss, way[:, 0])
+    assert scalar.dof == 1 and scalar(s).shape == (257, 1)      # np.array(data).T in the reference: always 2-D
+    with pytest.raises(AssertionError):
+        ta.UnivariateSplineInterpolator(ss + 1.0, way)

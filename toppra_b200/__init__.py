@@ -8,7 +8,7 @@ import logging
 
 from . import constants, exceptions
 from .interpolator import (AbstractGeometricPath, BatchSplineInterpolator, PolynomialPath, PPolyPath,
-                           SplineInterpolator, propose_gridpoints)
+                           SplineInterpolator, UnivariateSplineInterpolator, propose_gridpoints)
 from .simplepath import SimplePath
 from .parametrizer import (BatchParametrizeConstAccel, BatchParametrizeSpline, ParametrizeConstAccel,
                            ParametrizeSpline)
@@ -16,11 +16,12 @@ from . import constraint
 from . import solverwrapper
 from . import algorithm
 from .batch import BatchResult, BatchTOPPRA, BatchTOPPRAsd, solve_batch
+from .utils import setup_logging
 
 __version__ = "0.1.0"
 
 logging.getLogger("toppra_b200").addHandler(logging.NullHandler())
 
-__all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "PPolyPath", "PolynomialPath", "SimplePath", "SplineInterpolator", "propose_gridpoints",
+__all__ = ["AbstractGeometricPath", "BatchSplineInterpolator", "PPolyPath", "PolynomialPath", "SimplePath", "SplineInterpolator", "UnivariateSplineInterpolator", "propose_gridpoints",
            "ParametrizeConstAccel", "ParametrizeSpline", "BatchParametrizeConstAccel", "BatchParametrizeSpline", "constraint", "solverwrapper", "algorithm", "BatchResult",
-           "BatchTOPPRA", "BatchTOPPRAsd", "solve_batch", "constants", "exceptions"]
+           "BatchTOPPRA", "BatchTOPPRAsd", "solve_batch", "constants", "exceptions", "setup_logging"]

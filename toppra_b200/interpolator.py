@@ -271,7 +271,7 @@ class SplineInterpolator(AbstractGeometricPath):
         if self._scalar_dof:
             out = out[..., 0]
         if scalar_in:
-            out = out[0]
+            out = np.asarray(out[0])   # scipy returns a 0-d ndarray for a scalar path at a scalar position
         return out
 
     @property
@@ -383,3 +383,38 @@ class PolynomialPath(PPolyPath):
     @property
     def duration(self):
         return self.s_end - self.s_start
+
+
+class UnivariateSplineInterpolator(PPolyPath):
+    """Waypoints smoothed by one cubic smoothing spline per joint — public surface of the reference's
+    `UnivariateSplineInterpolator` (interpolator.py:508-581).
+
+    The smoothing fit is scipy's `UnivariateSpline` (FITPACK), exactly the call the reference makes; it is one-off host
+    data preparation.  The fitted splines are cubic, so they reach the GPU as "PPoly in": each joint's B-spline is converted
+    to piecewise-cubic form, the joints' knot sets are merged (FITPACK places knots per joint), and solving / evaluation
+    run on the device like for any other path.  Values agree with the reference to rounding (the conversion re-expands
+    each piece about its left breakpoint)."""
+
+    def __init__(self, ss_waypoints, waypoints, device=None):
+        from scipy.interpolate import PPoly, UnivariateSpline
+        assert ss_waypoints[0] == 0, "First index must equals zero."
+        self.ss_waypoints = np.array(ss_waypoints, dtype=np.float64)
+        q = np.array(waypoints, dtype=np.float64)
+        self._q_waypoints = q
+        cols = q.reshape(-1, 1) if q.ndim == 1 else q
+        assert self.ss_waypoints.shape[0] == cols.shape[0]
+        self.uspl = [UnivariateSpline(self.ss_waypoints, cols[:, i]) for i in range(cols.shape[1])]
+        pieces = [PPoly.from_spline(spl._eval_args) for spl in self.uspl]
+        lo, hi = self.ss_waypoints[0], self.ss_waypoints[-1]
+        knots = np.unique(np.concatenate([p.x for p in pieces] + [[lo, hi]]))
+        knots = knots[(knots >= lo) & (knots <= hi)]
+        c = np.empty((4, len(knots) - 1, cols.shape[1]))
+        for k, p in enumerate(pieces):      # Taylor coefficients at each left breakpoint (PPoly evaluates the right piece)
+            left = knots[:-1]
+            c[0, :, k], c[1, :, k] = p(left, 3) / 6.0, p(left, 2) / 2.0
+            c[2, :, k], c[3, :, k] = p(left, 1), p(left)
+        super(UnivariateSplineInterpolator, self).__init__(c, knots, device=device)
+
+    @property
+    def waypoints(self):
+        return self.ss_waypoints, self._q_waypoints

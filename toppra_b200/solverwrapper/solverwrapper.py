@@ -89,8 +89,15 @@ class B200SolverWrapper(SolverWrapper):
     def params(self):
         """Per-constraint 7-tuples (a, b, c, F, g, ubound, xbound), like seidelWrapper.params."""
         if self._params is None:
-            self._params = [c.compute_constraint_params(self.path, self.path_discretization)
-                            for c in self.constraints]
+            self._params = []
+            for c in self.constraints:
+                cached = getattr(c, "_hp_cache", None)
+                if cached is not None and cached[0] is self.ctx:
+                    # the very tuple the stage records were built from (the reference stores the tuples of its
+                    # constructor, pyx:440-442; matters for a constraint whose parameters are not reproducible)
+                    self._params.append(cached[1])
+                else:
+                    self._params.append(c.compute_constraint_params(self.path, self.path_discretization))
         return self._params
 
     def rows(self):
