@@ -107,3 +107,22 @@ class ParameterizationAlgorithm(object):
                     trajectory.path_interval[1], self.path.path_interval[1])
         logger.info("Finish parametrization in %.3f secs", time.time() - began)
         return trajectory
+
+    def inspect(self, compute=True):
+        """Plot what the last solve left in `problem_data` over the gridpoint index: feasible sets X, controllable sets K
+        and the squared velocity profile (algorithm.py:196-213).  Needs matplotlib, which is imported here only."""
+        import matplotlib.pyplot as plt
+        data = self.problem_data
+        for sets, style, label in ((data.X, dict(c="green"), "Feasible sets"),
+                                   (data.K, dict(c="red", ls="--"), "Controllable sets")):
+            if sets is not None:
+                plt.plot(sets[:, 0], label=label, **style)
+                plt.plot(sets[:, 1], **style)
+        if data.sd_vec is not None:
+            plt.plot(np.square(data.sd_vec), label="Velocity profile")
+        plt.title("Path-position path-velocity plot")
+        plt.xlabel("Path position")
+        plt.ylabel("Path velocity square")
+        plt.legend()
+        plt.tight_layout()
+        plt.show()

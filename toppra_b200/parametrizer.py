@@ -77,6 +77,31 @@ class ParametrizeConstAccel(AbstractGeometricPath):
             out = out[..., 0]
         return out[0] if scalar else out
 
+    def plot_parametrization(self, show=False, n_sample=500):
+        """Four panels: s(t), sd(s), the retimed joint positions and the original path (parametrizer.py:131-158).  Needs
+        matplotlib, which is imported here only."""
+        import matplotlib.pyplot as plt
+        ts = np.linspace(self.path_interval[0], self.path_interval[1], n_sample)
+        seg = np.clip(np.searchsorted(self._ts, ts, side="right") - 1, 0, len(self._us) - 1)   # plot-only: s(t), sd(t)
+        dt = ts - self._ts[seg]
+        vs = self._velocities[seg] + self._us[seg] * dt
+        ss = self._ss[seg] + dt * (self._velocities[seg] + 0.5 * self._us[seg] * dt)
+        s_dense = np.linspace(self._ss[0], self._ss[-1], n_sample)
+        panels = (("path(time)", [(ts, ss, "-", "s(t)"), (self._ts, self._ss, "o", "input")]),
+                  ("velocity(path)", [(ss, vs, "-", "v(s)"), (self._ss, self._velocities, "o", "input")]),
+                  ("retimed path", [(ts, self(ts, 0), "-", None)]),
+                  ("original path", [(s_dense, self._path(s_dense), "-", None)]))
+        for k, (title, curves) in enumerate(panels):
+            plt.subplot(2, 2, k + 1)
+            for x, y, style, label in curves:
+                plt.plot(x, y, style, label=label)
+            if any(c[3] for c in curves):
+                plt.legend()
+            plt.title(title)
+        plt.tight_layout()
+        if show:
+            plt.show()
+
 
 class BatchParametrizeSpline(object):
     """ParametrizeSpline (reference parametrizer.py:161-196) for B paths on the GPU: the time-stamp recurrence with its
