@@ -9,6 +9,7 @@ from typing import Union
 import numpy as np
 
 from . import engine
+from .utils import deprecated
 
 logger = logging.getLogger(__name__)
 
@@ -383,6 +384,19 @@ class PolynomialPath(PPolyPath):
     @property
     def duration(self):
         return self.s_end - self.s_start
+
+    # deprecated accessors the reference still carries (interpolator.py:652-665)
+    @deprecated
+    def get_path_interval(self):
+        return self.path_interval
+
+    @deprecated
+    def get_duration(self):
+        return self.duration
+
+    @deprecated
+    def get_dof(self):
+        return self.dof
 
 
 class UnivariateSplineInterpolator(PPolyPath):
