@@ -117,3 +117,42 @@ def test_batch_input_validation_on_cpu(monkeypatch):
         inst.compute_parameterization(torch.zeros(B - 1, dtype=torch.float64), 0.0)
     with pytest.raises(ta.exceptions.BadInputVelocities):
         inst.compute_parameterization(-0.1, 0.0)
+
+
+def test_plot_helpers_draw_through_matplotlib(monkeypatch):
+    """`inspect()` (algorithm.py:196-213) and `plot_parametrization()` (parametrizer.py:131-158): matplotlib is imported
+    lazily; a recording stand-in shows that the panels are drawn from the solve's data."""
+    import sys
+    import types
+    calls = []
+
+    class Rec(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return Rec(name)
+
+        def __call__(self, *args, **kwargs):
+            calls.append((self.__name__, args))
+            return Rec("result")
+
+    plt = Rec("pyplot")
+    root = Rec("matplotlib")
+    root.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", root)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    ta = cpu_engine.install(monkeypatch)
+    path = ta.SplineInterpolator([0, 1, 2], [(0, 0), (1, 2), (2, 0)])
+    traj = ta.ParametrizeConstAccel(path, [0, 0.5, 1, 1.5, 2], [1, 2, 2, 1, 0])
+    traj.plot_parametrization(show=True)
+    names = [n for n, _ in calls]
+    assert names.count("subplot") == 4 and names.count("plot") == 6 and names[-1] == "show"
+    s_of_t = [a for n, a in calls if n == "plot"][0]
+    assert np.all(np.diff(s_of_t[1]) >= 0) and abs(s_of_t[1][-1] - 2.0) < 1e-12      # s(t) runs to the path end
+    lim = np.array([[-1.0, 1.0], [-1.0, 1.0]])
+    inst = ta.algorithm.TOPPRA([ta.constraint.JointVelocityConstraint(lim), ta.constraint.JointAccelerationConstraint(lim)], path)
+    inst.compute_feasible_sets()
+    inst.compute_trajectory(0, 0)
+    del calls[:]
+    inst.inspect()
+    assert [n for n, _ in calls].count("plot") == 5                                    # X (2), K (2), sd^2
