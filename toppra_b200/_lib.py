@@ -103,6 +103,8 @@ def ptr(t):
         return None
     if not t.is_contiguous():
         raise ValueError("toppra_b200: tensor must be contiguous")
+    if str(t.dtype) not in ("torch.float64", "torch.int32"):   # the C-ABI takes `double *` and `int *` only
+        raise ValueError("toppra_b200: tensor must be float64 or int32, got %s" % t.dtype)
     return ctypes.c_void_p(t.data_ptr())
 
 

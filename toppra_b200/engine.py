@@ -136,6 +136,17 @@ def check_grid_shapes(B, breaks, nbreaks, grid, G):
         raise ValueError("gridpoints must have shape (G,) or (%d, G); got %s" % (B, tuple(grid.shape)))
 
 
+def check_grid(grid, B, G):
+    """gridpoints: (G,) shared by the batch or (B, G)."""
+    if grid.dim() not in (1, 2) or grid.shape[-1] != G or (grid.dim() == 2 and grid.shape[0] != B):
+        raise ValueError("gridpoints must have shape (%d,) or (%d, %d); got %s" % (G, B, G, tuple(grid.shape)))
+
+
+def check_shape(t, shape, what):
+    if t is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s; got %s" % (what, tuple(shape), tuple(t.shape)))
+
+
 def check_path_vector(t, B, what):
     if t is not None and tuple(t.shape) != (B,):
         raise ValueError("%s must have shape (%d,); got %s" % (what, B, tuple(t.shape)))
@@ -203,6 +214,16 @@ def rows_canlinear(a, b, c, F, g, F_mode, grid, interp, records, R_total, row0):
         k = F.shape[2]
     else:
         k = 2 * m
+    # shapes per include/toppra_b200.h: raw pointers go to the kernel, a short array would be read out of bounds
+    check_shape(b, (B, G, m), "b")
+    check_shape(c, (B, G, m), "c")
+    check_grid(grid, B, G)
+    if F_mode not in (0, 1, 2, 3):
+        raise ValueError("F_mode must be 0..3; got %r" % (F_mode,))
+    check_shape(F, {0: (k, m), 1: (B, G, k, m)}.get(F_mode, None if F is None else tuple(F.shape)), "F")
+    check_shape(g, {0: (k,), 1: (B, G, k), 2: (k,), 3: (B, k)}[F_mode], "g")
+    if tuple(records.shape[:2]) != (B, G):
+        raise ValueError("records must have shape (%d, %d, W); got %s" % (B, G, tuple(records.shape)))
     with torch.cuda.device(records.device):
         rc = _lib.load().tb_rows_canlinear(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(F), _lib.ptr(g), int(F_mode),
                                            B, G, m, k, _lib.ptr(grid), 1 if grid.dim() == 1 else 0, 1 if interp else 0,
@@ -218,8 +239,7 @@ def scan(records, R, grid, sd_start=None, sd_end=None, sd_end_hi=None, backward_
     torch = torch_mod()
     B, G, W = records.shape
     dev = records.device
-    if grid.dim() not in (1, 2) or grid.shape[-1] != G or (grid.dim() == 2 and grid.shape[0] != B):
-        raise ValueError("gridpoints must have shape (%d,) or (%d, %d); got %s" % (G, B, G, tuple(grid.shape)))
+    check_grid(grid, B, G)
     for t, what in ((sd_start, "sd_start"), (sd_end, "sd_end"), (sd_end_hi, "sd_end_hi")):
         check_path_vector(t, B, what)
     if forward_from is not None:  # forward pass alone on the K / status of an earlier backward-only launch
@@ -371,6 +391,7 @@ def scan_robust(records, R, conic_row0, conic_rows, ellipsoid, grid, sd_start=No
 def feasible_sets(records, R, grid):
     torch = torch_mod()
     B, G, W = records.shape
+    check_grid(grid, B, G)
     X = torch.empty((B, G, 2), dtype=torch.float64, device=records.device)
     with torch.cuda.device(records.device):
         rc = _lib.load().tb_feasible_sets_ex(_lib.ptr(records), W, int(R), _lib.ptr(grid), 1 if grid.dim() == 1 else 0, B,
@@ -385,6 +406,7 @@ def reachable_sets(records, R, grid, sdmin=None, sdmax=None):
     torch = torch_mod()
     B, G, W = records.shape
     dev = records.device
+    check_grid(grid, B, G)
     for t, what in ((sdmin, "sdmin"), (sdmax, "sdmax")):
         check_path_vector(t, B, what)
     X = torch.empty((B, G, 2), dtype=torch.float64, device=dev)
@@ -425,7 +447,13 @@ def sd_bisect(x_fast, u_fast, x_slow, u_slow, grid, desired, atol=1e-5, status_i
     torch = torch_mod()
     B, G = x_fast.shape
     dev = x_fast.device
+    check_grid(grid, B, G)
     check_path_vector(desired, B, "desired_duration")
+    check_shape(x_slow, (B, G), "x_slow")
+    for t, what in ((u_fast, "u_fast"), (u_slow, "u_slow")):
+        check_shape(t, (B, G - 1), what)
+    if status_in is not None and (status_in.dtype != torch.int32 or tuple(status_in.shape) != (B,)):
+        raise ValueError("status_in must be an int32 tensor of shape (%d,)" % B)
     sd = torch.empty((B, G), dtype=torch.float64, device=dev)
     u = torch.empty((B, G - 1), dtype=torch.float64, device=dev)
     info = torch.empty((B, 4), dtype=torch.float64, device=dev)
@@ -444,6 +472,7 @@ def spline_time_stamps(sd, grid, glen=None):
     torch = torch_mod()
     B, G = sd.shape
     dev = sd.device
+    check_grid(grid, B, G)
     check_glen(glen, B, grid)
     t = torch.empty((B, G), dtype=torch.float64, device=dev)
     s = torch.empty((B, G), dtype=torch.float64, device=dev)
