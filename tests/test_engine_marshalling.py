@@ -69,6 +69,10 @@ class RecordingLib(object):
     """Stands in for the loaded shared library: every entry point records its arguments, checks them against the ctypes
     prototype and reports success."""
 
+    # the two size queries answer like the library does (toppra_b200.h: W = 3R + 2 rounded up to even)
+    RESULTS = {"tb_record_doubles": lambda R: (3 * R + 2 + 1) & ~1,
+               "tb_spline_fit_workspace_doubles": lambda B, n, dof: 7 * B * n * dof}
+
     def __init__(self):
         self.calls = []
 
@@ -88,7 +92,7 @@ class RecordingLib(object):
                 else:
                     assert a is None or isinstance(a, (ctypes.c_void_p, int)), (name, k, a)
             self.calls.append((name, args))
-            return 0
+            return self.RESULTS.get(name, lambda *a: 0)(*args)
 
         return entry
 
