@@ -75,6 +75,21 @@ def test_ragged_batch_solve_bit_exact(ta, golden, fused):
         ta.BatchTOPPRA(_cons(ta, g), path, bad, glen=g["pg_toppra_len"])
 
 
+def test_ragged_batch_in_chunks_bit_exact(ta, golden):
+    """Ragged grids through a record buffer that holds only 5 of the 16 paths: chunks carry their own slice of the grid
+    lengths; results equal the reference's golden (and hence the one-launch solve) bit for bit."""
+    g = golden("frows_batch")
+    path = ta.BatchSplineInterpolator(g["ss"], g["way"])
+    whole = ta.BatchTOPPRA(_cons(ta, g), path, gridpoints=None, fused=False)
+    rows = sum(c.num_rows(whole.ctx) for c in whole.constraints)
+    per_path = 8 * ta.engine.record_doubles(rows) * whole.G
+    inst = ta.BatchTOPPRA(_cons(ta, g), path, gridpoints=None, fused=False, max_record_bytes=5 * per_path)
+    assert inst.chunk_size() == 5 and whole.chunk_size() == 16
+    h = inst.compute_parameterization(0.0, 0.0).to_host()
+    assert not h["status"].any()
+    assert _same(h["K"], g["ragged_K"]) and _same(h["sd"], g["ragged_sd"]) and _same(h["sdd"], g["ragged_sdd"])
+
+
 def test_reachable_sets_batch_bit_exact(ta, golden):
     g = golden("frows_batch")
     path = ta.BatchSplineInterpolator(g["ss"], g["way"])

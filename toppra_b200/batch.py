@@ -22,11 +22,13 @@ def conic_info(ctx, constraints):
 
 
 def scan_any(records, R, grid, conic, sd_start=None, sd_end=None, sd_end_hi=None, backward_only=False,
-             counters=False, fast_lower=False):
+             counters=False, fast_lower=False, glen=None):
     """K2 for purely linear problems, K2r when a robust constraint is present."""
     if conic is None:
         return engine.scan(records, R, grid, sd_start, sd_end, sd_end_hi, backward_only, counters,
-                           fast_lower=fast_lower)
+                           fast_lower=fast_lower, glen=glen)
+    if glen is not None:
+        raise NotImplementedError("robust problems on ragged grids")
     if sd_end_hi is not None:
         raise NotImplementedError("robust problems: compute_controllable_sets needs sdmin == sdmax")
     return engine.scan_robust(records, R, conic[0], conic[1], conic[2], grid, sd_start, sd_end, backward_only, counters)
@@ -376,8 +378,6 @@ class BatchTOPPRA(object):
         nchunk = self.chunk_size()
         if nchunk >= self.B:
             return BatchResult(self._scan(s0, s1, counters=counters))
-        if self.glen is not None:
-            raise NotImplementedError("ragged grids with chunked stage records: raise max_record_bytes or split the batch")
         B, G, dev = self.B, self.G, self.device
         out = dict(K=torch.empty((B, G, 2), dtype=torch.float64, device=dev),
                    sd=torch.empty((B, G), dtype=torch.float64, device=dev),
@@ -390,6 +390,7 @@ class BatchTOPPRA(object):
         for lo in range(0, B, nchunk):
             hi = min(B, lo + nchunk)
             grid = self.d_grid if self.d_grid.dim() == 1 else self.d_grid[lo:hi]
+            glen = None if self.glen is None else self.glen[lo:hi].contiguous()   # ragged grids: the chunk's lengths
             ctx = RecordContext(self.path.chunk(lo, hi), grid, self._grid_host, None, lo, hi)
             if buf is None:
                 buf, self.R = build_records(ctx, self.constraints)
@@ -397,7 +398,7 @@ class BatchTOPPRA(object):
             else:
                 rec, _ = build_records(ctx, self.constraints, out=buf)
             part = scan_any(rec, self.R, grid, self.conic, None if s0 is None else s0[lo:hi],
-                            None if s1 is None else s1[lo:hi], counters=counters, fast_lower=not self.exact)
+                            None if s1 is None else s1[lo:hi], counters=counters, fast_lower=not self.exact, glen=glen)
             for key in out:
                 out[key][lo:hi] = part[key]
         return BatchResult(out)
