@@ -29,7 +29,7 @@ def header_prototypes():
     text = re.sub(r"//[^\n]*", "", text)
     out = {}
     for ret, name, args in re.findall(r"\b(int|const char \*)\s*(tb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
-        kinds = []
+        kinds, names = [], []
         for arg in [a.strip() for a in args.split(",")]:
             if arg in ("", "void"):
                 continue
@@ -41,8 +41,20 @@ def header_prototypes():
                 kinds.append("int")
             else:
                 raise AssertionError("unparsed argument %r of %s" % (arg, name))
+            names.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", arg)[-1])
         out[name] = (kinds, "ptr" if "*" in ret else "int")
+        PARAM_NAMES[name] = names
     return out
+
+
+PARAM_NAMES = {}     # {entry point: parameter names of the header declaration}, filled by header_prototypes()
+
+
+def named_args(name, args):
+    """{parameter name: value} of one recorded call, by the header's parameter names."""
+    if not PARAM_NAMES:
+        header_prototypes()
+    return dict(zip(PARAM_NAMES[name], args))
 
 
 def _kind(ctype):
@@ -182,6 +194,22 @@ def test_every_engine_entry_marshals_its_prototype(lib):
     q = engine.constaccel_eval(ppoly, breaks, grid, x, tg, us, torch.zeros(5, dtype=torch.float64), 0)
     assert tuple(q.shape) == (B, 5, DOF)
     engine.init_bounds(records, R)
+    # sizes and the main arrays land in the parameters the header NAMES for them (catches swapped arguments of one kind)
+    sizes = {"B": B, "G": G, "dof": DOF, "nseg": NSEG}
+    arrays = {"ppoly": (ppoly.data_ptr(), c.data_ptr()), "breaks": (breaks.data_ptr(),)}   # c: the fit's OUTPUT
+    for name, args in lib.calls:
+        named = named_args(name, args)
+        for key, want in sizes.items():
+            if key in named and name != "tb_propose_gridpoints":
+                assert named[key] == want, (name, key, named[key])
+        for key, want in arrays.items():
+            if key in named:
+                assert named[key].value in want, (name, key)
+        if "grid" in named and named.get("grid_shared") == 1:
+            assert named["grid"].value == grid.data_ptr(), name
+        if "records" in named and "W" in named and name != "tb_xbound_velocity":      # that one writes a [B, G, 2] array
+            assert named["records"].value in (records.data_ptr(), rec_ub.data_ptr()) and \
+                named["W"] in (records.shape[-1], rec_ub.shape[-1]), name
     seen = {name for name, _ in lib.calls}
     assert {"tb_spline_fit", "tb_ppoly_eval", "tb_coeff_velacc", "tb_scan_ragged", "tb_scan_velacc_ragged",
             "tb_xbound_velocity", "tb_feasible_sets_ex", "tb_reachable_sets", "tb_scan_robust", "tb_propose_gridpoints",

@@ -11,7 +11,7 @@ import numpy as np
 
 import toppra_b200 as ta
 from toppra_b200 import engine
-from test_engine_marshalling import lib  # noqa: F401  (fixture)
+from test_engine_marshalling import lib, named_args  # noqa: F401  (lib: fixture)
 
 B, N, DOF, G = 8, 5, 6, 50
 SIZE_QUERIES = ("tb_record_doubles", "tb_spline_fit_workspace_doubles")
@@ -19,6 +19,15 @@ SIZE_QUERIES = ("tb_record_doubles", "tb_spline_fit_workspace_doubles")
 
 def _launches(lib, start=0):  # noqa: F811
     return [name for name, _ in lib.calls[start:] if name not in SIZE_QUERIES]
+
+
+def _last(lib, name):  # noqa: F811
+    """The last call of `name` as {header parameter name: value}."""
+    return named_args(name, lib.last(name))
+
+
+def _all(lib, name, start):  # noqa: F811
+    return [named_args(n, a) for n, a in lib.calls[start:] if n == name]
 
 
 def _problem(dof=DOF):
@@ -37,15 +46,15 @@ def test_cfg2_step_is_three_launches_and_builds_no_records(lib):  # noqa: F811
     res = inst.compute_parameterization(0.0, 0.0)
     assert _launches(lib, mark) == ["tb_xbound_velocity", "tb_scan_velacc_ragged"]
     assert inst.fused and tuple(res.sd.shape) == (B, G)
-    args = lib.last("tb_scan_velacc_ragged")
-    assert args[9] is None and args[17] == 0                      # no glen; exact mode: no flags
+    args = _last(lib, "tb_scan_velacc_ragged")
+    assert args["glen"] is None and args["flags"] == 0            # common grid length; exact mode: no flags
     mark = len(lib.calls)
     ta.BatchTOPPRA([vel, acc], path, gridpoints=np.linspace(0, 1, G), exact=False).compute_parameterization(0.0, 0.0)
-    assert lib.last("tb_scan_velacc_ragged")[17] == engine.SCAN_FLAGS["fast_lower"]
+    assert _last(lib, "tb_scan_velacc_ragged")["flags"] == engine.SCAN_FLAGS["fast_lower"]
     mark = len(lib.calls)
     inst.compute_controllable_sets(0.0, 0.0)
     assert _launches(lib, mark) == ["tb_scan_velacc_ragged"]     # the velocity bound is kept from the first solve
-    assert lib.last("tb_scan_velacc_ragged")[17] == engine.SCAN_FLAGS["backward_only"]
+    assert _last(lib, "tb_scan_velacc_ragged")["flags"] == engine.SCAN_FLAGS["backward_only"]
 
 
 def test_records_path_cfg3_and_chunking(lib):  # noqa: F811
@@ -58,8 +67,8 @@ def test_records_path_cfg3_and_chunking(lib):  # noqa: F811
     inst.compute_parameterization(0.0, 0.0)
     assert _launches(lib, mark) == ["tb_coeff_velacc", "tb_coeff_second_order", "tb_scan_ragged"]
     R = 4 * DOF + 4 * DOF                                          # interpolated acceleration + torque rows
-    assert inst.R == R and lib.last("tb_scan_ragged")[2] == R
-    assert lib.last("tb_coeff_second_order")[19] == 4 * DOF        # torque rows start behind the acceleration rows
+    assert inst.R == R and _last(lib, "tb_scan_ragged")["R"] == R
+    assert _last(lib, "tb_coeff_second_order")["row0"] == 4 * DOF  # torque rows start behind the acceleration rows
     # the same problem with a record buffer that holds 3 paths: chunks of 3, 3, 2 through ONE buffer
     per_path = 8 * engine.record_doubles(R) * G
     mark = len(lib.calls)
@@ -67,13 +76,12 @@ def test_records_path_cfg3_and_chunking(lib):  # noqa: F811
     assert small.chunk_size() == 3
     small.compute_parameterization(0.0, 0.0)
     assert _launches(lib, mark) == ["tb_coeff_velacc", "tb_coeff_second_order", "tb_scan_ragged"] * 3
-    scans = [a for n, a in lib.calls[mark:] if n == "tb_scan_ragged"]
-    k1s = [a for n, a in lib.calls[mark:] if n == "tb_coeff_velacc"]
-    assert [a[5] for a in scans] == [3, 3, 2] and [a[3] for a in k1s] == [3, 3, 2]
-    assert len({a[0].value for a in scans}) == 1                   # one record buffer, reused
+    scans, k1s = _all(lib, "tb_scan_ragged", mark), _all(lib, "tb_coeff_velacc", mark)
+    assert [a["B"] for a in scans] == [3, 3, 2] and [a["B"] for a in k1s] == [3, 3, 2]
+    assert len({a["records"].value for a in scans}) == 1           # one record buffer, reused
     ppoly0 = small.path.d_ppoly.data_ptr()
     stride = 8 * 4 * (N - 1) * DOF
-    assert [a[0].value - ppoly0 for a in k1s] == [0, 3 * stride, 6 * stride]   # each chunk reads ITS paths' coefficients
+    assert [a["ppoly"].value - ppoly0 for a in k1s] == [0, 3 * stride, 6 * stride]   # each chunk reads ITS paths' coefficients
 
 
 def test_robust_and_f_rows_plans(lib):  # noqa: F811
@@ -83,8 +91,8 @@ def test_robust_and_f_rows_plans(lib):  # noqa: F811
     mark = len(lib.calls)
     ta.BatchTOPPRA([vel, robust], path, gridpoints=grid).compute_parameterization(0.0, 0.0)
     assert _launches(lib, mark)[-1] == "tb_scan_robust" and "tb_scan_ragged" not in _launches(lib, mark)
-    args = lib.last("tb_scan_robust")
-    assert (args[3], args[4]) == (0, 4 * DOF)                      # the conic rows are the acceleration rows
+    args = _last(lib, "tb_scan_robust")
+    assert (args["conic_row0"], args["conic_rows"]) == (0, 4 * DOF)   # the conic rows are the acceleration rows
     mark = len(lib.calls)
     inst = ta.BatchTOPPRA([vel, acc], path, gridpoints=grid)
     inst.compute_reachable_sets(0.0, 0.0)
@@ -98,7 +106,7 @@ def test_robust_and_f_rows_plans(lib):  # noqa: F811
     sd.compute_parameterization(0.0, 0.0)
     plan = _launches(lib, mark)
     assert plan == ["tb_xbound_velocity", "tb_scan_velacc_ragged", "tb_scan_velacc_ragged", "tb_sd_bisect"]
-    flags = [a[17] for n, a in lib.calls[mark:] if n == "tb_scan_velacc_ragged"]
+    flags = [a["flags"] for a in _all(lib, "tb_scan_velacc_ragged", mark)]
     assert flags == [engine.SCAN_FLAGS["sd_fast"], engine.SCAN_FLAGS["sd_slow"]]   # fastest and slowest profile, each a full scan
 
 
@@ -126,8 +134,8 @@ def test_auto_gridpoints_plan_is_ragged(lib, monkeypatch):  # noqa: F811
     inst = ta.BatchTOPPRA([vel, acc], path)
     res = inst.compute_parameterization(0.0, 0.0)
     assert _launches(lib, mark) == ["tb_propose_gridpoints", "tb_xbound_velocity", "tb_scan_velacc_ragged"]
-    args = lib.last("tb_scan_velacc_ragged")
-    assert args[8] == int(lens.max()) and args[9] is not None and args[6] == 0        # G = longest grid, glen, per-path grid
+    args = _last(lib, "tb_scan_velacc_ragged")
+    assert args["G"] == int(lens.max()) and args["glen"] is not None and args["grid_shared"] == 0   # padded per-path grids
     assert tuple(res.sd.shape) == (B, int(lens.max())) and np.array_equal(inst.glen.numpy(), lens)
 
 
@@ -144,4 +152,4 @@ def test_single_path_api_plan(lib):  # noqa: F811
         inst.compute_parameterization(0, 0)      # status / sd are uninitialised memory here: the outcome is not the point
     except Exception:
         pass
-    assert _launches(lib, mark)[0] == "tb_scan_ragged" and lib.last("tb_scan_ragged")[5] == 1
+    assert _launches(lib, mark)[0] == "tb_scan_ragged" and _last(lib, "tb_scan_ragged")["B"] == 1
