@@ -125,6 +125,7 @@ def check_frows(p, rng):
     elif want is None:
         assert int(st[0]) != 0, "propose_gridpoints: the reference raised"
     else:
+        count("propose_gridpoints")
         assert int(st[0]) == 0 and int(glen[0]) == len(want) and eq(grid[0, :len(want)].numpy(), want), "propose_gridpoints"
     G = len(p["grid"])
     if G >= 3:
@@ -139,7 +140,101 @@ def check_frows(p, rng):
             return
         t, s, nk = cpu_engine.spline_time_stamps(torch.from_numpy(vel[None]), torch.from_numpy(p["grid"]))
         k = int(nk[0])
+        count("time stamps")
         assert k == len(traj.ss_waypoints) and eq(t[0, :k].numpy(), traj.ss_waypoints), "ParametrizeSpline time stamps"
+
+
+_MINE = []
+COUNTS = {}
+
+
+def count(what):
+    COUNTS[what] = COUNTS.get(what, 0) + 1
+
+
+def mine():
+    """toppra_b200 with its kernels replaced by the oracle-backed engine double (tests/cpu_engine.py)."""
+    if not _MINE:
+        import pytest
+        import cpu_engine
+        patch = pytest.MonkeyPatch()
+        _MINE.extend([cpu_engine.install(patch), patch])
+    return _MINE[0]
+
+
+def release():
+    """Undo the engine double (for callers that run inside another test process)."""
+    if _MINE:
+        _MINE[1].undo()
+        del _MINE[:]
+
+
+def check_sd_and_reachable(p, rng):
+    """TOPPRAsd and compute_reachable_sets through the PACKAGE's host code on the engine double against the reference
+    classes (the device forms of these two are pinned to the same restatements by the 16-path goldens on the GPU)."""
+    if p["bc"] != "not-a-knot" or len(p["ss"]) == 3 or len(p["grid"]) < 3:
+        return
+    tb = mine()
+    mk = lambda pkg, cons: [cons.JointVelocityConstraint(p["vlim"]),  # noqa: E731
+                            cons.JointAccelerationConstraint(p["alim"], discretization_scheme=p["interp"])]
+    theirs = ta.SplineInterpolator(p["ss"], p["way"])
+    ours = tb.SplineInterpolator(p["ss"], p["way"])
+    fast = algo.TOPPRA(mk(algo, constraint), theirs, gridpoints=p["grid"], solver_wrapper="seidel")
+    _, sd_f, _ = fast.compute_parameterization(0, 0)
+    if sd_f is not None and np.all(sd_f[1:] + sd_f[:-1] > 0):
+        t_fast = np.sum(2 * np.diff(p["grid"]) / (sd_f[1:] + sd_f[:-1]))
+        want_t = t_fast * rng.choice([0.5, 1.0, 1.2, 2.0, 7.0, 1e3])
+        a = algo.TOPPRAsd(mk(algo, constraint), theirs, gridpoints=p["grid"], solver_wrapper="seidel")
+        b = tb.algorithm.TOPPRAsd(mk(tb.algorithm, tb.constraint), ours, gridpoints=p["grid"], solver_wrapper="seidel")
+        a.set_desired_duration(want_t)
+        b.set_desired_duration(want_t)
+        ra = a.compute_parameterization(0, 0, return_data=True)
+        rb = b.compute_parameterization(0, 0, return_data=True)
+        count("TOPPRAsd")
+        assert a.problem_data.return_code.name == b.problem_data.return_code.name, "TOPPRAsd return code"
+        for x, y, what in zip(ra, rb, ("sdd", "sd", "v", "K")):
+            assert (x is None and y is None) or eq(x, y), "TOPPRAsd " + what
+    sdmin = 0.0 if rng.rand() < 0.5 else 10 ** rng.uniform(-3, -0.5)
+    sdmax = sdmin + (0.0 if rng.rand() < 0.3 else 10 ** rng.uniform(-3, 0))
+    for v in ("sdmin", "sdmax"):
+        val = locals()[v]
+        while float(val) ** 2 != float(val) * float(val):
+            val = float(np.nextafter(val, 10.0))
+        if v == "sdmin":
+            sdmin = val
+        else:
+            sdmax = val
+    La = algo.TOPPRA(mk(algo, constraint), theirs, gridpoints=p["grid"], solver_wrapper="seidel").compute_reachable_sets(sdmin, sdmax)
+    Lb = tb.algorithm.TOPPRA(mk(tb.algorithm, tb.constraint), ours, gridpoints=p["grid"],
+                             solver_wrapper="seidel").compute_reachable_sets(sdmin, sdmax)
+    count("reachable sets")
+    assert eq(La, Lb), "reachable sets"
+
+
+def check_torque(p, rng):
+    """vel + acc + SecondOrderConstraint.joint_torque_constraint with a numpy inverse dynamics (the reference-style callback
+    route, bit-exact by construction: same user function, same call order) and JointTorqueConstraint with dry friction."""
+    dof = p["way"].shape[1]
+    if p["bc"] != "not-a-knot" or len(p["ss"]) == 3 or not 2 <= dof <= 7 or len(p["grid"]) > 200:
+        return
+    from problems import inv_dyn_numpy
+    tb = mine()
+    taulim = np.stack((-(20 + 30 * rng.rand(dof)), 20 + 30 * rng.rand(dof)), axis=1)
+    fric = np.zeros(dof) if rng.rand() < 0.5 else 0.5 * rng.rand(dof)
+    scheme = int(rng.rand() < 0.6)
+    out = []
+    for pkg, cons, path in ((algo, constraint, ta.SplineInterpolator(p["ss"], p["way"])),
+                            (tb.algorithm, tb.constraint, tb.SplineInterpolator(p["ss"], p["way"]))):
+        torque = cons.SecondOrderConstraint.joint_torque_constraint(inv_dyn_numpy, taulim, fric,
+                                                                    discretization_scheme=scheme)
+        inst = pkg.TOPPRA([cons.JointVelocityConstraint(p["vlim"]), cons.JointAccelerationConstraint(p["alim"]), torque],
+                          path, gridpoints=p["grid"], solver_wrapper="seidel")
+        out.append(inst.compute_parameterization(p["sd0"], p["sd1"], return_data=True) +
+                   (inst.problem_data.return_code.name,))
+    count("torque (%s)" % out[0][-1])
+    for x, y, what in zip(out[0], out[1], ("sdd", "sd", "v", "K", "return code")):
+        same = (x == y) if isinstance(x, str) else ((x is None and y is None) or (x is not None and y is not None and eq(x, y)))
+        assert same, "torque " + what
 
 
 def main():
@@ -156,6 +251,8 @@ def main():
             st = check_solve(p)
             hist[st] = hist.get(st, 0) + 1
             check_frows(p, rng)
+            check_sd_and_reachable(p, rng)
+            check_torque(p, rng)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
             print("MISMATCH seed %d: %s  (dof %d, n %d, G %d, bc %s, interp %d, sd %.3g -> %.3g)"
@@ -164,8 +261,8 @@ def main():
         except Exception as e:                      # the reference itself raised (e.g. bad gridpoints): not a parity question
             hist["ref-raised:" + type(e).__name__] = hist.get("ref-raised:" + type(e).__name__, 0) + 1
         seed += 1
-    print("problems: %d (seeds %d..%d), status histogram %s, mismatches: %d" % (seed - args.seed, args.seed, seed - 1, hist,
-                                                                               len(bad)))
+    print("problems: %d (seeds %d..%d), status histogram %s, checks run %s, mismatches: %d"
+          % (seed - args.seed, args.seed, seed - 1, hist, COUNTS, len(bad)))
     return 1 if bad else 0
 
 

@@ -227,3 +227,33 @@ def test_univariate_spline_interpolator_vs_reference(ref, monkeypatch):
         np.testing.assert_allclose(K2, K, rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(sd2, sd, rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(sdd2, sdd, rtol=1e-6, atol=1e-7)
+
+
+def test_randomly_shaped_problems_vs_reference(ref):
+    """A slice of the campaign of scripts/fuzz_oracle_vs_reference.py (dof 1..14, 2..12 knots, 2..400 gridpoints, non-uniform
+    knots and grids, every boundary condition, both discretisations, non-zero boundary velocities, tiny motions): spline
+    coefficients, K, sd, u, status, feasible sets, propose_gridpoints, time stamps, TOPPRAsd, reachable sets, torque rows —
+    bit for bit against the reference (31 000 + 10 000 problems in the full runs, profiles/r02_fuzz_oracle_vs_reference.txt)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_oracle_vs_reference", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                                                 "fuzz_oracle_vs_reference.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    try:
+        for seed in range(400000, 400120):
+            rng = np.random.RandomState(seed)
+            p = fuzz.random_problem(rng)
+            try:
+                fuzz.check_solve(p)
+                fuzz.check_frows(p, rng)
+                fuzz.check_sd_and_reachable(p, rng)
+                fuzz.check_torque(p, rng)
+            except AssertionError as e:
+                raise AssertionError("seed %d: %s" % (seed, e))
+            except Exception:
+                pass            # the reference itself rejected the input (as in the campaign)
+    finally:
+        fuzz.release()          # the campaign installs the engine double process-wide
+    assert fuzz.COUNTS.get("TOPPRAsd", 0) >= 10 and fuzz.COUNTS.get("propose_gridpoints", 0) >= 80
