@@ -32,47 +32,7 @@ def eq(a, b):
     return np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float), equal_nan=True)
 
 
-def random_problem(rng):
-    dof = int(rng.choice([1, 2, 3, 6, 7, 7, 7, 10, 14]))
-    n = int(rng.randint(2, 13))
-    ss = np.r_[0.0, np.cumsum(0.05 + rng.rand(n - 1))]
-    if rng.rand() < 0.5:
-        ss = np.linspace(0, ss[-1], n)
-    scale = 10 ** rng.uniform(-3, 1) if rng.rand() < 0.25 else 1.0          # tiny motions now and then
-    way = rng.randn(n, dof) * scale
-    if rng.rand() < 0.1:
-        way[:, rng.randint(dof)] = way[0, 0]                                 # a joint that does not move
-    vl = (0.5 + rng.rand(dof)) * scale if rng.rand() < 0.4 else 10 + 20 * rng.rand(dof)
-    al = (10 + 2 * rng.rand(dof)) * (scale if rng.rand() < 0.5 else 1.0)
-    if rng.rand() < 0.3:                                                     # asymmetric limits
-        vlim = np.stack((-vl * (0.3 + rng.rand(dof)), vl), axis=1)
-        alim = np.stack((-al, al * (0.3 + rng.rand(dof))), axis=1)
-    else:
-        vlim, alim = np.stack((-vl, vl), axis=1), np.stack((-al, al), axis=1)
-    G = int(rng.choice([2, 3, 5, 17, 50, 100, 200, 400]))
-    grid = np.linspace(0, ss[-1], G)
-    if G > 3 and rng.rand() < 0.4:
-        grid = np.r_[0.0, np.sort(rng.uniform(0, ss[-1], G - 2)), ss[-1]]
-        if np.any(np.diff(grid) <= 0):
-            grid = np.linspace(0, ss[-1], G)
-    if G > n and rng.rand() < 0.2:                                           # gridpoints exactly on breakpoints
-        k = rng.randint(1, G - 1, size=min(n - 2, 3)) if n > 2 else []
-        for j, idx in enumerate(np.unique(k)):
-            cand = ss[1 + j % max(n - 2, 1)]
-            if grid[idx - 1] < cand < grid[idx + 1]:
-                grid[idx] = cand
-    bc = rng.choice(["not-a-knot", "clamped", "natural"]) if n > 2 else "not-a-knot"
-    interp_scheme = int(rng.rand() < 0.7)
-    r = rng.rand()
-    sd0 = 0.0 if r < 0.6 else (10 ** rng.uniform(-3, 0) if r < 0.9 else 50.0)
-    sd1 = 0.0 if rng.rand() < 0.6 else 10 ** rng.uniform(-3, 0)
-    # the reference squares the boundary velocities with libm pow(x, 2.0), which is not always correctly rounded
-    # (DESIGN.md section 2); keep to velocities where it is, so that everything else is compared bit for bit
-    while float(sd0) ** 2 != float(sd0) * float(sd0):
-        sd0 = float(np.nextafter(sd0, 1.0))
-    while float(sd1) ** 2 != float(sd1) * float(sd1):
-        sd1 = float(np.nextafter(sd1, 1.0))
-    return dict(ss=ss, way=way, vlim=vlim, alim=alim, grid=grid, bc=str(bc), interp=interp_scheme, sd0=sd0, sd1=sd1)
+from problems import random_shaped_problem as random_problem  # noqa: E402
 
 
 def check_solve(p):
