@@ -171,6 +171,35 @@ def check_sd_and_reachable(p, rng):
     assert eq(La, Lb), "reachable sets"
 
 
+def check_parametrizers(p, rng):
+    """ParametrizeConstAccel (time grid and accelerations bit for bit, evaluations to rounding) and ParametrizeSpline
+    (knot times bit for bit, the clamped re-fit and its evaluations to rounding) on the solved velocity profile."""
+    if p["bc"] != "not-a-knot" or len(p["ss"]) == 3 or len(p["grid"]) < 3:
+        return
+    from toppra.parametrizer import ParametrizeConstAccel
+    tb = mine()
+    theirs, ours = ta.SplineInterpolator(p["ss"], p["way"]), tb.SplineInterpolator(p["ss"], p["way"])
+    cons = [constraint.JointVelocityConstraint(p["vlim"]), constraint.JointAccelerationConstraint(p["alim"], p["interp"])]
+    _, sd, _ = algo.TOPPRA(cons, theirs, gridpoints=p["grid"], solver_wrapper="seidel").compute_parameterization(0, 0)
+    if sd is None or not np.all(sd[1:] + sd[:-1] > 0):
+        return
+    a, b = ParametrizeConstAccel(theirs, p["grid"], sd), tb.ParametrizeConstAccel(ours, p["grid"], sd)
+    count("ParametrizeConstAccel")
+    assert eq(a._ts, b._ts) and eq(a._us, b._us) and a.duration == b.duration, "ConstAccel time grid"
+    ts = np.r_[0.0, np.sort(rng.uniform(0, a.duration, 30)), a.duration]
+    scale = max(1.0, np.abs(p["way"]).max())
+    for order, tol in ((0, 1e-11), (1, 1e-9), (2, 1e-7)):
+        want = a(ts, order)
+        np.testing.assert_allclose(b(ts, order), want, rtol=tol, atol=tol * max(scale, np.abs(want).max()),
+                                   err_msg="ConstAccel order %d" % order)
+    sa, sb = ParametrizeSpline(theirs, p["grid"], sd), tb.ParametrizeSpline(ours, p["grid"], sd)
+    count("ParametrizeSpline")
+    assert eq(sa.ss_waypoints, sb.ss_waypoints) and sa.duration == sb.duration, "ParametrizeSpline knots"
+    ts = np.linspace(0, sa.duration, 25)
+    want = sa(ts)
+    np.testing.assert_allclose(sb(ts), want, rtol=1e-9, atol=1e-9 * max(scale, np.abs(want).max()), err_msg="ParametrizeSpline q")
+
+
 def check_torque(p, rng):
     """vel + acc + SecondOrderConstraint.joint_torque_constraint with a numpy inverse dynamics (the reference-style callback
     route, bit-exact by construction: same user function, same call order) and JointTorqueConstraint with dry friction."""
@@ -213,6 +242,7 @@ def main():
             check_frows(p, rng)
             check_sd_and_reachable(p, rng)
             check_torque(p, rng)
+            check_parametrizers(p, rng)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
             print("MISMATCH seed %d: %s  (dof %d, n %d, G %d, bc %s, interp %d, sd %.3g -> %.3g)"

@@ -232,7 +232,8 @@ def test_univariate_spline_interpolator_vs_reference(ref, monkeypatch):
 def test_randomly_shaped_problems_vs_reference(ref):
     """A slice of the campaign of scripts/fuzz_oracle_vs_reference.py (dof 1..14, 2..12 knots, 2..400 gridpoints, non-uniform
     knots and grids, every boundary condition, both discretisations, non-zero boundary velocities, tiny motions): spline
-    coefficients, K, sd, u, status, feasible sets, propose_gridpoints, time stamps, TOPPRAsd, reachable sets, torque rows —
+    coefficients, K, sd, u, status, feasible sets, propose_gridpoints, time stamps, TOPPRAsd, reachable sets, torque rows,
+    both output parametrizers —
     bit for bit against the reference (31 000 + 10 000 problems in the full runs, profiles/r02_fuzz_oracle_vs_reference.txt)."""
     import importlib.util
     import os
@@ -250,6 +251,7 @@ def test_randomly_shaped_problems_vs_reference(ref):
                 fuzz.check_frows(p, rng)
                 fuzz.check_sd_and_reachable(p, rng)
                 fuzz.check_torque(p, rng)
+                fuzz.check_parametrizers(p, rng)
             except AssertionError as e:
                 raise AssertionError("seed %d: %s" % (seed, e))
             except Exception:
