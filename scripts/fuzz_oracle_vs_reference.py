@@ -200,6 +200,51 @@ def check_parametrizers(p, rng):
     np.testing.assert_allclose(sb(ts), want, rtol=1e-9, atol=1e-9 * max(scale, np.abs(want).max()), err_msg="ParametrizeSpline q")
 
 
+def _ub_class(cons):
+    class UB(cons.LinearConstraint):
+        """Acceleration rows + a u-interval and an x-interval per gridpoint (seidelWrapper.__init__, pyx:512-520)."""
+
+        def __init__(self, acc, ub, xb):
+            super(UB, self).__init__()
+            self.acc, self.ub, self.xb = acc, ub, xb
+            self.discretization_type = acc.discretization_type
+            self.identical = True
+
+        def get_dof(self):
+            return self.acc.get_dof()
+
+        def compute_constraint_params(self, path, gridpoints, *a):
+            pa, pb, pc, F, g, _, _ = self.acc.compute_constraint_params(path, gridpoints)
+            return pa, pb, pc, F, g, self.ub, self.xb
+
+    return UB
+
+
+def check_ubound(p, rng):
+    """A user constraint that returns `ubound` / `xbound` next to its rows: parameterisation, feasible and reachable sets
+    through the package's generic-constraint path (host 7-tuple -> rows_canlinear -> records with the u-bound pair)."""
+    if p["bc"] != "not-a-knot" or len(p["ss"]) == 3 or len(p["grid"]) < 3 or p["way"].shape[1] > 7:
+        return
+    tb = mine()
+    G = len(p["grid"])
+    width = 10 ** rng.uniform(-1.5, 1.0) * max(1e-3, np.abs(p["alim"]).max())
+    ub = np.stack((-width * (0.5 + rng.rand(G)), width * (0.5 + rng.rand(G))), axis=1)
+    xb = np.stack((np.zeros(G), 10 ** rng.uniform(-2, 3) * (0.5 + rng.rand(G))), axis=1)
+    out = []
+    for pkg, cons, path in ((algo, constraint, ta.SplineInterpolator(p["ss"], p["way"])),
+                            (tb.algorithm, tb.constraint, tb.SplineInterpolator(p["ss"], p["way"]))):
+        mk = lambda: [cons.JointVelocityConstraint(p["vlim"]),  # noqa: E731
+                      _ub_class(cons)(cons.JointAccelerationConstraint(p["alim"], p["interp"]), ub, xb)]
+        inst = pkg.TOPPRA(mk(), path, gridpoints=p["grid"], solver_wrapper="seidel")
+        res = inst.compute_parameterization(0, 0, return_data=True)
+        X = pkg.TOPPRA(mk(), path, gridpoints=p["grid"], solver_wrapper="seidel").compute_feasible_sets()
+        L = pkg.TOPPRA(mk(), path, gridpoints=p["grid"], solver_wrapper="seidel").compute_reachable_sets(0.0, 0.25)
+        out.append((res[0], res[1], res[3], X, L))
+    count("ubound")
+    for x, y, what in zip(out[0], out[1], ("sdd", "sd", "K", "feasible sets", "reachable sets")):
+        assert (x is None and y is None) or (x is not None and y is not None and eq(x, y)), "ubound " + what
+
+
 def check_torque(p, rng):
     """vel + acc + SecondOrderConstraint.joint_torque_constraint with a numpy inverse dynamics (the reference-style callback
     route, bit-exact by construction: same user function, same call order) and JointTorqueConstraint with dry friction."""
@@ -243,6 +288,7 @@ def main():
             check_sd_and_reachable(p, rng)
             check_torque(p, rng)
             check_parametrizers(p, rng)
+            check_ubound(p, rng)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
             print("MISMATCH seed %d: %s  (dof %d, n %d, G %d, bc %s, interp %d, sd %.3g -> %.3g)"

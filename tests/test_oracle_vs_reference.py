@@ -252,6 +252,7 @@ def test_randomly_shaped_problems_vs_reference(ref):
                 fuzz.check_sd_and_reachable(p, rng)
                 fuzz.check_torque(p, rng)
                 fuzz.check_parametrizers(p, rng)
+                fuzz.check_ubound(p, rng)
             except AssertionError as e:
                 raise AssertionError("seed %d: %s" % (seed, e))
             except Exception:
