@@ -245,6 +245,38 @@ def check_ubound(p, rng):
         assert (x is None and y is None) or (x is not None and y is not None and eq(x, y)), "ubound " + what
 
 
+def check_other_constraints(p, rng):
+    """JointVelocityConstraintVarying (limits as a function of s) and JointTorqueConstraint (dry friction, both schemes)."""
+    dof = p["way"].shape[1]
+    if p["bc"] != "not-a-knot" or len(p["ss"]) == 3 or len(p["grid"]) < 3 or len(p["grid"]) > 200:
+        return
+    from problems import inv_dyn_numpy
+    tb = mine()
+    k0, k1 = 0.05 + rng.rand(), rng.rand() / p["ss"][-1]
+    vlim, span = p["vlim"], p["ss"][-1]
+    out = []
+    for pkg, cons, path in ((algo, constraint, ta.SplineInterpolator(p["ss"], p["way"])),
+                            (tb.algorithm, tb.constraint, tb.SplineInterpolator(p["ss"], p["way"]))):
+        var = cons.JointVelocityConstraintVarying(lambda s: vlim * (k0 + k1 * s))
+        inst = pkg.TOPPRA([var, cons.JointAccelerationConstraint(p["alim"], p["interp"])], path, gridpoints=p["grid"],
+                          solver_wrapper="seidel")
+        res = inst.compute_parameterization(0, 0, return_data=True)
+        item = [res[0], res[1], res[3], var.compute_constraint_params(path, p["grid"])[-1]]
+        if 2 <= dof <= 7:
+            taulim = np.stack((-(20 + 30 * np.arange(1, dof + 1) / dof), 25 + 30 * np.arange(1, dof + 1) / dof), axis=1)
+            tau = cons.JointTorqueConstraint(inv_dyn_numpy, taulim, 0.3 * np.ones(dof), discretization_scheme=p["interp"])
+            inst = pkg.TOPPRA([cons.JointVelocityConstraint(p["vlim"]), tau], path, gridpoints=p["grid"],
+                              solver_wrapper="seidel")
+            res = inst.compute_parameterization(0, 0, return_data=True)
+            item += [res[0], res[1], res[3]]
+        out.append(item)
+    count("varying velocity limits" + (" + JointTorqueConstraint" if len(out[0]) > 4 else ""))
+    names = ("varying: sdd", "varying: sd", "varying: K", "varying: xbound", "joint torque: sdd", "joint torque: sd",
+             "joint torque: K")
+    for x, y, what in zip(out[0], out[1], names):
+        assert (x is None and y is None) or (x is not None and y is not None and eq(x, y)), what
+
+
 def check_torque(p, rng):
     """vel + acc + SecondOrderConstraint.joint_torque_constraint with a numpy inverse dynamics (the reference-style callback
     route, bit-exact by construction: same user function, same call order) and JointTorqueConstraint with dry friction."""
@@ -289,6 +321,7 @@ def main():
             check_torque(p, rng)
             check_parametrizers(p, rng)
             check_ubound(p, rng)
+            check_other_constraints(p, rng)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
             print("MISMATCH seed %d: %s  (dof %d, n %d, G %d, bc %s, interp %d, sd %.3g -> %.3g)"

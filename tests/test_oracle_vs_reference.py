@@ -253,6 +253,7 @@ def test_randomly_shaped_problems_vs_reference(ref):
                 fuzz.check_torque(p, rng)
                 fuzz.check_parametrizers(p, rng)
                 fuzz.check_ubound(p, rng)
+                fuzz.check_other_constraints(p, rng)
             except AssertionError as e:
                 raise AssertionError("seed %d: %s" % (seed, e))
             except Exception:
