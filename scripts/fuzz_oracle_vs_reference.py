@@ -277,6 +277,42 @@ def check_other_constraints(p, rng):
         assert (x is None and y is None) or (x is not None and y is not None and eq(x, y)), what
 
 
+def check_batch(p, rng):
+    """The batched entry points against per-path reference solves: B paths with per-path limits and start velocities on a
+    common grid, and on the automatically proposed (ragged) grids — `BatchTOPPRA(gridpoints=None)` must equal
+    `TOPPRA(constraints, path)` of the reference path by path."""
+    dof, n = p["way"].shape[1], len(p["ss"])
+    if n < 4 or dof > 7 or rng.rand() > 0.25:
+        return
+    tb = mine()
+    B = int(rng.randint(2, 7))
+    way = rng.randn(B, n, dof)
+    vl, al = 1 + 20 * rng.rand(B, dof), 5 + 10 * rng.rand(B, dof)
+    vlim, alim = np.stack((-vl, vl), axis=-1), np.stack((-al, al), axis=-1)
+    sd0 = np.where(rng.rand(B) < 0.5, 0.0, 0.01)
+    bpath = tb.BatchSplineInterpolator(p["ss"], way)
+    cons_b = [tb.constraint.JointVelocityConstraint(vlim), tb.constraint.JointAccelerationConstraint(alim, p["interp"])]
+    common = tb.BatchTOPPRA(cons_b, bpath, gridpoints=p["grid"]).compute_parameterization(sd0, 0.0).to_host()
+    ragged_inst = tb.BatchTOPPRA(cons_b, bpath, gridpoints=None)
+    ragged = ragged_inst.compute_parameterization(sd0, 0.0).to_host()
+    glen = ragged_inst.glen.cpu().numpy()
+    count("batch (common + ragged grids)")
+    for b in range(B):
+        path = ta.SplineInterpolator(p["ss"], way[b])
+        cons = [constraint.JointVelocityConstraint(vlim[b]), constraint.JointAccelerationConstraint(alim[b], p["interp"])]
+        for grid, got, tag in ((p["grid"], common, "common grid"), (None, ragged, "proposed grid")):
+            inst = algo.TOPPRA(cons, path, gridpoints=grid, solver_wrapper="seidel")
+            sdd, sd, _, K = inst.compute_parameterization(float(sd0[b]), 0.0, return_data=True)
+            G = len(inst.gridpoints)
+            if grid is None:
+                assert glen[b] == G, "batch: proposed grid length"
+            assert eq(got["K"][b, :G], K), "batch K (%s)" % tag
+            if sd is not None:
+                assert eq(got["sd"][b, :G], sd) and eq(got["sdd"][b, :G - 1], sdd), "batch sd / u (%s)" % tag
+            else:
+                assert got["status"][b] != 0, "batch status (%s)" % tag
+
+
 def check_torque(p, rng):
     """vel + acc + SecondOrderConstraint.joint_torque_constraint with a numpy inverse dynamics (the reference-style callback
     route, bit-exact by construction: same user function, same call order) and JointTorqueConstraint with dry friction."""
@@ -322,6 +358,7 @@ def main():
             check_parametrizers(p, rng)
             check_ubound(p, rng)
             check_other_constraints(p, rng)
+            check_batch(p, rng)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
             print("MISMATCH seed %d: %s  (dof %d, n %d, G %d, bc %s, interp %d, sd %.3g -> %.3g)"
