@@ -313,6 +313,23 @@ def check_batch(p, rng):
                 assert got["status"][b] != 0, "batch status (%s)" % tag
 
 
+def check_robust_params(p, rng):
+    """RobustLinearConstraint (conic_constraint.py:47-124): the conic 6-tuple (a, b, c, P, ubound, xbound) of both packages.
+    (The robust SOLVE has no reference here — ECOS is not installed — and stays pinned by tests/test_robust.py.)"""
+    if p["bc"] != "not-a-knot" or len(p["ss"]) == 3 or len(p["grid"]) > 100:
+        return
+    tb = mine()
+    ell = list(10 ** rng.uniform(-4, 0, 3))
+    out = []
+    for cons, path in ((constraint, ta.SplineInterpolator(p["ss"], p["way"])), (tb.constraint, tb.SplineInterpolator(p["ss"], p["way"]))):
+        base = cons.JointAccelerationConstraint(p["alim"], p["interp"])
+        out.append(cons.RobustLinearConstraint(base, ell, p["interp"]).compute_constraint_params(path, p["grid"]))
+    count("robust parameters")
+    assert len(out[0]) == len(out[1]), "robust tuple length"
+    for x, y, what in zip(out[0], out[1], ("a", "b", "c", "P", "ubound", "xbound")):
+        assert (x is None and y is None) or (x is not None and y is not None and eq(x, y)), "robust " + what
+
+
 def check_torque(p, rng):
     """vel + acc + SecondOrderConstraint.joint_torque_constraint with a numpy inverse dynamics (the reference-style callback
     route, bit-exact by construction: same user function, same call order) and JointTorqueConstraint with dry friction."""
@@ -359,6 +376,7 @@ def main():
             check_ubound(p, rng)
             check_other_constraints(p, rng)
             check_batch(p, rng)
+            check_robust_params(p, rng)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
             print("MISMATCH seed %d: %s  (dof %d, n %d, G %d, bc %s, interp %d, sd %.3g -> %.3g)"

@@ -255,6 +255,7 @@ def test_randomly_shaped_problems_vs_reference(ref):
                 fuzz.check_ubound(p, rng)
                 fuzz.check_other_constraints(p, rng)
                 fuzz.check_batch(p, rng)
+                fuzz.check_robust_params(p, rng)
             except AssertionError as e:
                 raise AssertionError("seed %d: %s" % (seed, e))
             except Exception:
