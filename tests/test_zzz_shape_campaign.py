@@ -44,7 +44,7 @@ def test_kernels_equal_the_oracle_on_randomly_shaped_problems(ta):
         if p["bc"] == "not-a-knot":
             assert _same(c, fit), "spline fit, " + tag
         else:   # same algebra on both sides; the tolerance only guards the comparison against the order of a future refit
-            np.testing.assert_allclose(c, fit, rtol=1e-12, atol=1e-13 * max(1.0, np.abs(fit).max()), err_msg=tag)
+            np.testing.assert_allclose(c, fit, rtol=1e-11, atol=1e-12 * max(1.0, np.abs(fit).max()), err_msg=tag)
         cons = [ta.constraint.JointVelocityConstraint(p["vlim"]),
                 ta.constraint.JointAccelerationConstraint(p["alim"], discretization_scheme=p["interp"])]
         inst = ta.algorithm.TOPPRA(cons, path, gridpoints=p["grid"], solver_wrapper="seidel")
