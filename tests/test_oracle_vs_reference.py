@@ -263,3 +263,57 @@ def test_randomly_shaped_problems_vs_reference(ref):
     finally:
         fuzz.release()          # the campaign installs the engine double process-wide
     assert fuzz.COUNTS.get("TOPPRAsd", 0) >= 10 and fuzz.COUNTS.get("propose_gridpoints", 0) >= 80
+
+
+def test_public_classes_have_the_reference_methods_and_arguments(ref):
+    """Introspection of the reference build against this package: every public class the two share has the reference's public
+    methods / properties, and every shared callable takes the reference's argument names in the reference's order."""
+    import inspect
+    import toppra
+    import toppra.algorithm
+    import toppra.constraint
+    import toppra.interpolator
+    import toppra.parametrizer
+    import toppra.simplepath
+    import toppra.solverwrapper
+    import toppra_b200 as tb
+    import toppra_b200.simplepath
+
+    def params(f):
+        try:
+            return [p for p in inspect.signature(f).parameters if p not in ("args", "kwargs")]
+        except (TypeError, ValueError):
+            return None
+
+    openrave_only = {"compute_rave_trajectory"}
+    seen, problems = set(), []
+    pairs = ((toppra, tb), (toppra.algorithm, tb.algorithm), (toppra.constraint, tb.constraint),
+             (toppra.parametrizer, tb.parametrizer), (toppra.interpolator, tb.interpolator),
+             (toppra.simplepath, tb.simplepath), (toppra.solverwrapper, tb.solverwrapper))
+    for mod_r, mod_t in pairs:
+        for name in dir(mod_r):
+            obj = getattr(mod_r, name)
+            if name.startswith("_") or name in seen or not hasattr(mod_t, name):
+                continue
+            mine = getattr(mod_t, name)
+            if inspect.isclass(obj) and obj.__module__.startswith("toppra"):
+                seen.add(name)
+                for member in ["__init__"] + [m for m in dir(obj) if not m.startswith("_")]:
+                    if member in openrave_only:
+                        continue
+                    if not hasattr(mine, member):
+                        problems.append("%s.%s missing" % (name, member))
+                        continue
+                    fr, ft = getattr(obj, member), getattr(mine, member)
+                    pr, pt = (params(fr), params(ft)) if callable(fr) and not isinstance(fr, type) else (None, None)
+                    if pr is not None and pt is not None and [a for a in pr if a in pt] != pr:
+                        problems.append("%s.%s(%s) vs (%s)" % (name, member, ", ".join(pr), ", ".join(pt)))
+                    elif pr is not None and pt is not None and pt[:len(pr)] != pr and [a for a in pt if a in pr] != pr:
+                        problems.append("%s.%s argument order" % (name, member))
+            elif inspect.isfunction(obj) and obj.__module__.startswith("toppra"):
+                seen.add(name)
+                pr, pt = params(obj), params(mine)
+                if pr is not None and pt is not None and pt[:len(pr)] != pr:
+                    problems.append("%s(%s) vs (%s)" % (name, ", ".join(pr), ", ".join(pt)))
+    assert len(seen) >= 25, sorted(seen)
+    assert not problems, problems
